@@ -1,0 +1,109 @@
+"""PPO algorithm on the device rollout store (xt/algorithm/ppo/ppo.py:30-95)."""
+import ctypes as C
+import logging
+
+import numpy as np
+import torch
+
+from ..capi import check
+from ..engine import _ptr, stream_ptr
+from ..registry import Registers, import_config
+from .base import Algorithm
+
+GAMMA, LAM = 0.99, 0.95   # xt/agent/ppo/default_config.py:2-3 (the agent imports them by value)
+
+
+@Registers.algorithm
+class PPO(Algorithm):
+    """Accumulates trajectories straight into HBM (pinned staging + async H2D per trajectory) instead
+    of python lists + np.concatenate, then runs the fused minibatch-SGD loop.
+
+    ``prepare_data`` accepts the reference trajectory dict (xt/agent/ppo/ppo.py:99-106: cur_state,
+    action, logp, adv, old_value, target_value) and also the *raw* form (value[T+1], reward, done
+    instead of adv/target_value): then GAE (agent/ppo/ppo.py:77-106) runs on the device."""
+
+    def __init__(self, model_info, alg_config, **kwargs):
+        import_config(globals(), alg_config)
+        super().__init__(alg_name=kwargs.get("name") or "ppo", model_info=model_info["actor"], alg_config=alg_config)
+        self._init_train_list()
+        self.async_flag = False
+        self.sign_clip_reward = bool(alg_config.get("sign_clip_reward", False))
+        if model_info.get("finetune_weight"):
+            self.actor.load_model(model_info["finetune_weight"], by_name=True)
+            logging.info("load finetune weight: %s", model_info["finetune_weight"])
+
+    def _init_train_list(self):
+        self._count = 0           # samples staged so far
+        self._raw_segments = []   # (offset, length) of trajectories that still need device GAE
+        self._raw = None
+
+    # -- data path ---------------------------------------------------------------------------
+    def _stage(self, dst, arr, np_dtype):
+        """Copy one host array into device tensor `dst` through a pinned bounce buffer."""
+        a = np.ascontiguousarray(arr, dtype=np_dtype).reshape(dst.shape)
+        t = torch.from_numpy(a)
+        dst.copy_(t.pin_memory() if a.nbytes >= (1 << 20) else t, non_blocking=True)
+
+    def prepare_data(self, train_data, **kwargs):
+        ro = self.actor.rollout
+        obs = train_data["cur_state"]
+        n = len(obs)
+        ro.n = self._count
+        ro.reserve(self._count + n)
+        sl = slice(self._count, self._count + n)
+        obs_np = np.uint8 if self.actor.input_dtype == "uint8" else np.float32
+        self._stage(ro.obs[sl], np.asarray(obs), obs_np)
+        self._stage(ro.action[sl], train_data["action"], np.int32)
+        self._stage(ro.old_logp[sl], train_data["logp"], np.float32)
+        if "adv" in train_data:
+            self._stage(ro.adv[sl], train_data["adv"], np.float32)
+            self._stage(ro.old_v[sl], train_data["old_value"], np.float32)
+            self._stage(ro.target_v[sl], train_data["target_value"], np.float32)
+        else:
+            dev = ro.obs.device
+            val = torch.from_numpy(np.ascontiguousarray(train_data["value"], np.float32).reshape(-1)).to(dev)
+            rew = torch.from_numpy(np.ascontiguousarray(train_data["reward"], np.float32).reshape(-1)).to(dev)
+            don = torch.from_numpy(np.ascontiguousarray(train_data["done"], np.bool_).reshape(-1).view(np.uint8)).to(dev)
+            if val.numel() != n + 1:
+                raise ValueError("raw trajectory needs value[T+1] (bootstrap appended), got %d for T=%d" % (val.numel(), n))
+            self._raw_segments.append((self._count, n, val, rew, don))
+        self._count += n
+        ro.n = self._count
+
+    def _device_gae(self):
+        ro = self.actor.rollout
+        lib = self.actor.net.lib
+        segs = self._raw_segments
+        if not segs:
+            return
+        same = len({s[1] for s in segs}) == 1 and all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(len(segs) - 1))
+        if same and len(segs) > 1:   # one batched launch over [E, T]
+            t = segs[0][1]
+            off = segs[0][0]
+            val = torch.cat([s[2] for s in segs]); rew = torch.cat([s[3] for s in segs]); don = torch.cat([s[4] for s in segs])
+            check(lib.xtb_gae(_ptr(val), _ptr(rew), _ptr(don), len(segs), t, GAMMA, LAM, int(self.sign_clip_reward),
+                              _ptr(ro.adv[off:]), _ptr(ro.old_v[off:]), _ptr(ro.target_v[off:]), stream_ptr()))
+        else:
+            for off, t, val, rew, don in segs:
+                check(lib.xtb_gae(_ptr(val), _ptr(rew), _ptr(don), 1, t, GAMMA, LAM, int(self.sign_clip_reward),
+                                  _ptr(ro.adv[off:]), _ptr(ro.old_v[off:]), _ptr(ro.target_v[off:]), stream_ptr()))
+        torch.cuda.current_stream().synchronize()   # keep the staged inputs alive until consumed
+        self._raw_segments = []
+
+    def train(self, **kwargs):
+        """xt/algorithm/ppo/ppo.py:64-77."""
+        if self._count == 0:
+            raise ValueError("need at least one array to concatenate")   # np.concatenate([]) in the reference
+        self._device_gae()
+        loss = self.actor.train_device(self._count)
+        self._init_train_list()
+        return loss
+
+    def predict(self, state):
+        """xt/algorithm/ppo/ppo.py:87-95."""
+        if not isinstance(state, (list, tuple)):
+            state = state.reshape((1,) + state.shape)
+        else:
+            state = list(map(lambda x: x.reshape((1,) + x.shape), state))
+            state = np.vstack(state)
+        return self.actor.predict(state)

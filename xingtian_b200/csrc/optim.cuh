@@ -1,0 +1,87 @@
+// optim.cuh -- fused clip + Adam over one flat fp32 parameter bucket (HBM bound, 28 B/param).
+//   tf.train.AdamOptimizer + tf.clip_by_global_norm : xt/model/ppo/ppo.py:97-102,
+//                                                     xt/model/impala/impala_cnn_opt.py:198-217
+//   keras Adam(clipnorm)                            : xt/model/dqn/dqn_cnn.py:60
+// Three launches per step: sqnorm (per-segment sum of squares, one atomic per block), prep
+// (1 thread: clip scales, lr_t, beta powers, re-zero accumulators), adam (elementwise update).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xtb {
+
+constexpr int OPT_CHUNK = 4096;   // elements per block
+constexpr int OPT_THREADS = 256;
+
+struct AdamState {          // lives in device memory
+  float beta1_pow, beta2_pow, lr_t, grad_norm;
+};
+
+__global__ void __launch_bounds__(OPT_THREADS)
+sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ blk_seg,
+              const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
+              double* __restrict__ norm_sq) {
+  const float* p = g + blk_beg[blockIdx.x];
+  int n = blk_len[blockIdx.x];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += OPT_THREADS) { float v = p[i]; s = fmaf(v, v, s); }
+  __shared__ float red[OPT_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) atomicAdd(norm_sq + blk_seg[blockIdx.x], (double)t);
+  }
+}
+
+__global__ void adam_prep_kernel(AdamState* st, double* norm_sq, float* seg_scale, int n_seg,
+                                 int clip_mode, float clip, float grad_scale, float lr, float beta1,
+                                 float beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double tot = 0.0;
+  for (int s = 0; s < n_seg; s++) tot += norm_sq[s];
+  float gs = fabsf(grad_scale);
+  float gnorm = (float)sqrt(tot) * gs;
+  st->grad_norm = gnorm;
+  if (clip_mode == 1) {
+    float sc = clip / fmaxf(gnorm, clip);
+    for (int s = 0; s < n_seg; s++) seg_scale[s] = sc * grad_scale;
+  } else if (clip_mode == 2) {
+    for (int s = 0; s < n_seg; s++) {
+      float n = (float)sqrt(norm_sq[s]) * gs;
+      seg_scale[s] = (n > clip ? clip / n : 1.f) * grad_scale;
+    }
+  } else {
+    for (int s = 0; s < n_seg; s++) seg_scale[s] = grad_scale;
+  }
+  for (int s = 0; s < n_seg; s++) norm_sq[s] = 0.0;
+  float b1p = st->beta1_pow * beta1, b2p = st->beta2_pow * beta2;
+  st->beta1_pow = b1p; st->beta2_pow = b2p;
+  st->lr_t = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+}
+
+__global__ void __launch_bounds__(OPT_THREADS)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, const int* __restrict__ blk_seg,
+            const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
+            const float* __restrict__ seg_scale, const AdamState* __restrict__ st, float beta1,
+            float beta2, float eps) {
+  long long beg = blk_beg[blockIdx.x];
+  int n = blk_len[blockIdx.x];
+  float sc = seg_scale[blk_seg[blockIdx.x]];
+  float lr_t = st->lr_t;
+  for (int i = threadIdx.x; i < n; i += OPT_THREADS) {
+    long long j = beg + i;
+    float gg = g[j] * sc;
+    float mm = beta1 * m[j] + (1.f - beta1) * gg;
+    float vv = beta2 * v[j] + (1.f - beta2) * gg * gg;
+    m[j] = mm; v[j] = vv;
+    p[j] -= lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+
+}  // namespace xtb

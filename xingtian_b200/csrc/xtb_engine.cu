@@ -1,0 +1,691 @@
+// xtb_engine.cu -- C-ABI implementation (see include/xtb200.h).
+#include "../../include/xtb200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "gemm_f32.cuh"
+#include "optim.cuh"
+#include "rl_kernels.cuh"
+
+using namespace xtb;
+
+// ------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(x)                                                                          \
+  do {                                                                                       \
+    cudaError_t e_ = (x);                                                                    \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(XTB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+  } while (0)
+#define LAUNCH_CHECK()                                                                       \
+  do {                                                                                       \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+    cudaError_t e_ = cudaPeekAtLastError();                                                  \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(XTB_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int xtb_version(void) { return XTB_VERSION; }
+extern "C" const char* xtb_last_error(void) { return g_err.c_str(); }
+extern "C" long long xtb_launch_count(void) { return g_launches.load(); }
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------
+// network
+// ------------------------------------------------------------------------------------------
+struct LayerPlan {
+  xtb_layer_desc d;
+  ConvGeom g{};          // conv only
+  int in_size = 0;       // floats per sample of the source tensor
+  int out_size = 0;
+  int K = 0, N = 0;      // weight matrix [K,N]
+  long long w_off = 0, b_off = 0;
+  int src_act = 0;       // activation of the producing layer of the source tensor
+  // device tables (conv)
+  int* koff = nullptr; int* kyx = nullptr;            // forward / wgrad, indexed by k=(ky,kx,ci)
+  int* dkyx = nullptr; int* dco = nullptr; int* wk = nullptr;  // dgrad, indexed by k=(ky,kx,co)
+  int Kd = 0;            // KH*KW*Cout
+  int sshift = 0;
+  bool pad = false;
+};
+
+struct xtb_net {
+  xtb_net_desc desc;
+  int max_batch = 0;
+  std::vector<LayerPlan> L;
+  std::vector<int> tsize;       // per tensor floats/sample (0 = obs)
+  long long n_params = 0;
+  size_t ws_bytes = 0;
+  std::vector<size_t> out_off, gout_off;  // byte offsets in workspace per tensor
+  float* params = nullptr; float* grads = nullptr; char* ws = nullptr;
+};
+
+static int same_pad(int size, int k, int s, int* out, int* before) {
+  int o = (size + s - 1) / s;
+  int total = (o - 1) * s + k - size;
+  if (total < 0) total = 0;
+  *out = o; *before = total / 2;
+  return 0;
+}
+
+extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net** out) {
+  if (!desc || !out || max_batch <= 0) return fail(XTB_ERR_ARG, "xtb_net_create: null/invalid argument");
+  if (desc->n_layers <= 0 || desc->n_layers > XTB_MAX_LAYERS) return fail(XTB_ERR_ARG, "n_layers out of range");
+  auto* net = new xtb_net();
+  net->desc = *desc;
+  net->max_batch = max_batch;
+  struct Shape { int h, w, c; };
+  std::vector<Shape> shp(desc->n_layers + 1);
+  std::vector<int> tact(desc->n_layers + 1, 0);
+  shp[0] = {desc->in_h, desc->in_w, desc->in_c};
+  net->tsize.resize(desc->n_layers + 1);
+  net->tsize[0] = desc->in_h * desc->in_w * desc->in_c;
+  long long off = 0;
+  for (int i = 0; i < desc->n_layers; i++) {
+    LayerPlan lp;
+    lp.d = desc->layers[i];
+    const auto& d = lp.d;
+    if (d.src < 0 || d.src > i) { delete net; return fail(XTB_ERR_ARG, "layer %d: bad src %d", i, d.src); }
+    Shape is = shp[d.src];
+    lp.in_size = is.h * is.w * is.c;
+    lp.src_act = tact[d.src];
+    if (d.kind == XTB_CONV) {
+      if (d.stride != 1 && d.stride != 2 && d.stride != 4) { delete net; return fail(XTB_ERR_ARG, "layer %d: stride must be 1,2,4", i); }
+      ConvGeom& g = lp.g;
+      g.H = is.h; g.W = is.w; g.C = is.c; g.KH = g.KW = d.k; g.S = d.stride; g.Cout = d.cout;
+      if (d.pad_same) {
+        same_pad(g.H, d.k, d.stride, &g.OH, &g.padT);
+        same_pad(g.W, d.k, d.stride, &g.OW, &g.padL);
+        lp.pad = true;
+      } else {
+        g.OH = (g.H - d.k) / d.stride + 1; g.OW = (g.W - d.k) / d.stride + 1; g.padT = g.padL = 0;
+      }
+      if (g.OH <= 0 || g.OW <= 0) { delete net; return fail(XTB_ERR_ARG, "layer %d: empty conv output", i); }
+      g.K = d.k * d.k * g.C; g.P = g.OH * g.OW;
+      lp.K = g.K; lp.N = d.cout; lp.Kd = d.k * d.k * d.cout;
+      lp.sshift = d.stride == 1 ? 0 : (d.stride == 2 ? 1 : 2);
+      shp[i + 1] = {g.OH, g.OW, d.cout};
+      // tables
+      std::vector<int> koff(g.K), kyx(g.K), dkyx(lp.Kd), dco(lp.Kd), wk(lp.Kd);
+      for (int ky = 0; ky < d.k; ky++)
+        for (int kx = 0; kx < d.k; kx++) {
+          for (int ci = 0; ci < g.C; ci++) {
+            int k = (ky * d.k + kx) * g.C + ci;
+            koff[k] = (ky * g.W + kx) * g.C + ci;
+            kyx[k] = pack_yx(ky, kx);
+          }
+          for (int co = 0; co < d.cout; co++) {
+            int k = (ky * d.k + kx) * d.cout + co;
+            dkyx[k] = pack_yx(ky, kx);
+            dco[k] = co;
+            wk[k] = (ky * d.k + kx) * g.C * d.cout + co;
+          }
+        }
+      auto up = [&](int** dst, const std::vector<int>& v) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, v.size() * sizeof(int));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
+      };
+      cudaError_t e;
+      if ((e = up(&lp.koff, koff)) != cudaSuccess || (e = up(&lp.kyx, kyx)) != cudaSuccess ||
+          (e = up(&lp.dkyx, dkyx)) != cudaSuccess || (e = up(&lp.dco, dco)) != cudaSuccess ||
+          (e = up(&lp.wk, wk)) != cudaSuccess) {
+        delete net;
+        return fail(XTB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
+      }
+    } else if (d.kind == XTB_DENSE) {
+      lp.K = lp.in_size; lp.N = d.cout;
+      shp[i + 1] = {1, 1, d.cout};
+    } else {
+      delete net;
+      return fail(XTB_ERR_ARG, "layer %d: unknown kind %d", i, d.kind);
+    }
+    if (lp.N <= 0) { delete net; return fail(XTB_ERR_ARG, "layer %d: zero outputs", i); }
+    tact[i + 1] = d.act;
+    lp.out_size = shp[i + 1].h * shp[i + 1].w * shp[i + 1].c;
+    net->tsize[i + 1] = lp.out_size;
+    lp.w_off = off; off += (long long)lp.K * lp.N;
+    lp.b_off = off; off += lp.N;
+    net->L.push_back(lp);
+  }
+  net->n_params = off;
+  // workspace
+  size_t w = 0;
+  net->out_off.assign(desc->n_layers + 1, 0);
+  net->gout_off.assign(desc->n_layers + 1, 0);
+  for (int t = 1; t <= desc->n_layers; t++) {
+    size_t bytes = align_up((size_t)max_batch * net->tsize[t] * sizeof(float), 256);
+    net->out_off[t] = w; w += bytes;
+    net->gout_off[t] = w; w += bytes;
+  }
+  net->ws_bytes = w;
+  *out = net;
+  return XTB_OK;
+}
+
+extern "C" void xtb_net_destroy(xtb_net* net) {
+  if (!net) return;
+  for (auto& lp : net->L) {
+    cudaFree(lp.koff); cudaFree(lp.kyx); cudaFree(lp.dkyx); cudaFree(lp.dco); cudaFree(lp.wk);
+  }
+  delete net;
+}
+
+extern "C" long long xtb_net_param_count(const xtb_net* net) { return net ? net->n_params : -1; }
+
+extern "C" int xtb_net_layer_params(const xtb_net* net, int layer, long long* kernel_off, long long* bias_off,
+                                    int* k_rows, int* n_cols) {
+  if (!net || layer < 0 || layer >= (int)net->L.size()) return fail(XTB_ERR_ARG, "bad layer index");
+  const auto& lp = net->L[layer];
+  if (kernel_off) *kernel_off = lp.w_off;
+  if (bias_off) *bias_off = lp.b_off;
+  if (k_rows) *k_rows = lp.K;
+  if (n_cols) *n_cols = lp.N;
+  return XTB_OK;
+}
+
+extern "C" int xtb_net_tensor_size(const xtb_net* net, int t) {
+  if (!net || t < 0 || t >= (int)net->tsize.size()) return -1;
+  return net->tsize[t];
+}
+
+extern "C" size_t xtb_net_workspace_bytes(const xtb_net* net) { return net ? net->ws_bytes : 0; }
+
+extern "C" int xtb_net_bind(xtb_net* net, float* params, float* grads, void* workspace, size_t workspace_bytes) {
+  if (!net || !params || !workspace) return fail(XTB_ERR_ARG, "xtb_net_bind: null pointer");
+  if (workspace_bytes < net->ws_bytes) return fail(XTB_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, net->ws_bytes);
+  net->params = params; net->grads = grads; net->ws = (char*)workspace;
+  return XTB_OK;
+}
+
+extern "C" float* xtb_net_tensor(xtb_net* net, int t) {
+  if (!net || !net->ws || t < 1 || t >= (int)net->tsize.size()) return nullptr;
+  return (float*)(net->ws + net->out_off[t]);
+}
+extern "C" float* xtb_net_tensor_grad(xtb_net* net, int t) {
+  if (!net || !net->ws || t < 1 || t >= (int)net->tsize.size()) return nullptr;
+  return (float*)(net->ws + net->gout_off[t]);
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM dispatch
+// ------------------------------------------------------------------------------------------
+static const int kSMs = 148;
+
+template <int BM, int BN, int TM, int TN, class AL, class BL, class EP>
+static void launch_cfg(const AL& al, const BL& bl, const EP& ep, int M, int N, int K, int ksplit, cudaStream_t st) {
+  constexpr int BK = 16;
+  int kc = (K + ksplit - 1) / ksplit;
+  kc = (kc + BK - 1) / BK * BK;
+  int ks = (K + kc - 1) / kc;
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, ks);
+  gemm_f32_kernel<BM, BN, BK, TM, TN, AL, BL, EP><<<grid, (BM / TM) * (BN / TN), 0, st>>>(al, bl, ep, M, N, K, kc);
+}
+
+// split_ok: epilogue is atomic-accumulating so K may be partitioned over gridDim.z
+template <class AL, class BL, class EP>
+static void launch_gemm(const AL& al, const BL& bl, const EP& ep, int M, int N, int K, bool split_ok, cudaStream_t st) {
+  auto ctas = [&](int bm, int bn) { return (long long)((M + bm - 1) / bm) * ((N + bn - 1) / bn); };
+  int ksplit = 1;
+  if (N <= 32) {
+    long long c = ctas(128, 32);
+    if (c >= kSMs || split_ok) {
+      if (split_ok) { ksplit = (int)((2 * kSMs + c - 1) / c); int mx = (K + 63) / 64; if (ksplit > mx) ksplit = mx; if (ksplit < 1) ksplit = 1; }
+      launch_cfg<128, 32, 4, 4>(al, bl, ep, M, N, K, ksplit, st);
+      return;
+    }
+    launch_cfg<32, 32, 2, 2>(al, bl, ep, M, N, K, 1, st);
+    return;
+  }
+  long long c = ctas(64, 64);
+  if (c >= kSMs || split_ok) {
+    if (split_ok) { ksplit = (int)((2 * kSMs + c - 1) / c); int mx = (K + 63) / 64; if (ksplit > mx) ksplit = mx; if (ksplit < 1) ksplit = 1; }
+    launch_cfg<64, 64, 4, 4>(al, bl, ep, M, N, K, ksplit, st);
+    return;
+  }
+  launch_cfg<32, 32, 2, 2>(al, bl, ep, M, N, K, 1, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward / backward
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static void conv_fwd(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
+                     float alpha, float* out, int B, cudaStream_t st) {
+  int M = B * lp.g.P;
+  BRowMajor bl{w, lp.N};
+  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N};
+  if (lp.pad) { AIm2col<T, true> al{x, idx, lp.g, lp.koff, lp.kyx}; launch_gemm(al, bl, ep, M, lp.N, lp.K, false, st); }
+  else { AIm2col<T, false> al{x, idx, lp.g, lp.koff, lp.kyx}; launch_gemm(al, bl, ep, M, lp.N, lp.K, false, st); }
+}
+template <typename T>
+static void dense_fwd(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
+                      float alpha, float* out, int B, cudaStream_t st) {
+  ADense<T> al{x, idx, lp.K};
+  BRowMajor bl{w, lp.N};
+  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N};
+  launch_gemm(al, bl, ep, B, lp.N, lp.K, false, st);
+}
+template <typename T>
+static void conv_wgrad(const LayerPlan& lp, const T* x, const int32_t* idx, const float* dy, float alpha,
+                       float* dw, int B, cudaStream_t st) {
+  int Mr = B * lp.g.P;
+  BRowMajor bl{dy, lp.N};
+  EpiAtomic ep{dw, alpha, lp.N};
+  // rows 0..K-1 scaled by alpha (input decode scale); the bias row (K) must not be scaled:
+  // handled by launching it as part of the same GEMM only when alpha == 1, else separately.
+  if (lp.pad) { AIm2colT<T, true> al{x, idx, lp.g, lp.koff, lp.kyx, Mr}; launch_gemm(al, bl, ep, lp.K + (alpha == 1.f ? 1 : 0), lp.N, Mr, true, st); }
+  else { AIm2colT<T, false> al{x, idx, lp.g, lp.koff, lp.kyx, Mr}; launch_gemm(al, bl, ep, lp.K + (alpha == 1.f ? 1 : 0), lp.N, Mr, true, st); }
+}
+template <typename T>
+static void dense_wgrad(const LayerPlan& lp, const T* x, const int32_t* idx, const float* dy, float alpha,
+                        float* dw, int B, cudaStream_t st) {
+  ADenseT<T> al{x, idx, lp.K, lp.K};
+  BRowMajor bl{dy, lp.N};
+  EpiAtomic ep{dw, alpha, lp.N};
+  launch_gemm(al, bl, ep, lp.K + (alpha == 1.f ? 1 : 0), lp.N, B, true, st);
+}
+
+// bias gradient alone (used when the input scale alpha != 1 so the ones-row trick cannot share
+// the epilogue scale): db[n] = sum_m dy[m,n]
+__global__ void colsum_kernel(const float* __restrict__ dy, int M, int N, float* __restrict__ db) {
+  int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  int r0 = blockIdx.y * 1024 + (threadIdx.x >> 5);
+  float s = 0.f;
+  if (n < N)
+    for (int m = r0; m < min(M, (int)(blockIdx.y + 1) * 1024); m += 8) s += dy[(long long)m * N + n];
+  __shared__ float red[8][33];
+  red[threadIdx.x >> 5][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (threadIdx.x < 32 && n < N) {
+    float t = 0.f;
+    for (int i = 0; i < 8; i++) t += red[i][threadIdx.x];
+    atomicAdd(db + n, t);
+  }
+}
+
+extern "C" int xtb_net_forward(xtb_net* net, const float* params, const void* obs, const int32_t* gather_idx,
+                               int batch, void* stream) {
+  if (!net || !net->ws) return fail(XTB_ERR_STATE, "xtb_net_forward: net not bound");
+  if (batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "batch %d out of range (max %d)", batch, net->max_batch);
+  if (!obs) return fail(XTB_ERR_ARG, "obs is null");
+  const float* P = params ? params : net->params;
+  cudaStream_t st = S(stream);
+  for (size_t i = 0; i < net->L.size(); i++) {
+    const LayerPlan& lp = net->L[i];
+    float* out = (float*)(net->ws + net->out_off[i + 1]);
+    const float* w = P + lp.w_off;
+    const float* b = P + lp.b_off;
+    if (lp.d.src == 0) {
+      if (net->desc.input_u8) {
+        if (lp.d.kind == XTB_CONV) conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+        else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+      } else {
+        if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+        else dense_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+      }
+    } else {
+      const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
+      if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
+      else dense_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
+    }
+    LAUNCH_CHECK();
+  }
+  return XTB_OK;
+}
+
+extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
+                                const int32_t* head_tensors, int n_heads, void* stream) {
+  if (!net || !net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_net_backward: net not bound (grads required)");
+  if (batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "batch out of range");
+  cudaStream_t st = S(stream);
+  const int nl = (int)net->L.size();
+  std::vector<char> has_grad(nl + 1, 0), written(nl + 1, 0);
+  for (int h = 0; h < n_heads; h++) {
+    int t = head_tensors[h];
+    if (t < 1 || t > nl) return fail(XTB_ERR_ARG, "bad head tensor %d", t);
+    has_grad[t] = 1; written[t] = 1;
+  }
+  CUDA_TRY(cudaMemsetAsync(net->grads, 0, net->n_params * sizeof(float), st));
+  for (int i = nl - 1; i >= 0; i--) {
+    const LayerPlan& lp = net->L[i];
+    int t = i + 1;
+    if (!has_grad[t]) continue;   // tensor does not influence the loss
+    const float* dy = (const float*)(net->ws + net->gout_off[t]);
+    float* dw = net->grads + lp.w_off;
+    float* db = net->grads + lp.b_off;
+    // ---- weight + bias gradient
+    if (lp.d.src == 0) {
+      float alpha = net->desc.scale;
+      if (net->desc.input_u8) {
+        if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
+        else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
+      } else {
+        if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
+        else dense_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
+      }
+      LAUNCH_CHECK();
+      if (alpha != 1.f) {
+        int M = lp.d.kind == XTB_CONV ? batch * lp.g.P : batch;
+        dim3 grid((lp.N + 31) / 32, (M + 1023) / 1024);
+        colsum_kernel<<<grid, 256, 0, st>>>(dy, M, lp.N, db);
+        LAUNCH_CHECK();
+      }
+    } else {
+      const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
+      if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
+      else dense_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
+      LAUNCH_CHECK();
+      // ---- data gradient into the source tensor
+      int s = lp.d.src;
+      float* gsrc = (float*)(net->ws + net->gout_off[s]);
+      const float* xsrc = x;
+      const float* w = net->params + lp.w_off;
+      int acc = written[s] ? 1 : 0;
+      if (lp.d.kind == XTB_CONV) {
+        ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
+        BConvDgrad bl{w, lp.wk, lp.N};
+        EpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc};
+        launch_gemm(al, bl, ep, batch * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
+      } else {
+        ADense<float> al{dy, nullptr, lp.N};
+        BTransposed bl{w, lp.N};
+        EpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc};
+        launch_gemm(al, bl, ep, batch, lp.K, lp.N, false, st);
+      }
+      LAUNCH_CHECK();
+      written[s] = 1; has_grad[s] = 1;
+    }
+  }
+  return XTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// heads, GAE, losses
+// ------------------------------------------------------------------------------------------
+extern "C" int xtb_categorical_sample(const float* logits, int batch, int adim, const float* uniforms,
+                                      uint64_t seed, uint64_t offset, int32_t* action, float* logp, void* stream) {
+  if (!logits || !action || !logp || batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_categorical_sample: bad argument");
+  sample_kernel<<<(batch + 127) / 128, 128, 0, S(stream)>>>(logits, batch, adim, uniforms, seed, offset, action, logp);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+extern "C" int xtb_argmax(const float* q, int batch, int adim, int32_t* action, void* stream) {
+  if (!q || !action || batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_argmax: bad argument");
+  argmax_kernel<<<(batch + 127) / 128, 128, 0, S(stream)>>>(q, batch, adim, action);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+extern "C" int xtb_gae(const float* value, const float* reward, const uint8_t* done, int n_env, int n_step,
+                       float gamma, float lam, int sign_clip, float* adv, float* old_value, float* target_value,
+                       void* stream) {
+  if (!value || !reward || !done || !adv || !old_value || !target_value) return fail(XTB_ERR_ARG, "xtb_gae: null pointer");
+  if (n_env == 0 || n_step == 0) return XTB_OK;   // empty rollout: nothing to do
+  if (n_env < 0 || n_step < 0) return fail(XTB_ERR_ARG, "xtb_gae: negative size");
+  int threads = 128;  // 4 envs per block
+  int blocks = (n_env * 32 + threads - 1) / threads;
+  gae_kernel<<<blocks, threads, 0, S(stream)>>>(value, reward, done, n_env, n_step, gamma, lam, sign_clip, adv,
+                                                old_value, target_value);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+extern "C" int xtb_ppo_loss_grad(const float* logits, const float* v, const int32_t* gather_idx,
+                                 const int32_t* action, const float* old_logp, const float* adv,
+                                 const float* old_v, const float* target_v, int batch, int adim,
+                                 const xtb_ppo_hyper* hp, float inv_count, float* dlogits, float* dv,
+                                 float* loss_out, void* stream) {
+  if (!logits || !v || !action || !old_logp || !adv || !old_v || !target_v || !hp || !dlogits || !dv || !loss_out)
+    return fail(XTB_ERR_ARG, "xtb_ppo_loss_grad: null pointer");
+  if (batch <= 0 || adim <= 0 || adim > MAX_ADIM) return fail(XTB_ERR_ARG, "xtb_ppo_loss_grad: batch/adim out of range");
+  PpoHyperDev h{hp->clip_ratio, hp->ent_coef, hp->vf_clip, hp->critic_coef};
+  ppo_loss_kernel<<<(batch + 127) / 128, 128, 0, S(stream)>>>(logits, v, gather_idx, action, old_logp, adv, old_v,
+                                                              target_v, batch, adim, h, inv_count, dlogits, dv, loss_out);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+extern "C" int xtb_vtrace_loss_grad(const float* tp_logits, const float* baseline, const float* bp_logits,
+                                    const int32_t* action, const uint8_t* done, const float* reward,
+                                    int n_traj, int step_len, int adim, float gamma, float* dlogits,
+                                    float* dbaseline, float* vs_out, float* pg_adv_out, float* loss_out,
+                                    void* stream) {
+  if (!tp_logits || !baseline || !bp_logits || !action || !done || !reward || !dlogits || !dbaseline || !loss_out)
+    return fail(XTB_ERR_ARG, "xtb_vtrace_loss_grad: null pointer");
+  if (n_traj <= 0 || step_len < 2 || adim <= 0 || adim > MAX_ADIM) return fail(XTB_ERR_ARG, "xtb_vtrace_loss_grad: bad sizes");
+  int threads = 128;
+  int blocks = (n_traj * 32 + threads - 1) / threads;
+  vtrace_kernel<<<blocks, threads, 0, S(stream)>>>(tp_logits, baseline, bp_logits, action, done, reward, n_traj,
+                                                   step_len, adim, gamma, dlogits, dbaseline, vs_out, pg_adv_out, loss_out);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+extern "C" int xtb_dqn_loss_grad(const float* q, const float* q_next_target, const float* q_next_online,
+                                 const int32_t* action, const float* reward, const uint8_t* done, int batch,
+                                 int adim, float gamma, float inv_count, float* dq, float* y_out,
+                                 float* loss_out, void* stream) {
+  if (!q || !q_next_target || !action || !reward || !done || !dq || !loss_out) return fail(XTB_ERR_ARG, "xtb_dqn_loss_grad: null pointer");
+  if (batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_dqn_loss_grad: bad sizes");
+  dqn_loss_kernel<<<(batch + 127) / 128, 128, 0, S(stream)>>>(q, q_next_target, q_next_online, action, reward, done,
+                                                              batch, adim, gamma, inv_count, dq, y_out, loss_out);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+extern "C" int xtb_mse_loss_grad(const float* q, const float* y, int batch, int adim, float inv_count, float* dq,
+                                 float* loss_out, void* stream) {
+  if (!q || !y || !dq || !loss_out || batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_mse_loss_grad: bad argument");
+  long long n = (long long)batch * adim;
+  mse_loss_kernel<<<(unsigned)((n + 127) / 128), 128, 0, S(stream)>>>(q, y, n, inv_count, dq, loss_out);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// optimiser
+// ------------------------------------------------------------------------------------------
+struct xtb_adam {
+  long long count = 0;
+  float lr, beta1, beta2, eps, clip;
+  int clip_mode = 0, n_seg = 0, n_blk = 0;
+  float *m = nullptr, *v = nullptr;
+  int* blk_seg = nullptr; long long* blk_beg = nullptr; int* blk_len = nullptr;
+  double* norm_sq = nullptr; float* seg_scale = nullptr; AdamState* st = nullptr;
+};
+
+extern "C" int xtb_adam_create(long long count, float lr, float beta1, float beta2, float eps, int clip_mode,
+                               float clip, const long long* seg_offsets, int n_seg, float* m, float* v,
+                               xtb_adam** out) {
+  if (count <= 0 || !m || !v || !out) return fail(XTB_ERR_ARG, "xtb_adam_create: bad argument");
+  std::vector<long long> seg;
+  if (clip_mode == XTB_CLIP_PER_TENSOR) {
+    if (!seg_offsets || n_seg <= 0) return fail(XTB_ERR_ARG, "per-tensor clip needs segment offsets");
+    seg.assign(seg_offsets, seg_offsets + n_seg + 1);
+    if (seg.front() != 0 || seg.back() != count) return fail(XTB_ERR_ARG, "segment offsets must span [0,count]");
+  } else {
+    seg = {0, count};
+  }
+  auto* o = new xtb_adam();
+  o->count = count; o->lr = lr; o->beta1 = beta1; o->beta2 = beta2; o->eps = eps; o->clip = clip;
+  o->clip_mode = clip_mode; o->n_seg = (int)seg.size() - 1; o->m = m; o->v = v;
+  std::vector<int> bseg, blen; std::vector<long long> bbeg;
+  for (int s = 0; s < o->n_seg; s++)
+    for (long long b = seg[s]; b < seg[s + 1]; b += OPT_CHUNK) {
+      bseg.push_back(s); bbeg.push_back(b); blen.push_back((int)std::min<long long>(OPT_CHUNK, seg[s + 1] - b));
+    }
+  o->n_blk = (int)bseg.size();
+  AdamState init{1.f, 1.f, 0.f, 0.f};
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  chk(cudaMalloc(&o->blk_seg, o->n_blk * sizeof(int)));
+  chk(cudaMalloc(&o->blk_beg, o->n_blk * sizeof(long long)));
+  chk(cudaMalloc(&o->blk_len, o->n_blk * sizeof(int)));
+  chk(cudaMalloc(&o->norm_sq, o->n_seg * sizeof(double)));
+  chk(cudaMalloc(&o->seg_scale, o->n_seg * sizeof(float)));
+  chk(cudaMalloc(&o->st, sizeof(AdamState)));
+  if (e == cudaSuccess) {
+    chk(cudaMemcpy(o->blk_seg, bseg.data(), o->n_blk * sizeof(int), cudaMemcpyHostToDevice));
+    chk(cudaMemcpy(o->blk_beg, bbeg.data(), o->n_blk * sizeof(long long), cudaMemcpyHostToDevice));
+    chk(cudaMemcpy(o->blk_len, blen.data(), o->n_blk * sizeof(int), cudaMemcpyHostToDevice));
+    chk(cudaMemset(o->norm_sq, 0, o->n_seg * sizeof(double)));
+    chk(cudaMemcpy(o->st, &init, sizeof init, cudaMemcpyHostToDevice));
+    chk(cudaMemset(m, 0, count * sizeof(float)));
+    chk(cudaMemset(v, 0, count * sizeof(float)));
+  }
+  if (e != cudaSuccess) { xtb_adam_destroy(o); return fail(XTB_ERR_CUDA, "xtb_adam_create: %s", cudaGetErrorString(e)); }
+  *out = o;
+  return XTB_OK;
+}
+
+extern "C" void xtb_adam_destroy(xtb_adam* o) {
+  if (!o) return;
+  cudaFree(o->blk_seg); cudaFree(o->blk_beg); cudaFree(o->blk_len);
+  cudaFree(o->norm_sq); cudaFree(o->seg_scale); cudaFree(o->st);
+  delete o;
+}
+
+extern "C" int xtb_adam_step(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream) {
+  if (!o || !params || !grads) return fail(XTB_ERR_ARG, "xtb_adam_step: null pointer");
+  cudaStream_t st = S(stream);
+  sqnorm_kernel<<<o->n_blk, OPT_THREADS, 0, st>>>(grads, o->blk_seg, o->blk_beg, o->blk_len, o->norm_sq);
+  LAUNCH_CHECK();
+  adam_prep_kernel<<<1, 32, 0, st>>>(o->st, o->norm_sq, o->seg_scale, o->n_seg, o->clip_mode, o->clip, grad_scale,
+                                     o->lr, o->beta1, o->beta2);
+  LAUNCH_CHECK();
+  adam_kernel<<<o->n_blk, OPT_THREADS, 0, st>>>(params, grads, o->m, o->v, o->blk_seg, o->blk_beg, o->blk_len,
+                                                o->seg_scale, o->st, o->beta1, o->beta2, o->eps);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+extern "C" const float* xtb_adam_grad_norm(const xtb_adam* o) { return o ? &o->st->grad_norm : nullptr; }
+extern "C" int xtb_adam_set_lr(xtb_adam* o, float lr) {
+  if (!o) return fail(XTB_ERR_ARG, "null optimiser");
+  o->lr = lr;
+  return XTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused PPO learner loop
+// ------------------------------------------------------------------------------------------
+struct GraphKey {
+  const void* net; const void* opt; const void* obs; const void* perm; const void* loss; int n, b, e;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(net, opt, obs, perm, loss, n, b, e) < std::tie(o.net, o.opt, o.obs, o.perm, o.loss, o.n, o.b, o.e);
+  }
+};
+struct GraphVal { cudaGraphExec_t exec; long long kernels; };
+static std::map<GraphKey, GraphVal> g_graphs;
+
+static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* ro, int N, int B, int E,
+                            const int32_t* perm, const xtb_ppo_hyper* hp, int pi_t, int v_t,
+                            float* loss_per_step, void* stream) {
+  int steps_per_epoch = (N + B - 1) / B;
+  CUDA_TRY(cudaMemsetAsync(loss_per_step, 0, sizeof(float) * E * steps_per_epoch, S(stream)));
+  int heads[2] = {pi_t, v_t};
+  int adim = net->tsize[pi_t];
+  int step = 0;
+  for (int e = 0; e < E; e++) {
+    for (int s0 = 0; s0 < N; s0 += B, step++) {
+      int mb = std::min(B, N - s0);
+      const int32_t* idx = perm + (long long)e * N + s0;
+      int rc = xtb_net_forward(net, nullptr, ro->obs, idx, mb, stream);
+      if (rc) return rc;
+      rc = xtb_ppo_loss_grad(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), idx, ro->action, ro->old_logp,
+                             ro->adv, ro->old_v, ro->target_v, mb, adim, hp, 1.f / mb,
+                             xtb_net_tensor_grad(net, pi_t), xtb_net_tensor_grad(net, v_t), loss_per_step + step, stream);
+      if (rc) return rc;
+      rc = xtb_net_backward(net, ro->obs, idx, mb, heads, 2, stream);
+      if (rc) return rc;
+      rc = xtb_adam_step(opt, net->params, net->grads, 1.f, stream);
+      if (rc) return rc;
+    }
+  }
+  return XTB_OK;
+}
+
+extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* ro, int n_sample,
+                             int batch_size, int n_epoch, const int32_t* perm, const xtb_ppo_hyper* hp,
+                             int pi_tensor, int v_tensor, float* loss_per_step, int use_graph, void* stream) {
+  if (!net || !opt || !ro || !perm || !hp || !loss_per_step) return fail(XTB_ERR_ARG, "xtb_ppo_train: null pointer");
+  if (!net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_ppo_train: net not bound");
+  if (n_sample <= 0 || batch_size <= 0 || n_epoch <= 0) return fail(XTB_ERR_ARG, "xtb_ppo_train: bad sizes");
+  if (std::min(batch_size, n_sample) > net->max_batch) return fail(XTB_ERR_ARG, "batch_size exceeds net max_batch");
+  int nl = (int)net->L.size();
+  if (pi_tensor < 1 || pi_tensor > nl || v_tensor < 1 || v_tensor > nl || net->tsize[v_tensor] != 1)
+    return fail(XTB_ERR_ARG, "xtb_ppo_train: bad head tensors");
+  if (!use_graph || !stream)
+    return ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, stream);
+  GraphKey key{net, opt, ro->obs, perm, loss_per_step, n_sample, batch_size, n_epoch};
+  auto it = g_graphs.find(key);
+  if (it == g_graphs.end()) {
+    cudaStream_t st = S(stream);
+    long long before = g_launches.load();
+    CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    long long captured = g_launches.load() - before;
+    g_launches.store(before);   // captured, not launched yet
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    it = g_graphs.emplace(key, GraphVal{exec, captured}).first;
+  }
+  CUDA_TRY(cudaGraphLaunch(it->second.exec, S(stream)));
+  g_launches.fetch_add(it->second.kernels, std::memory_order_relaxed);
+  return XTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// staging helpers
+// ------------------------------------------------------------------------------------------
+extern "C" void* xtb_pinned_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail(XTB_ERR_NOMEM, "cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+  return p;
+}
+extern "C" void xtb_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" int xtb_copy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, S(stream)));
+  return XTB_OK;
+}
+extern "C" int xtb_copy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, S(stream)));
+  return XTB_OK;
+}
+extern "C" int xtb_stream_sync(void* stream) {
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));
+  return XTB_OK;
+}
