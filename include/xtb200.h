@@ -192,6 +192,19 @@ int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* ro, int n_
                   int batch_size, int n_epoch, const int32_t* perm, const xtb_ppo_hyper* hp,
                   int pi_tensor, int v_tensor, float* loss_per_step, int use_graph, void* stream);
 
+/* Data-parallel hook: called between backward and the optimiser with the flat
+ * gradient bucket; must SUM it over ranks on `stream` (e.g. ncclAllReduce).  Called once with
+ * grads == NULL before the loop: must return the world size.  While a hook is installed the
+ * loss/gradient scale becomes 1/(world*B_local) and CUDA-graph replay is disabled.
+ * Reference precedent: xt/framework/trainer.py:82-92 (shared-memory gradient averaging). */
+typedef int (*xtb_grad_hook)(void* user, float* grads, long long count, void* stream);
+int xtb_set_grad_hook(xtb_grad_hook hook, void* user);
+
+/* Launch one kernel of one layer alone (which: 0 forward, 1 weight gradient) on the tensors
+ * currently in the workspace -- measurement hook for bench.py's roofline object. */
+int xtb_net_bench_layer(xtb_net* net, int layer, int which, const void* obs, const int32_t* gather_idx,
+                        int batch, void* stream);
+
 /* ---- host <-> device staging (pinned ring replacing feed_dict copies) --- */
 void* xtb_pinned_alloc(size_t bytes);
 void xtb_pinned_free(void* p);

@@ -29,11 +29,23 @@ def xb():
     return dict(pkg=pkg, capi=capi, engine=engine, lib=capi.lib())
 
 
+_KEEP = []   # device tensors must outlive the raw pointers handed to the C-ABI
+
+
+@pytest.fixture(autouse=True)
+def _keepalive():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 def dev(a, dtype=None):
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:
         t = t.to(dtype)
-    return t.cuda()
+    t = t.cuda()
+    _KEEP.append(t)
+    return t
 
 
 # ------------------------------------------------------------------------------------------- GAE

@@ -36,6 +36,7 @@ class PpoRollout(C.Structure):
 
 
 _P = C.c_void_p
+GRAD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p)
 _SIGS = {
     "xtb_version": (C.c_int, []),
     "xtb_last_error": (C.c_char_p, []),
@@ -70,6 +71,8 @@ _SIGS = {
     "xtb_adam_set_lr": (C.c_int, [_P, C.c_float]),
     "xtb_ppo_train": (C.c_int, [_P, _P, C.POINTER(PpoRollout), C.c_int, C.c_int, C.c_int, _P,
                                 C.POINTER(PpoHyper), C.c_int, C.c_int, _P, C.c_int, _P]),
+    "xtb_set_grad_hook": (C.c_int, [GRAD_HOOK, _P]),
+    "xtb_net_bench_layer": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "xtb_pinned_alloc": (_P, [C.c_size_t]),
     "xtb_pinned_free": (None, [_P]),
     "xtb_copy_h2d": (C.c_int, [_P, _P, C.c_size_t, _P]),

@@ -425,6 +425,47 @@ extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* ga
   return XTB_OK;
 }
 
+// Launch ONE kernel of one layer (0 = forward, 1 = weight gradient, 2 = data gradient) on the tensors
+// currently in the workspace: lets bench.py time the dominant kernel alone with CUDA events.
+extern "C" int xtb_net_bench_layer(xtb_net* net, int layer, int which, const void* obs, const int32_t* gather_idx,
+                                   int batch, void* stream) {
+  if (!net || !net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_net_bench_layer: net not bound");
+  if (layer < 0 || layer >= (int)net->L.size() || batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "bad layer/batch");
+  const LayerPlan& lp = net->L[layer];
+  cudaStream_t st = S(stream);
+  float* out = (float*)(net->ws + net->out_off[layer + 1]);
+  const float* dy = (const float*)(net->ws + net->gout_off[layer + 1]);
+  const float* w = net->params + lp.w_off;
+  const float* b = net->params + lp.b_off;
+  bool from_obs = lp.d.src == 0;
+  const float* x = from_obs ? nullptr : (const float*)(net->ws + net->out_off[lp.d.src]);
+  float alpha = from_obs ? net->desc.scale : 1.f;
+  if (which == 0) {
+    if (from_obs && net->desc.input_u8) {
+      if (lp.d.kind == XTB_CONV) conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, alpha, out, batch, st);
+      else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, alpha, out, batch, st);
+    } else {
+      const float* xin = from_obs ? (const float*)obs : x;
+      if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, xin, from_obs ? gather_idx : nullptr, w, b, alpha, out, batch, st);
+      else dense_fwd<float>(lp, xin, from_obs ? gather_idx : nullptr, w, b, alpha, out, batch, st);
+    }
+  } else if (which == 1) {
+    float* dw = net->grads + lp.w_off;
+    if (from_obs && net->desc.input_u8) {
+      if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
+      else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
+    } else {
+      const float* xin = from_obs ? (const float*)obs : x;
+      if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, xin, from_obs ? gather_idx : nullptr, dy, alpha, dw, batch, st);
+      else dense_wgrad<float>(lp, xin, from_obs ? gather_idx : nullptr, dy, alpha, dw, batch, st);
+    }
+  } else {
+    return fail(XTB_ERR_ARG, "xtb_net_bench_layer: which must be 0 or 1");
+  }
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // heads, GAE, losses
 // ------------------------------------------------------------------------------------------
@@ -605,9 +646,16 @@ struct GraphKey {
 struct GraphVal { cudaGraphExec_t exec; long long kernels; };
 static std::map<GraphKey, GraphVal> g_graphs;
 
+static xtb_grad_hook g_grad_hook = nullptr;
+static void* g_grad_hook_user = nullptr;
+extern "C" int xtb_set_grad_hook(xtb_grad_hook hook, void* user) {
+  g_grad_hook = hook; g_grad_hook_user = user;
+  return XTB_OK;
+}
+
 static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* ro, int N, int B, int E,
                             const int32_t* perm, const xtb_ppo_hyper* hp, int pi_t, int v_t,
-                            float* loss_per_step, void* stream) {
+                            float* loss_per_step, float inv_world, void* stream) {
   int steps_per_epoch = (N + B - 1) / B;
   CUDA_TRY(cudaMemsetAsync(loss_per_step, 0, sizeof(float) * E * steps_per_epoch, S(stream)));
   int heads[2] = {pi_t, v_t};
@@ -620,11 +668,15 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
       int rc = xtb_net_forward(net, nullptr, ro->obs, idx, mb, stream);
       if (rc) return rc;
       rc = xtb_ppo_loss_grad(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), idx, ro->action, ro->old_logp,
-                             ro->adv, ro->old_v, ro->target_v, mb, adim, hp, 1.f / mb,
+                             ro->adv, ro->old_v, ro->target_v, mb, adim, hp, inv_world / mb,
                              xtb_net_tensor_grad(net, pi_t), xtb_net_tensor_grad(net, v_t), loss_per_step + step, stream);
       if (rc) return rc;
       rc = xtb_net_backward(net, ro->obs, idx, mb, heads, 2, stream);
       if (rc) return rc;
+      if (g_grad_hook) {
+        rc = g_grad_hook(g_grad_hook_user, net->grads, net->n_params, stream);
+        if (rc) return fail(XTB_ERR_STATE, "gradient hook failed with %d", rc);
+      }
       rc = xtb_adam_step(opt, net->params, net->grads, 1.f, stream);
       if (rc) return rc;
     }
@@ -642,15 +694,22 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
   int nl = (int)net->L.size();
   if (pi_tensor < 1 || pi_tensor > nl || v_tensor < 1 || v_tensor > nl || net->tsize[v_tensor] != 1)
     return fail(XTB_ERR_ARG, "xtb_ppo_train: bad head tensors");
-  if (!use_graph || !stream)
-    return ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, stream);
+  float inv_world = 1.f;
+  if (g_grad_hook) {   // data-parallel: the hook sums gradients over ranks; every rank holds B/world samples
+    int world = 1;
+    int rc = g_grad_hook(g_grad_hook_user, nullptr, 0, nullptr);   // query: returns world size when grads == NULL
+    if (rc > 0) world = rc;
+    inv_world = 1.f / world;
+  }
+  if (!use_graph || !stream || g_grad_hook)
+    return ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, inv_world, stream);
   GraphKey key{net, opt, ro->obs, perm, loss_per_step, n_sample, batch_size, n_epoch};
   auto it = g_graphs.find(key);
   if (it == g_graphs.end()) {
     cudaStream_t st = S(stream);
     long long before = g_launches.load();
     CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, stream);
+    int rc = ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, 1.f, stream);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     long long captured = g_launches.load() - before;

@@ -209,3 +209,35 @@ class Adam(object):
         check(self.lib.xtb_copy_d2h(C.c_void_p(out.data_ptr()), C.c_void_p(p), 4, stream_ptr()))
         torch.cuda.current_stream().synchronize()
         return float(out[0])
+
+
+class GradAllReduce(object):
+    """Data-parallel learner: one process per GPU, every rank holds the rollouts of its
+    own envs, gradients of the flat bucket are summed over ranks with NCCL between backward and the
+    optimiser (weights stay replicated because every rank applies the same clipped Adam update)."""
+
+    _active = None
+
+    def __init__(self, net, group=None):
+        import torch.distributed as dist
+        self.dist, self.group, self.net = dist, group, net
+        self.world = dist.get_world_size(group)
+
+        def hook(user, grads, count, stream):
+            try:
+                if not grads:
+                    return self.world
+                self.dist.all_reduce(self.net.grads, op=self.dist.ReduceOp.SUM, group=self.group)
+                return 0
+            except Exception:   # never unwind through C
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        self._cb = capi.GRAD_HOOK(hook)
+        check(capi.lib().xtb_set_grad_hook(self._cb, None))
+        GradAllReduce._active = self
+
+    def close(self):
+        check(capi.lib().xtb_set_grad_hook(C.cast(None, capi.GRAD_HOOK), None))
+        GradAllReduce._active = None

@@ -124,9 +124,9 @@ class PPO(XTModel):
             self._pred_bufs[batch] = b
         return b
 
-    def predict_device(self, obs_dev, batch, uniforms=None, out_action=None, out_logp=None):
-        """Batched inference on device-resident observations; returns device views
-        (action[B] i32, logp[B] f32, v[B,1] f32)."""
+    def predict_device(self, obs_dev, batch, uniforms=None, out_action=None, out_logp=None, idx=None):
+        """Batched inference on device-resident observations (row b = obs_dev[idx[b]] when idx is
+        given); returns device views (action[B] i32, logp[B] f32, v[B,1] f32)."""
         net = self.net
         done = 0
         bufs = self._pred_buffers(batch) if out_action is None else None
@@ -135,7 +135,10 @@ class PPO(XTModel):
         vout = torch.empty(batch, 1, dtype=torch.float32, device=self.device) if batch > net.max_batch else None
         while done < batch:
             mb = min(net.max_batch, batch - done)
-            net.forward(obs_dev[done:done + mb], mb)
+            if idx is None:
+                net.forward(obs_dev[done:done + mb], mb)
+            else:
+                net.forward(obs_dev, mb, idx=idx[done:done + mb])
             u = None if uniforms is None else uniforms[done:done + mb]
             check(net.lib.xtb_categorical_sample(_ptr(net.tensor("pi_latent")), mb, self.action_dim, _ptr(u),
                                                  C.c_uint64(self._sample_seed), C.c_uint64(self._sample_offset),
