@@ -205,6 +205,15 @@ int xtb_set_grad_hook(xtb_grad_hook hook, void* user);
 int xtb_net_bench_layer(xtb_net* net, int layer, int which, const void* obs, const int32_t* gather_idx,
                         int batch, void* stream);
 
+/* Kernel-path selection: 1 (default) = tcgen05 tensor-core kernels wherever the shape is covered,
+ * 0 = fp32 CUDA-core kernels only (also XTB_TC=0 in the environment).  For A/B parity tests. */
+int xtb_set_tc_mode(int mode);
+int xtb_get_tc_mode(void);
+/* Self-test of the tcgen05 GEMM core on plain fp32 matrices (sizes multiples of 8):
+ * mode 0: C = A[M,K] B[K,N]; mode 1: C = A[M,K] Bt[N,K]^T; mode 2: C = At[K,M]^T B[K,N]. */
+int xtb_tc_gemm_test(int mode, const float* a, const float* b, float* c, int M, int N, int K, int ksplit,
+                     void* stream);
+
 /* ---- host <-> device staging (pinned ring replacing feed_dict copies) --- */
 void* xtb_pinned_alloc(size_t bytes);
 void xtb_pinned_free(void* p);

@@ -249,10 +249,20 @@ def _arch_cases():
     }
 
 
-@pytest.mark.parametrize("case,B", [("ppo_cnn", 5), ("ppo_cnn", 64), ("ppo_cnn_sep", 9), ("ppo_mlp", 200), ("ppo_mlp_shared", 33),
-                                    ("impala_cnn", 6), ("dqn_cnn", 7), ("dqn_mlp", 32)])
-def test_network_forward_backward(xb, case, B):
-    """a1-a5: forward of every tensor and the full parameter gradient vs torch-CPU autograd."""
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "fp32"])
+def tc_mode(request, xb):
+    lib = xb["lib"]
+    old = lib.xtb_get_tc_mode()
+    lib.xtb_set_tc_mode(request.param)
+    yield request.param
+    lib.xtb_set_tc_mode(old)
+
+
+@pytest.mark.parametrize("case,B", [("ppo_cnn", 5), ("ppo_cnn", 64), ("ppo_cnn", 320), ("ppo_cnn_sep", 9), ("ppo_mlp", 200), ("ppo_mlp_shared", 33),
+                                    ("impala_cnn", 6), ("impala_cnn", 130), ("dqn_cnn", 7), ("dqn_cnn", 129), ("dqn_mlp", 32)])
+def test_network_forward_backward(xb, tc_mode, case, B):
+    """a1-a5: forward of every tensor and the full parameter gradient vs torch-CPU autograd, on the
+    tcgen05 path and on the fp32 CUDA-core path."""
     from xingtian_b200.engine import Net
     arch, nparam = _arch_cases()[case]
     w = orc.init_weights(arch, seed=11)

@@ -73,6 +73,9 @@ _SIGS = {
                                 C.POINTER(PpoHyper), C.c_int, C.c_int, _P, C.c_int, _P]),
     "xtb_set_grad_hook": (C.c_int, [GRAD_HOOK, _P]),
     "xtb_net_bench_layer": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "xtb_set_tc_mode": (C.c_int, [C.c_int]),
+    "xtb_get_tc_mode": (C.c_int, []),
+    "xtb_tc_gemm_test": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "xtb_pinned_alloc": (_P, [C.c_size_t]),
     "xtb_pinned_free": (None, [_P]),
     "xtb_copy_h2d": (C.c_int, [_P, _P, C.c_size_t, _P]),

@@ -1,0 +1,463 @@
+// gemm_tc.cuh -- tcgen05 (5th-gen tensor core) implicit-GEMM family for sm_100a.
+//
+//   D[128 x N] (fp32, TMEM) += A[128 x 16] * B[16 x N]   per tcgen05.mma.cta_group::1.kind::f16
+//
+// One warp-specialised kernel serves every conv / dense layer in forward, data-gradient and
+// weight-gradient form:
+//   warps 0-3 : producers.  Each operand tile is a 2-D array of 16-byte chunks [rows][chunks]
+//               gathered straight from the fp32 / uint8 tensors in global memory (im2col with
+//               the minibatch gather and uint8 decode folded in, transposed-conv gather, plain
+//               rows) and written to shared memory in the UMMA canonical no-swizzle layout.
+//               fp32 values are split on the fly into bf16 hi + bf16 lo ("bf16x3"): the tensor
+//               core computes hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM, which
+//               reproduces fp32 products to ~2^-17 -- the parity contract (1e-3) is met with
+//               margin while the math runs on tcgen05.  uint8 frames are exact in bf16 (no lo).
+//   warp 4    : allocates TMEM, issues the MMAs (one elected lane), tcgen05.commit -> mbarriers.
+//   warps 0-3 : epilogue after the K loop: tcgen05.ld (32 lanes x 16 columns per instruction),
+//               bias+activation / activation-gradient mask / split-K atomic accumulation.
+//
+// Shared-memory tile layout (both majors): addr(row, chunk) = chunk*ROWS*16 + row*16.
+//   K-major operand  (rows = M/N entity, chunks along K):  core matrix = 8 rows x 16 B contiguous,
+//       SBO (8-row group stride) = 128 B, LBO (stride between the two K chunks of one MMA) = ROWS*16.
+//   MN-major operand (rows = K entity, chunks along M/N): core matrix = 8 K-rows x 16 B contiguous,
+//       LBO (stride between 8-row K groups) = 128 B, SBO (stride between 16-byte MN chunks) = ROWS*16.
+// The same row-gather therefore feeds the forward GEMM (K-major) and the weight-gradient GEMM
+// (MN-major) without any transpose.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_f32.cuh"
+
+namespace xtb {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// bounded spin: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (SWIZZLE_NONE, sm_100 version bits)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version = 1 (Blackwell)
+  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+// instruction descriptor: bf16 x bf16 -> fp32, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// fp32 x8 -> bf16 hi (and residual lo) packed as 16-byte chunks
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void split8(const float v[8], uint4& hi, uint4& lo) {
+  float r[8];
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    __nv_bfloat16 b = __float2bfloat16_rn(v[i]);
+    r[i] = v[i] - __bfloat162float(b);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) { h[i] = pack_bf16(v[2 * i], v[2 * i + 1]); l[i] = pack_bf16(r[2 * i], r[2 * i + 1]); }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Row-gather sources.  A source is a logical 2-D array [n_rows][n_cols] whose rows are gathered
+// independently and whose columns come in contiguous groups of 8.
+//   struct Row;  void init_row(int row, Row&) const;  void load8(const Row&, int col, float v[8]) const;
+// load8 must return zeros for row >= n_rows (Row::valid == 0); the caller guards col < n_cols.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void zero8(float v[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = 0.f;
+}
+__device__ __forceinline__ void ld8(const float* p, float v[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld4(const float* p, float* v) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void ld4(const uint8_t* p, float* v) {
+  uchar4 a = *reinterpret_cast<const uchar4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void ld8(const uint8_t* p, float v[8]) {
+  uint2 a = *reinterpret_cast<const uint2*>(p);
+  v[0] = a.x & 0xff; v[1] = (a.x >> 8) & 0xff; v[2] = (a.x >> 16) & 0xff; v[3] = a.x >> 24;
+  v[4] = a.y & 0xff; v[5] = (a.y >> 8) & 0xff; v[6] = (a.y >> 16) & 0xff; v[7] = a.y >> 24;
+}
+
+// plain rows: X[row(m)*ld + col], optional row gather.  Requires ld % 4 == 0 (fp32) / ld % 8 == 0 (u8).
+template <typename T>
+struct SrcDense {
+  const T* x; const int32_t* idx; int ld; int n_rows;
+  struct Row { long long base; int valid; };
+  __device__ __forceinline__ void init_row(int m, Row& r) const {
+    r.valid = m < n_rows;
+    r.base = r.valid ? (long long)(idx ? idx[m] : m) * ld : 0;
+  }
+  __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
+    if (!r.valid) { zero8(v); return; }
+    ld8(x + r.base + col, v);
+  }
+};
+
+// im2col rows: row = output position (b,oy,ox) [sample gathered through idx], col = (ky,kx,ci).
+// C % 8 == 0: a chunk is 8 channels of one pixel;  C == 4: a chunk is 2 horizontally adjacent pixels.
+template <typename T, bool PAD>
+struct SrcIm2col {
+  const T* x; const int32_t* idx; ConvGeom g; const int* koff; const int* kyx; int n_rows;
+  struct Row { long long base; int iy0, ix0, valid; };
+  __device__ __forceinline__ void init_row(int m, Row& r) const {
+    r.valid = m < n_rows;
+    if (!r.valid) { r.base = 0; r.iy0 = r.ix0 = 0; return; }
+    int b = m / g.P; int p = m - b * g.P; int oy = p / g.OW; int ox = p - oy * g.OW;
+    long long sb = idx ? idx[b] : b;
+    r.iy0 = oy * g.S - g.padT; r.ix0 = ox * g.S - g.padL;
+    r.base = ((sb * g.H + r.iy0) * g.W + r.ix0) * g.C;
+  }
+  __device__ __forceinline__ bool ok(const Row& r, int k) const {
+    if (!PAD) return true;
+    int yx = kyx[k];
+    int iy = r.iy0 + (yx >> 16), ix = r.ix0 + (yx & 0xffff);
+    return (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
+  }
+  __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
+    if (!r.valid) { zero8(v); return; }
+    if (g.C == 4) {
+      if (ok(r, col)) ld4(x + r.base + koff[col], v); else { v[0] = v[1] = v[2] = v[3] = 0.f; }
+      if (ok(r, col + 4)) ld4(x + r.base + koff[col + 4], v + 4); else { v[4] = v[5] = v[6] = v[7] = 0.f; }
+    } else {
+      if (ok(r, col)) ld8(x + r.base + koff[col], v); else zero8(v);
+    }
+  }
+};
+
+// transposed-conv gather: row = input position (b,iy,ix), col = (ky,kx,co); value = dY[b,oy,ox,co]
+// with oy=(iy+padT-ky)/S when divisible and in range.  Cout % 8 == 0.
+struct SrcDgrad {
+  const float* dy; ConvGeom g; const int* dkyx; const int* dco; int sshift; int n_rows;
+  struct Row { long long base; int iy0, ix0, valid; };
+  __device__ __forceinline__ void init_row(int m, Row& r) const {
+    r.valid = m < n_rows;
+    if (!r.valid) { r.base = 0; r.iy0 = r.ix0 = 0; return; }
+    int HW = g.H * g.W; int b = m / HW; int p = m - b * HW; int iy = p / g.W; int ix = p - iy * g.W;
+    r.base = (long long)b * g.P * g.Cout; r.iy0 = iy + g.padT; r.ix0 = ix + g.padL;
+  }
+  __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
+    if (!r.valid) { zero8(v); return; }
+    int yx = dkyx[col];
+    int ty = r.iy0 - (yx >> 16), tx = r.ix0 - (yx & 0xffff);
+    int mask = g.S - 1;
+    if (ty < 0 || tx < 0 || (ty & mask) || (tx & mask)) { zero8(v); return; }
+    int oy = ty >> sshift, ox = tx >> sshift;
+    if (oy >= g.OH || ox >= g.OW) { zero8(v); return; }
+    ld8(dy + r.base + (long long)(oy * g.OW + ox) * g.Cout + dco[col], v);
+  }
+};
+
+// conv weights for the data gradient: row = ci, col = (ky,kx,co) -> W[ky,kx,ci,co]
+struct SrcWDgrad {
+  const float* w; const int* wk; int Cin, Cout; int n_rows;
+  struct Row { int ci, valid; };
+  __device__ __forceinline__ void init_row(int m, Row& r) const { r.valid = m < n_rows; r.ci = m; }
+  __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
+    if (!r.valid) { zero8(v); return; }
+    ld8(w + wk[col] + (long long)r.ci * Cout, v);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Epilogues: store16(row m, first column n, 16 accumulators)
+// ------------------------------------------------------------------------------------------
+struct TcEpiBiasAct {
+  float* out; const float* bias; float alpha; int act; int ld; int M, N;
+  __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
+    if (m >= M) return;
+    float* o = out + (long long)m * ld + n0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      if (n0 + j + 3 < N) {
+        float4 r;
+        r.x = act_apply(act, alpha * v[j] + bias[n0 + j]);
+        r.y = act_apply(act, alpha * v[j + 1] + bias[n0 + j + 1]);
+        r.z = act_apply(act, alpha * v[j + 2] + bias[n0 + j + 2]);
+        r.w = act_apply(act, alpha * v[j + 3] + bias[n0 + j + 3]);
+        *reinterpret_cast<float4*>(o + j) = r;
+      } else {
+        for (int t = 0; t < 4; t++)
+          if (n0 + j + t < N) o[j + t] = act_apply(act, alpha * v[j + t] + bias[n0 + j + t]);
+      }
+    }
+  }
+};
+struct TcEpiDgrad {
+  float* gout; const float* srcout; int act; int ld; int accumulate; int M, N;
+  __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
+    if (m >= M) return;
+    long long o = (long long)m * ld + n0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      if (n0 + j < N) {
+        float gq = v[j] * act_grad_from_out(act, srcout[o + j]);
+        gout[o + j] = accumulate ? gout[o + j] + gq : gq;
+      }
+    }
+  }
+};
+struct TcEpiStore {     // plain row-major store (self-test)
+  float* out; int ld; int M, N;
+  __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
+    if (m >= M) return;
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+      if (n0 + j < N) out[(long long)m * ld + n0 + j] = v[j];
+  }
+};
+struct TcEpiAtomic {
+  float* out; float alpha; int ld; int M, N;
+  __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
+    if (m >= M) return;
+    float* o = out + (long long)m * ld + n0;
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+      if (n0 + j < N) atomicAdd(o + j, alpha * v[j]);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// The kernel.
+//   A_MN / B_MN : operand is MN-major (its tile rows are the K entity) instead of K-major.
+//   KT          : reduction elements per pipeline stage (multiple of 16)
+//   NT          : N tile (16..256, multiple of 16) = UMMA N
+//   A_SPLIT / B_SPLIT : operand carries a bf16 residual (bf16x3); false = exact in bf16
+// grid = (ceil(Mext/128), ceil(Next/NT), ksplit);  block = 160 threads
+// ------------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 160;
+constexpr int TC_PRODUCERS = 128;
+
+template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT>
+struct TcCfg {
+  static constexpr int A_ROWS = A_MN ? KT : 128;
+  static constexpr int A_CHUNKS = A_MN ? 16 : KT / 8;
+  static constexpr int B_ROWS = B_MN ? KT : NT;
+  static constexpr int B_CHUNKS = B_MN ? NT / 8 : KT / 8;
+  static constexpr int A_BYTES = A_ROWS * A_CHUNKS * 16;
+  static constexpr int B_BYTES = B_ROWS * B_CHUNKS * 16;
+  static constexpr int STAGE_BYTES = A_BYTES * (A_SPLIT ? 2 : 1) + B_BYTES * (B_SPLIT ? 2 : 1);
+  static constexpr int STAGES = (STAGE_BYTES * 3 <= 96 * 1024) ? 3 : 2;
+  static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + 1024;
+  static constexpr int TMEM_COLS = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));
+};
+
+template <int ROWS, int CHUNKS, bool MN, bool SPLIT, class SRC>
+__device__ __forceinline__ void produce_tile(const SRC& src, uint8_t* hi, uint8_t* lo, int mn0, int k0,
+                                             int mn_ext, int k_end, int tid) {
+  // slot s -> (row = s % ROWS, chunk = s / ROWS); K-major: row is an MN entity (mn0+row), chunk along K
+  // (k0+8*chunk); MN-major: row is a K entity (k0+row), chunk along MN (mn0+8*chunk).
+  constexpr int SLOTS = ROWS * CHUNKS;
+  static_assert(SLOTS % TC_PRODUCERS == 0 || SLOTS < TC_PRODUCERS, "tile slots must tile the producer threads");
+  typename SRC::Row row;
+  int cur_row = -1;
+#pragma unroll 1
+  for (int s = tid; s < SLOTS; s += TC_PRODUCERS) {
+    int r = s % ROWS, c = s / ROWS;
+    int grow = MN ? k0 + r : mn0 + r;
+    int gcol = MN ? mn0 + 8 * c : k0 + 8 * c;
+    int row_lim = MN ? k_end : mn_ext;
+    int col_lim = MN ? mn_ext : k_end;
+    if (r != cur_row) {
+      // rows past the limit are initialised as invalid by clamping through n_rows inside the source;
+      // additionally mask rows past this CTA's k range (split-K) for MN-major operands
+      src.init_row(grow, row);
+      if (grow >= row_lim) row.valid = 0;
+      cur_row = r;
+    }
+    float v[8];
+    if (gcol < col_lim) src.load8(row, gcol, v); else zero8(v);
+    uint32_t off = (uint32_t)c * ROWS * 16 + (uint32_t)r * 16;
+    if (SPLIT) {
+      uint4 h, l;
+      split8(v, h, l);
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    } else {
+      uint4 h = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      *reinterpret_cast<uint4*>(hi + off) = h;
+    }
+  }
+}
+
+template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT, class ASRC, class BSRC, class EPI>
+__global__ void __launch_bounds__(TC_THREADS)
+tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, int k_chunk) {
+  using Cfg = TcCfg<NT, KT, A_MN, B_MN, A_SPLIT, B_SPLIT>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned carve-up
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * NT;
+  const int kbeg = blockIdx.z * k_chunk;
+  const int kend = min(k_ext, kbeg + k_chunk);
+  const int n_tiles = (kend - kbeg + KT - 1) / KT;
+
+  uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum = smem_u32(&bars[2 * STAGES]);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, TC_PRODUCERS); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 4) {
+    // ================= producers =================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = 0; t < n_tiles; t++) {
+      mbar_wait(empty0 + 8 * stage, phase ^ 1);
+      uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+      uint8_t* sa_lo = sa + Cfg::A_BYTES;
+      uint8_t* sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
+      uint8_t* sb_lo = sb + Cfg::B_BYTES;
+      int k0 = kbeg + t * KT;
+      produce_tile<Cfg::A_ROWS, Cfg::A_CHUNKS, A_MN, A_SPLIT>(asrc, sa, sa_lo, m0, k0, m_ext, kend, tid);
+      produce_tile<Cfg::B_ROWS, Cfg::B_CHUNKS, B_MN, B_SPLIT>(bsrc, sb, sb_lo, n0, k0, n_ext, kend, tid);
+      fence_proxy_async();
+      mbar_arrive(full0 + 8 * stage);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ================= epilogue =================
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int row = m0 + warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < NT; c += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + c, v);
+      if (n_tiles > 0) epi.store16(row, n0 + c, v);
+    }
+    tc_fence_before();
+  } else {
+    // ================= MMA issuer =================
+    constexpr uint32_t IDESC = make_idesc(NT, A_MN, B_MN);
+    // per-k-step descriptor geometry (bytes)
+    constexpr uint32_t A_LBO = A_MN ? 128 : Cfg::A_ROWS * 16, A_SBO = A_MN ? Cfg::A_ROWS * 16 : 128;
+    constexpr uint32_t B_LBO = B_MN ? 128 : Cfg::B_ROWS * 16, B_SBO = B_MN ? Cfg::B_ROWS * 16 : 128;
+    constexpr uint32_t A_KSTEP = A_MN ? 256 : 2 * Cfg::A_ROWS * 16;   // advance of one K=16 step
+    constexpr uint32_t B_KSTEP = B_MN ? 256 : 2 * Cfg::B_ROWS * 16;
+    int stage = 0; uint32_t phase = 0;
+    for (int t = 0; t < n_tiles; t++) {
+      mbar_wait(full0 + 8 * stage, phase);
+      tc_fence_after();
+      if (lane == 0) {
+        uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        uint32_t sa_lo = sa + Cfg::A_BYTES;
+        uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
+        uint32_t sb_lo = sb + Cfg::B_BYTES;
+#pragma unroll
+        for (int j = 0; j < KT / 16; j++) {
+          uint64_t ah = make_desc(sa + j * A_KSTEP, A_LBO, A_SBO);
+          uint64_t bh = make_desc(sb + j * B_KSTEP, B_LBO, B_SBO);
+          umma_bf16(tmem_base, ah, bh, IDESC, (t > 0 || j > 0) ? 1u : 0u);
+          if (B_SPLIT) umma_bf16(tmem_base, ah, make_desc(sb_lo + j * B_KSTEP, B_LBO, B_SBO), IDESC, 1u);
+          if (A_SPLIT) umma_bf16(tmem_base, make_desc(sa_lo + j * A_KSTEP, A_LBO, A_SBO), bh, IDESC, 1u);
+        }
+        umma_commit(empty0 + 8 * stage);          // frees the smem stage when these MMAs retire
+        if (t == n_tiles - 1) umma_commit(accum); // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (n_tiles == 0 && lane == 0) mbar_arrive(accum);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace xtb

@@ -16,6 +16,9 @@
 #include "gemm_f32.cuh"
 #include "optim.cuh"
 #include "rl_kernels.cuh"
+#include "tc_dispatch.cuh"
+#include <cstdlib>
+#include <type_traits>
 
 using namespace xtb;
 
@@ -114,6 +117,11 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
     Shape is = shp[d.src];
     lp.in_size = is.h * is.w * is.c;
     lp.src_act = tact[d.src];
+    if (d.kind == XTB_CONV && !d.pad_same && d.k == is.h && d.k == is.w) {
+      // a VALID conv whose window covers the whole map (ImpalaCnnOpt's 11x11) is a dense layer on the
+      // HWC-flattened input with the identical [kh*kw*cin, cout] weight matrix
+      lp.d.kind = XTB_DENSE;
+    }
     if (d.kind == XTB_CONV) {
       if (d.stride != 1 && d.stride != 2 && d.stride != 4) { delete net; return fail(XTB_ERR_ARG, "layer %d: stride must be 1,2,4", i); }
       ConvGeom& g = lp.g;
@@ -271,6 +279,148 @@ static void launch_gemm(const AL& al, const BL& bl, const EP& ep, int M, int N, 
   launch_cfg<32, 32, 2, 2>(al, bl, ep, M, N, K, 1, st);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 path (gemm_tc.cuh).  g_tc_mode: 1 = use tensor cores where the shape is covered,
+// 0 = fp32 CUDA-core kernels only (XTB_TC=0 in the environment, or xtb_set_tc_mode).
+// ------------------------------------------------------------------------------------------
+static int g_tc_mode = [] { const char* e = getenv("XTB_TC"); return e ? atoi(e) : 1; }();
+extern "C" int xtb_set_tc_mode(int mode) { g_tc_mode = mode; return XTB_OK; }
+extern "C" int xtb_get_tc_mode(void) { return g_tc_mode; }
+
+__global__ void bias_act_kernel(float* __restrict__ out, const float* __restrict__ bias, long long total, int N,
+                                float alpha, int act) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = act_apply(act, alpha * out[i] + bias[i % N]);
+}
+
+static bool tc_conv_ok(const LayerPlan& lp) {
+  return g_tc_mode && (lp.g.C == 4 || lp.g.C % 8 == 0) && lp.N % 8 == 0 && lp.N <= 64 && lp.K % 8 == 0;
+}
+static bool tc_dense_ok(const LayerPlan& lp) { return g_tc_mode && lp.K % 8 == 0 && lp.N % 8 == 0 && lp.K >= 64 && lp.N >= 16; }
+
+template <typename T, bool PAD>
+static cudaError_t tc_conv_fwd_t(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
+                                 float alpha, float* out, int B, cudaStream_t st) {
+  int M = B * lp.g.P;
+  tc::SrcIm2col<T, PAD> a{x, idx, lp.g, lp.koff, lp.kyx, M};
+  tc::SrcDense<float> bs{w, nullptr, lp.N, lp.K};
+  tc::TcEpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, M, lp.N};
+  constexpr bool AS = !std::is_same<T, uint8_t>::value;
+  if (lp.N <= 16) return tc::launch_tc<16, 64, false, true, AS, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+  if (lp.N <= 32) return tc::launch_tc<32, 64, false, true, AS, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+  return tc::launch_tc<64, 64, false, true, AS, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+}
+template <typename T>
+static cudaError_t tc_conv_fwd(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
+                               float alpha, float* out, int B, cudaStream_t st) {
+  return lp.pad ? tc_conv_fwd_t<T, true>(lp, x, idx, w, b, alpha, out, B, st)
+                : tc_conv_fwd_t<T, false>(lp, x, idx, w, b, alpha, out, B, st);
+}
+
+static cudaError_t tc_dense_fwd(const LayerPlan& lp, const float* x, const float* w, const float* b, float* out,
+                                int B, cudaStream_t st) {
+  tc::SrcDense<float> a{x, nullptr, lp.K, B};
+  tc::SrcDense<float> bs{w, nullptr, lp.N, lp.K};
+  int nt = lp.N <= 64 ? 64 : 256;
+  long long ctas = (long long)((B + 127) / 128) * ((lp.N + nt - 1) / nt);
+  int ks = lp.K >= 1024 ? tc::pick_ksplit(ctas, lp.K, 64, 48) : 1;
+  if (ks > 1) {   // split-K: atomics into a zeroed buffer, then bias + activation in place
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * lp.N * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    tc::TcEpiAtomic ep{out, 1.f, lp.N, B, lp.N};
+    e = nt == 64 ? tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, ks, st)
+                 : tc::launch_tc<256, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, ks, st);
+    if (e != cudaSuccess) return e;
+    long long total = (long long)B * lp.N;
+    bias_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, b, total, lp.N, 1.f, lp.d.act);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaPeekAtLastError();
+  }
+  tc::TcEpiBiasAct ep{out, b, 1.f, lp.d.act, lp.N, B, lp.N};
+  return nt == 64 ? tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, 1, st)
+                  : tc::launch_tc<256, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, 1, st);
+}
+
+template <typename T, bool PAD>
+static cudaError_t tc_conv_wgrad_t(const LayerPlan& lp, const T* x, const int32_t* idx, const float* dy, float alpha,
+                                   float* dw, int B, cudaStream_t st) {
+  int Mr = B * lp.g.P;
+  tc::SrcIm2col<T, PAD> a{x, idx, lp.g, lp.koff, lp.kyx, Mr};
+  tc::SrcDense<float> bs{dy, nullptr, lp.N, Mr};
+  tc::TcEpiAtomic ep{dw, alpha, lp.N, lp.K, lp.N};
+  constexpr bool AS = !std::is_same<T, uint8_t>::value;
+  long long ctas = (long long)((lp.K + 127) / 128);
+  int ks = tc::pick_ksplit(ctas, Mr, 64, 148);
+  if (lp.N <= 16) return tc::launch_tc<16, 64, true, true, AS, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
+  if (lp.N <= 32) return tc::launch_tc<32, 64, true, true, AS, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
+  return tc::launch_tc<64, 64, true, true, AS, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
+}
+template <typename T>
+static cudaError_t tc_conv_wgrad(const LayerPlan& lp, const T* x, const int32_t* idx, const float* dy, float alpha,
+                                 float* dw, int B, cudaStream_t st) {
+  return lp.pad ? tc_conv_wgrad_t<T, true>(lp, x, idx, dy, alpha, dw, B, st)
+                : tc_conv_wgrad_t<T, false>(lp, x, idx, dy, alpha, dw, B, st);
+}
+
+static cudaError_t tc_dense_wgrad(const LayerPlan& lp, const float* x, const float* dy, float* dw, int B, cudaStream_t st) {
+  tc::SrcDense<float> a{x, nullptr, lp.K, B};
+  tc::SrcDense<float> bs{dy, nullptr, lp.N, B};
+  tc::TcEpiAtomic ep{dw, 1.f, lp.N, lp.K, lp.N};
+  int nt = lp.N <= 64 ? 64 : 256;
+  long long ctas = (long long)((lp.K + 127) / 128) * ((lp.N + nt - 1) / nt);
+  int ks = tc::pick_ksplit(ctas, B, 64, 48);
+  return nt == 64 ? tc::launch_tc<64, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st)
+                  : tc::launch_tc<256, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st);
+}
+
+static cudaError_t tc_conv_dgrad(const LayerPlan& lp, const float* dy, const float* w, float* gsrc, const float* xsrc,
+                                 int acc, int B, cudaStream_t st) {
+  int M = B * lp.g.H * lp.g.W;
+  tc::SrcDgrad a{dy, lp.g, lp.dkyx, lp.dco, lp.sshift, M};
+  tc::SrcWDgrad bs{w, lp.wk, lp.g.C, lp.N, lp.g.C};
+  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc, M, lp.g.C};
+  if (lp.g.C <= 16) return tc::launch_tc<16, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
+  if (lp.g.C <= 32) return tc::launch_tc<32, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
+  return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
+}
+
+static cudaError_t tc_dense_dgrad(const LayerPlan& lp, const float* dy, const float* w, float* gsrc, const float* xsrc,
+                                  int acc, int B, cudaStream_t st) {
+  tc::SrcDense<float> a{dy, nullptr, lp.N, B};
+  tc::SrcDense<float> bs{w, nullptr, lp.N, lp.K};          // rows = kw (N' entity), cols = n (K')
+  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc, B, lp.K};
+  return lp.K <= 64 ? tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, B, lp.K, lp.N, 1, st)
+                    : tc::launch_tc<256, 64, false, false, true, true>(a, bs, ep, B, lp.K, lp.N, 1, st);
+}
+
+// Self-test of the three operand-major combinations on plain matrices (see tests/test_gpu_tc.py):
+//   mode 0: C[M,N] = A[M,K]   * B[K,N]      (A K-major, B MN-major : forward)
+//   mode 1: C[M,N] = A[M,K]   * Bt[N,K]^T   (both K-major         : data gradient)
+//   mode 2: C[M,N] = At[K,M]^T * B[K,N]     (both MN-major        : weight gradient)
+extern "C" int xtb_tc_gemm_test(int mode, const float* a, const float* b, float* c, int M, int N, int K, int ksplit,
+                                void* stream) {
+  if (!a || !b || !c || M <= 0 || N <= 0 || K <= 0) return fail(XTB_ERR_ARG, "xtb_tc_gemm_test: bad argument");
+  if (M % 8 || N % 8 || K % 8) return fail(XTB_ERR_ARG, "xtb_tc_gemm_test: sizes must be multiples of 8");
+  cudaStream_t st = S(stream);
+  cudaError_t e;
+  if (ksplit > 1) {
+    CUDA_TRY(cudaMemsetAsync(c, 0, (size_t)M * N * sizeof(float), st));
+    tc::TcEpiAtomic ep{c, 1.f, N, M, N};
+    if (mode == 0) { tc::SrcDense<float> as{a, nullptr, K, M}, bs{b, nullptr, N, K}; e = tc::launch_tc<64, 64, false, true, true, true>(as, bs, ep, M, N, K, ksplit, st); }
+    else if (mode == 1) { tc::SrcDense<float> as{a, nullptr, K, M}, bs{b, nullptr, K, N}; e = tc::launch_tc<64, 64, false, false, true, true>(as, bs, ep, M, N, K, ksplit, st); }
+    else { tc::SrcDense<float> as{a, nullptr, M, K}, bs{b, nullptr, N, K}; e = tc::launch_tc<64, 64, true, true, true, true>(as, bs, ep, M, N, K, ksplit, st); }
+  } else {
+    tc::TcEpiStore ep{c, N, M, N};
+    if (mode == 0) { tc::SrcDense<float> as{a, nullptr, K, M}, bs{b, nullptr, N, K}; e = tc::launch_tc<32, 64, false, true, true, true>(as, bs, ep, M, N, K, 1, st); }
+    else if (mode == 1) { tc::SrcDense<float> as{a, nullptr, K, M}, bs{b, nullptr, K, N}; e = tc::launch_tc<32, 64, false, false, true, true>(as, bs, ep, M, N, K, 1, st); }
+    else { tc::SrcDense<float> as{a, nullptr, M, K}, bs{b, nullptr, N, K}; e = tc::launch_tc<32, 64, true, true, true, true>(as, bs, ep, M, N, K, 1, st); }
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "tc gemm launch: %s", cudaGetErrorString(e));
+  return XTB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // forward / backward
 // ------------------------------------------------------------------------------------------
@@ -341,19 +491,30 @@ extern "C" int xtb_net_forward(xtb_net* net, const float* params, const void* ob
     float* out = (float*)(net->ws + net->out_off[i + 1]);
     const float* w = P + lp.w_off;
     const float* b = P + lp.b_off;
+    cudaError_t te = cudaSuccess;
     if (lp.d.src == 0) {
       if (net->desc.input_u8) {
-        if (lp.d.kind == XTB_CONV) conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
-        else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+        if (lp.d.kind == XTB_CONV) {
+          if (tc_conv_ok(lp)) te = tc_conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+          else conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+        } else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
       } else {
-        if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
-        else dense_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+        if (lp.d.kind == XTB_CONV) {
+          if (tc_conv_ok(lp)) te = tc_conv_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+          else conv_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
+        } else dense_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
       }
     } else {
       const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
-      if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
-      else dense_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
+      if (lp.d.kind == XTB_CONV) {
+        if (tc_conv_ok(lp)) te = tc_conv_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
+        else conv_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
+      } else {
+        if (tc_dense_ok(lp)) te = tc_dense_fwd(lp, x, w, b, out, batch, st);
+        else dense_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
+      }
     }
+    if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 forward launch (layer %zu): %s", i, cudaGetErrorString(te));
     LAUNCH_CHECK();
   }
   return XTB_OK;
@@ -382,15 +543,22 @@ extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* ga
     // ---- weight + bias gradient
     if (lp.d.src == 0) {
       float alpha = net->desc.scale;
+      cudaError_t te = cudaSuccess;
+      bool tc_w = lp.d.kind == XTB_CONV && tc_conv_ok(lp);
       if (net->desc.input_u8) {
-        if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
-        else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
+        if (lp.d.kind == XTB_CONV) {
+          if (tc_w) te = tc_conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
+          else conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
+        } else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
       } else {
-        if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
-        else dense_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
+        if (lp.d.kind == XTB_CONV) {
+          if (tc_w) te = tc_conv_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
+          else conv_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
+        } else dense_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
       }
+      if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 wgrad launch (layer %d): %s", i, cudaGetErrorString(te));
       LAUNCH_CHECK();
-      if (alpha != 1.f) {
+      if (alpha != 1.f || tc_w) {
         int M = lp.d.kind == XTB_CONV ? batch * lp.g.P : batch;
         dim3 grid((lp.N + 31) / 32, (M + 1023) / 1024);
         colsum_kernel<<<grid, 256, 0, st>>>(dy, M, lp.N, db);
@@ -398,9 +566,23 @@ extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* ga
       }
     } else {
       const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
-      if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
-      else dense_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
+      cudaError_t te = cudaSuccess;
+      bool tc_w = lp.d.kind == XTB_CONV ? tc_conv_ok(lp) : tc_dense_ok(lp);
+      if (lp.d.kind == XTB_CONV) {
+        if (tc_w) te = tc_conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
+        else conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
+      } else {
+        if (tc_w) te = tc_dense_wgrad(lp, x, dy, dw, batch, st);
+        else dense_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
+      }
+      if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 wgrad launch (layer %d): %s", i, cudaGetErrorString(te));
       LAUNCH_CHECK();
+      if (tc_w) {   // the tensor-core wgrad has no ones-row: bias gradient = column sums of dY
+        int Mb = lp.d.kind == XTB_CONV ? batch * lp.g.P : batch;
+        dim3 gridb((lp.N + 31) / 32, (Mb + 1023) / 1024);
+        colsum_kernel<<<gridb, 256, 0, st>>>(dy, Mb, lp.N, db);
+        LAUNCH_CHECK();
+      }
       // ---- data gradient into the source tensor
       int s = lp.d.src;
       float* gsrc = (float*)(net->ws + net->gout_off[s]);
@@ -408,16 +590,25 @@ extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* ga
       const float* w = net->params + lp.w_off;
       int acc = written[s] ? 1 : 0;
       if (lp.d.kind == XTB_CONV) {
-        ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
-        BConvDgrad bl{w, lp.wk, lp.N};
-        EpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc};
-        launch_gemm(al, bl, ep, batch * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
+        if (g_tc_mode && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.N % 8 == 0) {
+          te = tc_conv_dgrad(lp, dy, w, gsrc, xsrc, acc, batch, st);
+        } else {
+          ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
+          BConvDgrad bl{w, lp.wk, lp.N};
+          EpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc};
+          launch_gemm(al, bl, ep, batch * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
+        }
       } else {
-        ADense<float> al{dy, nullptr, lp.N};
-        BTransposed bl{w, lp.N};
-        EpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc};
-        launch_gemm(al, bl, ep, batch, lp.K, lp.N, false, st);
+        if (tc_dense_ok(lp)) {
+          te = tc_dense_dgrad(lp, dy, w, gsrc, xsrc, acc, batch, st);
+        } else {
+          ADense<float> al{dy, nullptr, lp.N};
+          BTransposed bl{w, lp.N};
+          EpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc};
+          launch_gemm(al, bl, ep, batch, lp.K, lp.N, false, st);
+        }
       }
+      if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 dgrad launch (layer %d): %s", i, cudaGetErrorString(te));
       LAUNCH_CHECK();
       written[s] = 1; has_grad[s] = 1;
     }
