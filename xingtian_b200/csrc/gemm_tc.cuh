@@ -176,10 +176,11 @@ struct SrcDense {
 };
 
 // im2col rows: row = output position (b,oy,ox) [sample gathered through idx], col = (ky,kx,ci).
-// C % 8 == 0: a chunk is 8 channels of one pixel;  C == 4: a chunk is 2 horizontally adjacent pixels.
+// C is a power of two (cshift = log2 C).  C >= 8: a chunk is 8 channels of one pixel;  C == 4: a chunk is
+// 2 horizontally adjacent taps.  Column -> (ky,kx,ci) is decoded arithmetically (no table loads).
 template <typename T, bool PAD>
 struct SrcIm2col {
-  const T* x; const int32_t* idx; ConvGeom g; const int* koff; const int* kyx; int n_rows;
+  const T* x; const int32_t* idx; ConvGeom g; int cshift; int n_rows;
   struct Row { long long base; int iy0, ix0, valid; };
   __device__ __forceinline__ void init_row(int m, Row& r) const {
     r.valid = m < n_rows;
@@ -189,27 +190,33 @@ struct SrcIm2col {
     r.iy0 = oy * g.S - g.padT; r.ix0 = ox * g.S - g.padL;
     r.base = ((sb * g.H + r.iy0) * g.W + r.ix0) * g.C;
   }
-  __device__ __forceinline__ bool ok(const Row& r, int k) const {
-    if (!PAD) return true;
-    int yx = kyx[k];
-    int iy = r.iy0 + (yx >> 16), ix = r.ix0 + (yx & 0xffff);
-    return (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
+  // offset of tap `tap` (= ky*KW+kx) relative to the patch origin, or -1 when it falls in the padding
+  __device__ __forceinline__ int tap_off(const Row& r, int tap) const {
+    int ky = tap / g.KW, kx = tap - ky * g.KW;
+    if (PAD) {
+      int iy = r.iy0 + ky, ix = r.ix0 + kx;
+      if ((unsigned)iy >= (unsigned)g.H || (unsigned)ix >= (unsigned)g.W) return -1;
+    }
+    return (ky * g.W + kx) << cshift;
   }
   __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
     if (!r.valid) { zero8(v); return; }
+    int tap = col >> cshift, ci = col & (g.C - 1);
     if (g.C == 4) {
-      if (ok(r, col)) ld4(x + r.base + koff[col], v); else { v[0] = v[1] = v[2] = v[3] = 0.f; }
-      if (ok(r, col + 4)) ld4(x + r.base + koff[col + 4], v + 4); else { v[4] = v[5] = v[6] = v[7] = 0.f; }
+      int o0 = tap_off(r, tap), o1 = tap_off(r, tap + 1);
+      if (o0 >= 0) ld4(x + r.base + o0, v); else { v[0] = v[1] = v[2] = v[3] = 0.f; }
+      if (o1 >= 0) ld4(x + r.base + o1, v + 4); else { v[4] = v[5] = v[6] = v[7] = 0.f; }
     } else {
-      if (ok(r, col)) ld8(x + r.base + koff[col], v); else zero8(v);
+      int o = tap_off(r, tap);
+      if (o >= 0) ld8(x + r.base + o + ci, v); else zero8(v);
     }
   }
 };
 
 // transposed-conv gather: row = input position (b,iy,ix), col = (ky,kx,co); value = dY[b,oy,ox,co]
-// with oy=(iy+padT-ky)/S when divisible and in range.  Cout % 8 == 0.
+// with oy=(iy+padT-ky)/S when divisible and in range.  Cout is a power of two >= 8 (oshift = log2 Cout).
 struct SrcDgrad {
-  const float* dy; ConvGeom g; const int* dkyx; const int* dco; int sshift; int n_rows;
+  const float* dy; ConvGeom g; int oshift; int sshift; int n_rows;
   struct Row { long long base; int iy0, ix0, valid; };
   __device__ __forceinline__ void init_row(int m, Row& r) const {
     r.valid = m < n_rows;
@@ -219,24 +226,26 @@ struct SrcDgrad {
   }
   __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
     if (!r.valid) { zero8(v); return; }
-    int yx = dkyx[col];
-    int ty = r.iy0 - (yx >> 16), tx = r.ix0 - (yx & 0xffff);
+    int tap = col >> oshift, co = col & (g.Cout - 1);
+    int ky = tap / g.KW, kx = tap - ky * g.KW;
+    int ty = r.iy0 - ky, tx = r.ix0 - kx;
     int mask = g.S - 1;
     if (ty < 0 || tx < 0 || (ty & mask) || (tx & mask)) { zero8(v); return; }
     int oy = ty >> sshift, ox = tx >> sshift;
     if (oy >= g.OH || ox >= g.OW) { zero8(v); return; }
-    ld8(dy + r.base + (long long)(oy * g.OW + ox) * g.Cout + dco[col], v);
+    ld8(dy + r.base + (((long long)(oy * g.OW + ox)) << oshift) + co, v);
   }
 };
 
 // conv weights for the data gradient: row = ci, col = (ky,kx,co) -> W[ky,kx,ci,co]
 struct SrcWDgrad {
-  const float* w; const int* wk; int Cin, Cout; int n_rows;
+  const float* w; int Cin, Cout, oshift; int n_rows;
   struct Row { int ci, valid; };
   __device__ __forceinline__ void init_row(int m, Row& r) const { r.valid = m < n_rows; r.ci = m; }
   __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
     if (!r.valid) { zero8(v); return; }
-    ld8(w + wk[col] + (long long)r.ci * Cout, v);
+    int tap = col >> oshift, co = col & (Cout - 1);
+    ld8(w + ((long long)(tap * Cin + r.ci) << oshift) + co, v);
   }
 };
 
@@ -328,35 +337,48 @@ __device__ __forceinline__ void produce_tile(const SRC& src, uint8_t* hi, uint8_
                                              int mn_ext, int k_end, int tid) {
   // slot s -> (row = s % ROWS, chunk = s / ROWS); K-major: row is an MN entity (mn0+row), chunk along K
   // (k0+8*chunk); MN-major: row is a K entity (k0+row), chunk along MN (mn0+8*chunk).
+  // Loads of U slots are issued back to back before any conversion so that U independent global loads are
+  // in flight per thread (the gather is latency bound otherwise).
   constexpr int SLOTS = ROWS * CHUNKS;
-  static_assert(SLOTS % TC_PRODUCERS == 0 || SLOTS < TC_PRODUCERS, "tile slots must tile the producer threads");
+  static_assert(SLOTS % TC_PRODUCERS == 0, "tile slots must tile the producer threads");
+  constexpr int PER = SLOTS / TC_PRODUCERS;
+  constexpr int U = PER >= 8 ? 8 : PER;
+  static_assert(PER % U == 0, "slots per thread must be a multiple of the load batch");
+  const int row_lim = MN ? k_end : mn_ext;
+  const int col_lim = MN ? mn_ext : k_end;
   typename SRC::Row row;
   int cur_row = -1;
 #pragma unroll 1
-  for (int s = tid; s < SLOTS; s += TC_PRODUCERS) {
-    int r = s % ROWS, c = s / ROWS;
-    int grow = MN ? k0 + r : mn0 + r;
-    int gcol = MN ? mn0 + 8 * c : k0 + 8 * c;
-    int row_lim = MN ? k_end : mn_ext;
-    int col_lim = MN ? mn_ext : k_end;
-    if (r != cur_row) {
-      // rows past the limit are initialised as invalid by clamping through n_rows inside the source;
-      // additionally mask rows past this CTA's k range (split-K) for MN-major operands
-      src.init_row(grow, row);
-      if (grow >= row_lim) row.valid = 0;
-      cur_row = r;
+  for (int i0 = 0; i0 < PER; i0 += U) {
+    float v[U][8];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int s = tid + (i0 + u) * TC_PRODUCERS;
+      int r = s % ROWS, c = s / ROWS;
+      int grow = MN ? k0 + r : mn0 + r;
+      int gcol = MN ? mn0 + 8 * c : k0 + 8 * c;
+      if (r != cur_row) {
+        src.init_row(grow, row);
+        if (grow >= row_lim) row.valid = 0;
+        cur_row = r;
+      }
+      if (gcol < col_lim) src.load8(row, gcol, v[u]); else zero8(v[u]);
     }
-    float v[8];
-    if (gcol < col_lim) src.load8(row, gcol, v); else zero8(v);
-    uint32_t off = (uint32_t)c * ROWS * 16 + (uint32_t)r * 16;
-    if (SPLIT) {
-      uint4 h, l;
-      split8(v, h, l);
-      *reinterpret_cast<uint4*>(hi + off) = h;
-      *reinterpret_cast<uint4*>(lo + off) = l;
-    } else {
-      uint4 h = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-      *reinterpret_cast<uint4*>(hi + off) = h;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int s = tid + (i0 + u) * TC_PRODUCERS;
+      int r = s % ROWS, c = s / ROWS;
+      uint32_t off = (uint32_t)c * ROWS * 16 + (uint32_t)r * 16;
+      if (SPLIT) {
+        uint4 h, l;
+        split8(v[u], h, l);
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        *reinterpret_cast<uint4*>(lo + off) = l;
+      } else {
+        uint4 h = make_uint4(pack_bf16(v[u][0], v[u][1]), pack_bf16(v[u][2], v[u][3]), pack_bf16(v[u][4], v[u][5]),
+                             pack_bf16(v[u][6], v[u][7]));
+        *reinterpret_cast<uint4*>(hi + off) = h;
+      }
     }
   }
 }

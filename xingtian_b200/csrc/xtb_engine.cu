@@ -74,6 +74,7 @@ struct LayerPlan {
   int* dkyx = nullptr; int* dco = nullptr; int* wk = nullptr;  // dgrad, indexed by k=(ky,kx,co)
   int Kd = 0;            // KH*KW*Cout
   int sshift = 0;
+  int cshift = -1, oshift = -1;   // log2(Cin), log2(Cout) when powers of two (tensor-core gathers), else -1
   bool pad = false;
 };
 
@@ -137,6 +138,7 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
       g.K = d.k * d.k * g.C; g.P = g.OH * g.OW;
       lp.K = g.K; lp.N = d.cout; lp.Kd = d.k * d.k * d.cout;
       lp.sshift = d.stride == 1 ? 0 : (d.stride == 2 ? 1 : 2);
+      for (int sft = 0; sft < 12; sft++) { if ((1 << sft) == g.C) lp.cshift = sft; if ((1 << sft) == d.cout) lp.oshift = sft; }
       shp[i + 1] = {g.OH, g.OW, d.cout};
       // tables
       std::vector<int> koff(g.K), kyx(g.K), dkyx(lp.Kd), dco(lp.Kd), wk(lp.Kd);
@@ -295,7 +297,7 @@ __global__ void bias_act_kernel(float* __restrict__ out, const float* __restrict
 }
 
 static bool tc_conv_ok(const LayerPlan& lp) {
-  return g_tc_mode && (lp.g.C == 4 || lp.g.C % 8 == 0) && lp.N % 8 == 0 && lp.N <= 64 && lp.K % 8 == 0;
+  return g_tc_mode && lp.cshift >= 2 && lp.N % 8 == 0 && lp.N <= 64 && lp.K % 8 == 0;
 }
 static bool tc_dense_ok(const LayerPlan& lp) { return g_tc_mode && lp.K % 8 == 0 && lp.N % 8 == 0 && lp.K >= 64 && lp.N >= 16; }
 
@@ -303,7 +305,7 @@ template <typename T, bool PAD>
 static cudaError_t tc_conv_fwd_t(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
                                  float alpha, float* out, int B, cudaStream_t st) {
   int M = B * lp.g.P;
-  tc::SrcIm2col<T, PAD> a{x, idx, lp.g, lp.koff, lp.kyx, M};
+  tc::SrcIm2col<T, PAD> a{x, idx, lp.g, lp.cshift, M};
   tc::SrcDense<float> bs{w, nullptr, lp.N, lp.K};
   tc::TcEpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, M, lp.N};
   constexpr bool AS = !std::is_same<T, uint8_t>::value;
@@ -346,7 +348,7 @@ template <typename T, bool PAD>
 static cudaError_t tc_conv_wgrad_t(const LayerPlan& lp, const T* x, const int32_t* idx, const float* dy, float alpha,
                                    float* dw, int B, cudaStream_t st) {
   int Mr = B * lp.g.P;
-  tc::SrcIm2col<T, PAD> a{x, idx, lp.g, lp.koff, lp.kyx, Mr};
+  tc::SrcIm2col<T, PAD> a{x, idx, lp.g, lp.cshift, Mr};
   tc::SrcDense<float> bs{dy, nullptr, lp.N, Mr};
   tc::TcEpiAtomic ep{dw, alpha, lp.N, lp.K, lp.N};
   constexpr bool AS = !std::is_same<T, uint8_t>::value;
@@ -377,8 +379,8 @@ static cudaError_t tc_dense_wgrad(const LayerPlan& lp, const float* x, const flo
 static cudaError_t tc_conv_dgrad(const LayerPlan& lp, const float* dy, const float* w, float* gsrc, const float* xsrc,
                                  int acc, int B, cudaStream_t st) {
   int M = B * lp.g.H * lp.g.W;
-  tc::SrcDgrad a{dy, lp.g, lp.dkyx, lp.dco, lp.sshift, M};
-  tc::SrcWDgrad bs{w, lp.wk, lp.g.C, lp.N, lp.g.C};
+  tc::SrcDgrad a{dy, lp.g, lp.oshift, lp.sshift, M};
+  tc::SrcWDgrad bs{w, lp.g.C, lp.N, lp.oshift, lp.g.C};
   tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc, M, lp.g.C};
   if (lp.g.C <= 16) return tc::launch_tc<16, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
   if (lp.g.C <= 32) return tc::launch_tc<32, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
@@ -590,7 +592,7 @@ extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* ga
       const float* w = net->params + lp.w_off;
       int acc = written[s] ? 1 : 0;
       if (lp.d.kind == XTB_CONV) {
-        if (g_tc_mode && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.N % 8 == 0) {
+        if (g_tc_mode && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.oshift >= 3) {
           te = tc_conv_dgrad(lp, dy, w, gsrc, xsrc, acc, batch, st);
         } else {
           ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
