@@ -1,0 +1,134 @@
+"""CPU tier: the host-side mirror of the reference plugin interface (no GPU, no CUDA calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import xt_oracle as orc
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol(repo_root):
+    from xingtian_b200 import build, capi
+    build.build()
+    lib = capi.lib()
+    assert lib.xtb_version() == 100
+    header = open(os.path.join(repo_root, "include", "xtb200.h")).read()
+    declared = set(re.findall(r"\b(xtb_[a-z0-9_]+)\s*\(", header)) - {"xtb_grad_hook"}
+    assert declared, "no declarations parsed"
+    missing_binding = declared - set(capi.EXPORTED)
+    assert not missing_binding, missing_binding
+    raw = C.CDLL(capi.LIB_PATH)
+    for name in declared:
+        getattr(raw, name)          # raises AttributeError if the .so does not export it
+    assert lib.xtb_launch_count() == 0
+    # argument validation happens before any CUDA call
+    assert lib.xtb_gae(None, None, None, 1, 1, 0.99, 0.95, 0, None, None, None, None) == -1
+    assert b"null" in lib.xtb_last_error()
+
+
+def test_product_has_no_oracle_or_cpu_fallback(repo_root):
+    for root, _, files in os.walk(os.path.join(repo_root, "xingtian_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), (f, "product code must not import the oracle")
+    import torch
+    if not torch.cuda.is_available():
+        import xingtian_b200 as xb
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            xb.model_builder({"model_name": "PpoMlp", "state_dim": [4], "action_dim": 2, "model_config": {"action_type": "Categorical"}})
+
+
+def test_registry_semantics():
+    from xingtian_b200.registry import Registers, RegisterStub, import_config
+    assert {"PpoCnn", "PpoMlp", "ImpalaCnnOpt", "DqnCnn", "DqnMlp", "PPO"} <= set(Registers.model.keys())
+    assert {"PPO", "IMPALAOpt", "DQN"} <= set(Registers.algorithm.keys())
+    assert {"PPO", "AtariPpo"} <= set(Registers.agent.keys())
+    r = RegisterStub("x")
+
+    @r
+    class Foo(object):
+        pass
+    first = r["Foo"]
+
+    @r
+    class Foo(object):      # noqa: F811  re-registering replaces (register.py:58-69)
+        pass
+    assert r["Foo"] is not first
+    with pytest.raises(KeyError):
+        r["missing"]
+    with pytest.raises(Exception):
+        r(3)
+    with pytest.raises(RuntimeError):
+        Registers()
+    g = {"LR": 1.0, "OTHER": 2}
+    import_config(g, {"LR": 0.5, "UNKNOWN": 7})
+    assert g == {"LR": 0.5, "OTHER": 2}
+    import_config(g, None)
+
+
+def test_arch_tables_match_oracle():
+    from xingtian_b200.model import archs
+    pairs = [(archs.ppo_cnn((84, 84, 4), 4, [256], "relu", True), orc.ppo_cnn_arch()),
+             (archs.ppo_cnn((84, 84, 4), 6, [512], "relu", False), orc.ppo_cnn_arch(action_dim=6, hidden_sizes=(512,), vf_share_layers=False)),
+             (archs.ppo_mlp((4,), 2, [64, 64], "tanh", False), orc.ppo_mlp_arch()),
+             (archs.impala_cnn((84, 84, 4), 4), orc.impala_cnn_arch()),
+             (archs.dqn_cnn((84, 84, 4), 4), orc.dqn_cnn_arch()),
+             (archs.dqn_mlp((4,), 2, 128, 1), orc.dqn_mlp_arch())]
+    for a, b in pairs:
+        assert [(l[0], l[1], l[2]) for l in a["layers"]] == [(l[0], l[1], l[2]) for l in b["layers"]]
+        assert [l[3] for l in a["layers"]] == [l[3] for l in b["layers"]]
+        assert a["outputs"] == b["outputs"] and a["input_dtype"] == b["input_dtype"]
+    with pytest.raises(ValueError):
+        archs.ppo_cnn((80, 80, 4), 4, [256], "relu", True)
+
+
+def test_algorithm_base_cadence_and_policies():
+    from xingtian_b200.registry import Registers
+    from xingtian_b200.algorithm.base import Algorithm, DefaultAlgDistPolicy, FIFODistPolicy
+
+    @Registers.model
+    class _FakeModel(object):
+        def __init__(self, info):
+            self.w = {"a": np.zeros(2)}
+
+        def predict(self, s):
+            return np.array([[0.1, 0.9, 0.3]])
+
+        def get_weights(self):
+            return self.w
+
+        def set_weights(self, w):
+            self.w = w
+
+        def save_model(self, name):
+            return name + ".npz"
+
+    class _Buf(object):
+        def __init__(self, n):
+            self.n = n
+
+        def size(self):
+            return self.n
+    alg = Algorithm("x", {"model_name": "_FakeModel", "state_dim": [4], "action_dim": 3},
+                    {"instance_num": 5, "agent_num": 2, "learning_starts": 10, "train_per_checkpoint": 3, "save_model": True, "save_interval": 4})
+    assert alg.prepare_data_times == 10 and alg.async_flag is True
+    assert alg.if_save(8) and not alg.if_save(9)
+    assert alg.checkpoint_ready(6) and not alg.checkpoint_ready(7)
+    alg.buff = _Buf(3)
+    assert not alg.train_ready(0)
+    alg.buff = _Buf(10)
+    assert alg.train_ready(0)
+    assert alg.predict(np.zeros(4)) == 1
+    assert alg.save("/tmp/m", 7) == ["/tmp/m/actor_00007.npz"]
+    alg.restore(model_weights={"a": np.ones(2)})
+    assert alg.get_weights()["a"][0] == 1
+    p = DefaultAlgDistPolicy(4)
+    assert p.get_dist_info(0) == {"broker_id": -1, "explorer_id": -1}
+    f = FIFODistPolicy(4, prepare_times=1)
+    f.add_processed_ctr_info((0, 3, 0)); f.add_processed_ctr_info((0, 1, 0)); f.add_processed_ctr_info((1, 2, 0))
+    info = f.get_dist_info(5)
+    assert sorted((d["broker_id"], sorted(d["explorer_id"])) for d in info) == [(0, [1, 3]), (1, [2])]
+    assert f.get_dist_info(5) == []

@@ -633,27 +633,57 @@ extern "C" int xtb_net_bench_layer(xtb_net* net, int layer, int which, const voi
   bool from_obs = lp.d.src == 0;
   const float* x = from_obs ? nullptr : (const float*)(net->ws + net->out_off[lp.d.src]);
   float alpha = from_obs ? net->desc.scale : 1.f;
+  const bool tcc = lp.d.kind == XTB_CONV && tc_conv_ok(lp);
+  const bool tcd = lp.d.kind == XTB_DENSE && !from_obs && tc_dense_ok(lp);
   if (which == 0) {
     if (from_obs && net->desc.input_u8) {
-      if (lp.d.kind == XTB_CONV) conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, alpha, out, batch, st);
+      if (tcc) tc_conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, alpha, out, batch, st);
+      else if (lp.d.kind == XTB_CONV) conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, alpha, out, batch, st);
       else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, alpha, out, batch, st);
     } else {
       const float* xin = from_obs ? (const float*)obs : x;
-      if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, xin, from_obs ? gather_idx : nullptr, w, b, alpha, out, batch, st);
+      if (tcc) tc_conv_fwd<float>(lp, xin, from_obs ? gather_idx : nullptr, w, b, alpha, out, batch, st);
+      else if (tcd) tc_dense_fwd(lp, xin, w, b, out, batch, st);
+      else if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, xin, from_obs ? gather_idx : nullptr, w, b, alpha, out, batch, st);
       else dense_fwd<float>(lp, xin, from_obs ? gather_idx : nullptr, w, b, alpha, out, batch, st);
     }
   } else if (which == 1) {
     float* dw = net->grads + lp.w_off;
     if (from_obs && net->desc.input_u8) {
-      if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
+      if (tcc) tc_conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
+      else if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
       else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
     } else {
       const float* xin = from_obs ? (const float*)obs : x;
-      if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, xin, from_obs ? gather_idx : nullptr, dy, alpha, dw, batch, st);
+      if (tcc) tc_conv_wgrad<float>(lp, xin, from_obs ? gather_idx : nullptr, dy, alpha, dw, batch, st);
+      else if (tcd) tc_dense_wgrad(lp, xin, dy, dw, batch, st);
+      else if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, xin, from_obs ? gather_idx : nullptr, dy, alpha, dw, batch, st);
       else dense_wgrad<float>(lp, xin, from_obs ? gather_idx : nullptr, dy, alpha, dw, batch, st);
     }
+  } else if (which == 2) {
+    if (from_obs) return fail(XTB_ERR_ARG, "layer reads the observation: no data gradient");
+    float* gsrc = (float*)(net->ws + net->gout_off[lp.d.src]);
+    cudaError_t te = cudaSuccess;
+    if (lp.d.kind == XTB_CONV) {
+      if (g_tc_mode && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.oshift >= 3) te = tc_conv_dgrad(lp, dy, w, gsrc, x, 0, batch, st);
+      else {
+        ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
+        BConvDgrad bl{w, lp.wk, lp.N};
+        EpiDgrad ep{gsrc, x, lp.src_act, lp.g.C, 0};
+        launch_gemm(al, bl, ep, batch * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
+      }
+    } else {
+      if (tc_dense_ok(lp)) te = tc_dense_dgrad(lp, dy, w, gsrc, x, 0, batch, st);
+      else {
+        ADense<float> al{dy, nullptr, lp.N};
+        BTransposed bl{w, lp.N};
+        EpiDgrad ep{gsrc, x, lp.src_act, lp.K, 0};
+        launch_gemm(al, bl, ep, batch, lp.K, lp.N, false, st);
+      }
+    }
+    if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "bench dgrad: %s", cudaGetErrorString(te));
   } else {
-    return fail(XTB_ERR_ARG, "xtb_net_bench_layer: which must be 0 or 1");
+    return fail(XTB_ERR_ARG, "xtb_net_bench_layer: which must be 0, 1 or 2");
   }
   LAUNCH_CHECK();
   return XTB_OK;

@@ -27,6 +27,18 @@ MLP_SHARE_LAYERS = False
 _SUPPORTED_ACT = ("relu", "tanh", "linear", None)
 
 
+def minibatch_order(nbatch, num_sgd_iter):
+    """Index order of xt/model/ppo/ppo.py:114-121: `inds` is shuffled IN PLACE once per epoch with the
+    global numpy RNG (so epoch e's order is a shuffle of epoch e-1's); returns int32 [num_sgd_iter, nbatch].
+    Minibatch j of epoch e is row e, columns [j*BATCH_SIZE, (j+1)*BATCH_SIZE) -- the last one may be ragged."""
+    inds = np.arange(nbatch)
+    out = np.empty((num_sgd_iter, nbatch), np.int32)
+    for e in range(num_sgd_iter):
+        np.random.shuffle(inds)
+        out[e] = inds
+    return out
+
+
 class DeviceRollout(object):
     """Device-resident PPO rollout (grow-only, so CUDA-graph pointers stay valid)."""
 
@@ -165,12 +177,7 @@ class PPO(XTModel):
     # -- training ----------------------------------------------------------------------------
     def make_perm(self, nbatch):
         """Index order of xt/model/ppo/ppo.py:114-121: `inds` shuffled in place every epoch."""
-        inds = np.arange(nbatch)
-        out = np.empty((self.num_sgd_iter, nbatch), np.int32)
-        for e in range(self.num_sgd_iter):
-            np.random.shuffle(inds)
-            out[e] = inds
-        return out
+        return minibatch_order(nbatch, self.num_sgd_iter)
 
     def train_device(self, nbatch, perm=None):
         """Run the minibatch-SGD loop on the device rollout (`self.rollout`, first nbatch rows)."""
