@@ -223,9 +223,7 @@ def run_b200(args):
 
     def device_iteration():
         # (1) batched inference over the E stacked observations, once per env step
-        for t in range(T):
-            a, lp, v = model.predict_device(store.obs, E, idx=step_idx[t], out_action=act_t[t], out_logp=logp_t[t])
-            val_t[t].copy_(v[:, 0])
+        model.rollout_infer_device(store.obs, step_idx, E, T, act_t, logp_t, val_t)
         val_t[T].copy_(val_t[T - 1])            # bootstrap value (synthetic rollout: no next observation)
         store.action[:n].copy_(act_t.t().reshape(-1)); store.old_logp[:n].copy_(logp_t.t().reshape(-1))
         value_d.copy_(val_t.t())

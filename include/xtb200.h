@@ -192,6 +192,15 @@ int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* ro, int n_
                   int batch_size, int n_epoch, const int32_t* perm, const xtb_ppo_hyper* hp,
                   int pi_tensor, int v_tensor, float* loss_per_step, int use_graph, void* stream);
 
+/* Rollout inference: for t in [0,n_step): forward over n_env observations (row e of step t is
+ * obs[step_idx[t*n_env+e]], NULL = rows t*n_env..), sample actions with Philox(seed, *offset_dev + t), and
+ * write action/logp/value time-major [n_step, n_env]; finally *offset_dev += n_step.  This is the batched
+ * replacement of the per-explorer batch-1 PPO.predict calls (xt/agent/ppo/ppo.py:35-45,
+ * xt/algorithm/ppo/ppo.py:87-95); use_graph caches one CUDA graph per (buffers, n_env, n_step). */
+int xtb_ppo_rollout_infer(xtb_net* net, const void* obs, const int32_t* step_idx, int n_env, int n_step,
+                          int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
+                          int32_t* action, float* logp, float* value, int use_graph, void* stream);
+
 /* Data-parallel hook: called between backward and the optimiser with the flat
  * gradient bucket; must SUM it over ranks on `stream` (e.g. ncclAllReduce).  Called once with
  * grads == NULL before the loop: must return the world size.  While a hook is installed the

@@ -257,3 +257,57 @@ def test_dqn_train_matches_oracle():
     y = ref.predict(s[:8]); y[:, 1] += 1.0
     l1 = alg.actor.train(s[:8], y)
     assert abs(l1 - 0.25) < 0.05
+
+
+def test_rollout_infer_graph_matches_per_step_predict():
+    """The T-step graph-captured rollout inference equals T separate predict calls under the same Philox
+    stream, and replays draw fresh noise (device-side offset counter)."""
+    import xingtian_b200 as xb
+    alg = xb.alg_builder("PPO", ppo_cnn_info(), alg_cfg())
+    m = alg.actor
+    E, T = 8, 5
+    rng = np.random.default_rng(0)
+    obs = torch.from_numpy(rng.integers(0, 256, (E * T, 84, 84, 4), dtype=np.uint8)).cuda()
+    step_idx = (torch.arange(E, dtype=torch.int32, device="cuda")[None, :] * T + torch.arange(T, dtype=torch.int32, device="cuda")[:, None]).contiguous()
+    act = torch.empty(T, E, dtype=torch.int32, device="cuda"); lp = torch.empty(T, E, device="cuda"); val = torch.empty(T + 1, E, device="cuda")
+    m.rollout_infer_device(obs, step_idx, E, T, act, lp, val)
+    a1 = act.cpu().numpy().copy()
+    arch = orc.ppo_cnn_arch(); w = alg.get_weights()
+    for t in range(T):
+        rows = (np.arange(E) * T + t)
+        u = orc.philox_uniforms(m._sample_seed, t, E, 4)
+        ract, rlogp, rval = orc.ppo_predict(arch, w, obs.cpu().numpy()[rows], u)
+        assert rel_err(val[t].cpu().numpy(), rval[:, 0]) < REL and rel_err(lp[t].cpu().numpy(), rlogp[:, 0]) < REL
+        assert (a1[t] == ract).mean() >= 0.85
+    m.rollout_infer_device(obs, step_idx, E, T, act, lp, val)     # graph replay: offset advanced by T
+    assert int(m._offset_dev.cpu()[0]) == 2 * T
+    u = orc.philox_uniforms(m._sample_seed, T, E, 4)
+    ract, _, _ = orc.ppo_predict(arch, w, obs.cpu().numpy()[np.arange(E) * T], u)
+    assert (act[0].cpu().numpy() == ract).mean() >= 0.85
+
+
+@pytest.mark.parametrize("fuse", [1, 0])
+def test_fused_heads_equals_unfused(fuse):
+    """The fused heads+loss kernel and the layer-by-layer path give the same loss trace and weights."""
+    import subprocess, sys, json
+    code = r"""
+import os, sys, json, numpy as np
+sys.path.insert(0, %r)
+import xingtian_b200 as xb
+from tests.test_gpu_plugins import ppo_cnn_info, alg_cfg, make_trajs
+alg = xb.alg_builder("PPO", ppo_cnn_info(batch=24, iters=2), alg_cfg())
+for tr in make_trajs(4, 16, seed=3):
+    alg.prepare_data({k: tr[k] for k in ("cur_state", "action", "logp", "adv", "old_value", "target_value")})
+np.random.seed(5)
+loss = alg.train()
+w = alg.get_weights()
+print(json.dumps({"loss": loss, "trace": [float(x) for x in alg.actor.last_losses], "wsum": float(sum(np.abs(v).sum() for v in w.values()))}))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for f in (fuse, 1 - fuse):
+        env = dict(os.environ, XTB_FUSE_HEADS=str(f))
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert rel_err(outs[0]["trace"], outs[1]["trace"]) < 1e-4
+    assert abs(outs[0]["wsum"] - outs[1]["wsum"]) < 1e-4 * outs[1]["wsum"]

@@ -71,6 +71,7 @@ _SIGS = {
     "xtb_adam_set_lr": (C.c_int, [_P, C.c_float]),
     "xtb_ppo_train": (C.c_int, [_P, _P, C.POINTER(PpoRollout), C.c_int, C.c_int, C.c_int, _P,
                                 C.POINTER(PpoHyper), C.c_int, C.c_int, _P, C.c_int, _P]),
+    "xtb_ppo_rollout_infer": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, _P, C.c_int, _P]),
     "xtb_set_grad_hook": (C.c_int, [GRAD_HOOK, _P]),
     "xtb_net_bench_layer": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "xtb_set_tc_mode": (C.c_int, [C.c_int]),

@@ -142,6 +142,38 @@ __global__ void sample_kernel(const float* __restrict__ logits, int B, int A,
   logp[b] = l[bi] - mx - lz;
 }
 
+// rollout variant: Philox offset = *offset_dev + t_add (device-resident counter so that CUDA-graph replays
+// draw fresh noise), and the value head output is copied out alongside.
+__global__ void sample_rollout_kernel(const float* __restrict__ logits, const float* __restrict__ v_in, int B, int A,
+                                      uint64_t seed, const unsigned long long* __restrict__ offset_dev, int t_add,
+                                      int32_t* __restrict__ action, float* __restrict__ logp, float* __restrict__ v_out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  uint64_t offset = (uint64_t)(*offset_dev) + (uint64_t)t_add;
+  const float* l = logits + (long long)b * A;
+  float mx = -INFINITY;
+  for (int i = 0; i < A; i++) mx = fmaxf(mx, l[i]);
+  float z = 0.f;
+  for (int i = 0; i < A; i++) z += expf(l[i] - mx);
+  float lz = logf(z);
+  float best = -INFINITY; int bi = 0;
+  uint32_t c[4] = {0, 0, 0, 0};
+  for (int i = 0; i < A; i++) {
+    if ((i & 3) == 0) {
+      c[0] = (uint32_t)b; c[1] = (uint32_t)(i >> 2);
+      c[2] = (uint32_t)(offset & 0xffffffffu); c[3] = (uint32_t)(offset >> 32);
+      philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+    }
+    float u = (float)(c[i & 3] >> 8) * 5.9604644775390625e-08f + 2.98023223876953125e-08f;
+    float s = l[i] - logf(-logf(u));
+    if (s > best) { best = s; bi = i; }
+  }
+  action[b] = bi;
+  logp[b] = l[bi] - mx - lz;
+  v_out[b] = v_in[b];
+}
+__global__ void bump_counter_kernel(unsigned long long* ctr, int add) { *ctr += (unsigned long long)add; }
+
 __global__ void argmax_kernel(const float* __restrict__ q, int B, int A, int32_t* __restrict__ action) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -346,6 +378,166 @@ __global__ void dqn_loss_kernel(const float* __restrict__ q, const float* __rest
     lsum = diff * diff * inv_count;
   }
   block_atomic_add(lsum, loss_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused PPO heads: pi/v dense heads + categorical loss + their backward in ONE kernel (K4/K7 of the
+// kernel work-list: the logits never leave the chip between the head GEMM and the loss).
+//   logits = h_pi @ Wpi + bpi,  v = h_v @ Wv + bv            (xt/model/model_utils.py:63-65)
+//   loss, dlogits, dv                                        (xt/model/ppo/__init__.py:4-25)
+//   dWpi,dbpi,dWv,dbv += ...   (atomics into the flat gradient bucket)
+//   g(h) = (dlogits @ Wpi^T [+ dv * Wv^T]) * act'(h)         -> gradient wrt the hidden pre-activation
+// One warp per sample, lane owns hidden units lane, lane+32, ...  (K <= 32*HEAD_KPL, A <= HEAD_AMAX)
+// ------------------------------------------------------------------------------------------
+// template: HEAD_KPL hidden units per lane (K <= 32*HEAD_KPL), HEAD_AMAX >= A
+
+struct PpoHeadsArgs {
+  const float* h_pi; const float* h_v;     // [B,K] hidden activations (may alias)
+  float* g_pi; float* g_v;                 // [B,K] gradient wrt hidden pre-activation (may alias)
+  const float* w_pi; const float* b_pi; const float* w_v; const float* b_v;
+  float* dw_pi; float* db_pi; float* dw_v; float* db_v;
+  const int32_t* idx; const int32_t* action; const float* old_logp; const float* adv; const float* old_v; const float* target_v;
+  float* logits_out; float* v_out; float* loss_out;
+  int B, K, A, act_pi, act_v, shared;
+  PpoHyperDev hp; float inv_count;
+};
+
+template <int HEAD_KPL, int HEAD_AMAX>
+__global__ void __launch_bounds__(256) ppo_heads_kernel(PpoHeadsArgs a) {
+  extern __shared__ float sh_dw[];          // [K*(A+1) + (A+1)] block-level weight/bias gradient accumulators
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int K = a.K, A = a.A, kpl = K / 32;
+  const int nacc = K * (A + 1) + (A + 1);
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sh_dw[i] = 0.f;
+  __syncthreads();
+  float wpi[HEAD_KPL][HEAD_AMAX], wv[HEAD_KPL];
+  float dwp[HEAD_KPL][HEAD_AMAX], dwv[HEAD_KPL];
+#pragma unroll
+  for (int j = 0; j < HEAD_KPL; j++) {
+    wv[j] = 0.f; dwv[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_AMAX; i++) { wpi[j][i] = 0.f; dwp[j][i] = 0.f; }
+    if (j < kpl) {
+      int k = lane + 32 * j;
+      wv[j] = a.w_v[k];
+#pragma unroll
+      for (int i = 0; i < HEAD_AMAX; i++) if (i < A) wpi[j][i] = a.w_pi[k * A + i];
+    }
+  }
+  float dbp[HEAD_AMAX]; float dbv = 0.f, lsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < HEAD_AMAX; i++) dbp[i] = 0.f;
+  for (int b = blockIdx.x * nwarp + warp; b < a.B; b += gridDim.x * nwarp) {
+    float hp_[HEAD_KPL], hv_[HEAD_KPL];
+    float acc[HEAD_AMAX + 1];
+#pragma unroll
+    for (int i = 0; i <= HEAD_AMAX; i++) acc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < HEAD_KPL; j++) {
+      hp_[j] = 0.f; hv_[j] = 0.f;
+      if (j < kpl) {
+        int k = lane + 32 * j;
+        hp_[j] = a.h_pi[(long long)b * K + k];
+        hv_[j] = a.shared ? hp_[j] : a.h_v[(long long)b * K + k];
+#pragma unroll
+        for (int i = 0; i < HEAD_AMAX; i++) acc[i] = fmaf(hp_[j], wpi[j][i], acc[i]);
+        acc[HEAD_AMAX] = fmaf(hv_[j], wv[j], acc[HEAD_AMAX]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i <= HEAD_AMAX; i++) acc[i] = warp_sum(acc[i]);
+    // ---- loss + d(logits), d(v): every lane computes the same values
+    float lg[HEAD_AMAX]; float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < HEAD_AMAX; i++) { lg[i] = (i < A) ? acc[i] + a.b_pi[i] : -INFINITY; mx = fmaxf(mx, lg[i]); }
+    float vv = acc[HEAD_AMAX] + a.b_v[0];
+    float z = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_AMAX; i++) if (i < A) z += expf(lg[i] - mx);
+    float lz = logf(z), H = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_AMAX; i++) if (i < A) { float rl = lg[i] - mx; H += (expf(rl) / z) * (lz - rl); }
+    int r = a.idx ? a.idx[b] : b;
+    int ac = a.action[r];
+    float logp_a = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_AMAX; i++) if (i == ac) logp_a = lg[i] - mx - lz;
+    float ratio = expf(logp_a - a.old_logp[r]);
+    float ad = a.adv[r];
+    float s1 = ratio * ad;
+    float s2 = fminf(fmaxf(ratio, 1.f - a.hp.clip_ratio), 1.f + a.hp.clip_ratio) * ad;
+    float surr = fminf(s1, s2);
+    float dsurr = (s1 <= s2) ? ratio * ad
+                             : ((ratio >= 1.f - a.hp.clip_ratio && ratio <= 1.f + a.hp.clip_ratio) ? ratio * ad : 0.f);
+    float R = a.target_v[r], ov = a.old_v[r];
+    float l1 = (vv - R) * (vv - R);
+    float vc = ov + fminf(fmaxf(vv - ov, -a.hp.vf_clip), a.hp.vf_clip);
+    float l2 = (vc - R) * (vc - R);
+    float dvl = (l1 >= l2) ? 2.f * (vv - R)
+                           : ((vv - ov >= -a.hp.vf_clip && vv - ov <= a.hp.vf_clip) ? 2.f * (vc - R) : 0.f);
+    float dv = a.hp.critic_coef * 0.5f * dvl * a.inv_count;
+    float dl[HEAD_AMAX];
+#pragma unroll
+    for (int i = 0; i < HEAD_AMAX; i++) {
+      dl[i] = 0.f;
+      if (i < A) {
+        float rl = lg[i] - mx, p = expf(rl) / z;
+        dl[i] = (-dsurr * (((i == ac) ? 1.f : 0.f) - p) + a.hp.ent_coef * p * (rl - lz + H)) * a.inv_count;
+      }
+    }
+    if (lane == 0) {
+      lsum += (-surr - a.hp.ent_coef * H + a.hp.critic_coef * 0.5f * fmaxf(l1, l2)) * a.inv_count;
+      if (a.logits_out) for (int i = 0; i < A; i++) a.logits_out[(long long)b * A + i] = lg[i];
+      if (a.v_out) a.v_out[b] = vv;
+      dbv += dv;
+#pragma unroll
+      for (int i = 0; i < HEAD_AMAX; i++) dbp[i] += dl[i];
+    }
+    // ---- head weight gradients (registers) and gradient wrt the hidden units
+#pragma unroll
+    for (int j = 0; j < HEAD_KPL; j++) {
+      if (j < kpl) {
+        int k = lane + 32 * j;
+        float gp = 0.f;
+#pragma unroll
+        for (int i = 0; i < HEAD_AMAX; i++) { dwp[j][i] = fmaf(hp_[j], dl[i], dwp[j][i]); gp = fmaf(dl[i], wpi[j][i], gp); }
+        dwv[j] = fmaf(hv_[j], dv, dwv[j]);
+        float gv = dv * wv[j];
+        if (a.shared) {
+          a.g_pi[(long long)b * K + k] = (gp + gv) * act_grad_from_out(a.act_pi, hp_[j]);
+        } else {
+          a.g_pi[(long long)b * K + k] = gp * act_grad_from_out(a.act_pi, hp_[j]);
+          a.g_v[(long long)b * K + k] = gv * act_grad_from_out(a.act_v, hv_[j]);
+        }
+      }
+    }
+  }
+  // ---- block reduction of the parameter gradients, then one atomic per parameter per block
+#pragma unroll
+  for (int j = 0; j < HEAD_KPL; j++) {
+    if (j < kpl) {
+      int k = lane + 32 * j;
+#pragma unroll
+      for (int i = 0; i < HEAD_AMAX; i++) if (i < A) atomicAdd(&sh_dw[k * (A + 1) + i], dwp[j][i]);
+      atomicAdd(&sh_dw[k * (A + 1) + A], dwv[j]);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < HEAD_AMAX; i++) if (i < A) atomicAdd(&sh_dw[K * (A + 1) + i], dbp[i]);
+    atomicAdd(&sh_dw[K * (A + 1) + A], dbv);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * (A + 1); i += blockDim.x) {
+    int k = i / (A + 1), n = i - k * (A + 1);
+    float g = sh_dw[i];
+    if (n < A) atomicAdd(a.dw_pi + k * A + n, g); else atomicAdd(a.dw_v + k, g);
+  }
+  if (threadIdx.x <= A) {
+    float g = sh_dw[K * (A + 1) + threadIdx.x];
+    if ((int)threadIdx.x < A) atomicAdd(a.db_pi + threadIdx.x, g); else atomicAdd(a.db_v, g);
+  }
+  block_atomic_add(lsum, a.loss_out);
 }
 
 // Keras train_on_batch(states, y) with loss='mse': mean over B*A of (q-y)^2

@@ -324,9 +324,9 @@ static cudaError_t tc_dense_fwd(const LayerPlan& lp, const float* x, const float
                                 int B, cudaStream_t st) {
   tc::SrcDense<float> a{x, nullptr, lp.K, B};
   tc::SrcDense<float> bs{w, nullptr, lp.N, lp.K};
-  int nt = lp.N <= 64 ? 64 : 256;
+  int nt = 64;
   long long ctas = (long long)((B + 127) / 128) * ((lp.N + nt - 1) / nt);
-  int ks = lp.K >= 1024 ? tc::pick_ksplit(ctas, lp.K, 64, 48) : 1;
+  int ks = lp.K >= 1024 ? tc::pick_ksplit(ctas, lp.K, 64, 148) : 1;
   if (ks > 1) {   // split-K: atomics into a zeroed buffer, then bias + activation in place
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * lp.N * sizeof(float), st);
     if (e != cudaSuccess) return e;
@@ -369,9 +369,9 @@ static cudaError_t tc_dense_wgrad(const LayerPlan& lp, const float* x, const flo
   tc::SrcDense<float> a{x, nullptr, lp.K, B};
   tc::SrcDense<float> bs{dy, nullptr, lp.N, B};
   tc::TcEpiAtomic ep{dw, 1.f, lp.N, lp.K, lp.N};
-  int nt = lp.N <= 64 ? 64 : 256;
+  int nt = 64;
   long long ctas = (long long)((lp.K + 127) / 128) * ((lp.N + nt - 1) / nt);
-  int ks = tc::pick_ksplit(ctas, B, 64, 48);
+  int ks = tc::pick_ksplit(ctas, B, 64, 148);
   return nt == 64 ? tc::launch_tc<64, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st)
                   : tc::launch_tc<256, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st);
 }
@@ -392,8 +392,7 @@ static cudaError_t tc_dense_dgrad(const LayerPlan& lp, const float* dy, const fl
   tc::SrcDense<float> a{dy, nullptr, lp.N, B};
   tc::SrcDense<float> bs{w, nullptr, lp.N, lp.K};          // rows = kw (N' entity), cols = n (K')
   tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc, B, lp.K};
-  return lp.K <= 64 ? tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, B, lp.K, lp.N, 1, st)
-                    : tc::launch_tc<256, 64, false, false, true, true>(a, bs, ep, B, lp.K, lp.N, 1, st);
+  return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, B, lp.K, lp.N, 1, st);
 }
 
 // Self-test of the three operand-major combinations on plain matrices (see tests/test_gpu_tc.py):
@@ -481,14 +480,21 @@ __global__ void colsum_kernel(const float* __restrict__ dy, int M, int N, float*
   }
 }
 
+static int net_forward_impl(xtb_net* net, const float* params, const void* obs, const int32_t* gather_idx,
+                            int batch, void* stream, unsigned skip_mask);
 extern "C" int xtb_net_forward(xtb_net* net, const float* params, const void* obs, const int32_t* gather_idx,
                                int batch, void* stream) {
+  return net_forward_impl(net, params, obs, gather_idx, batch, stream, 0u);
+}
+static int net_forward_impl(xtb_net* net, const float* params, const void* obs, const int32_t* gather_idx,
+                            int batch, void* stream, unsigned skip_mask) {
   if (!net || !net->ws) return fail(XTB_ERR_STATE, "xtb_net_forward: net not bound");
   if (batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "batch %d out of range (max %d)", batch, net->max_batch);
   if (!obs) return fail(XTB_ERR_ARG, "obs is null");
   const float* P = params ? params : net->params;
   cudaStream_t st = S(stream);
   for (size_t i = 0; i < net->L.size(); i++) {
+    if (skip_mask & (1u << i)) continue;
     const LayerPlan& lp = net->L[i];
     float* out = (float*)(net->ws + net->out_off[i + 1]);
     const float* w = P + lp.w_off;
@@ -522,8 +528,15 @@ extern "C" int xtb_net_forward(xtb_net* net, const float* params, const void* ob
   return XTB_OK;
 }
 
+static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
+                             const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads);
 extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
                                 const int32_t* head_tensors, int n_heads, void* stream) {
+  return net_backward_impl(net, obs, gather_idx, batch, head_tensors, n_heads, stream, 0u, true);
+}
+// head_tensors: tensors whose gradient buffers were filled by the caller; skip_mask: layers handled elsewhere
+static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
+                             const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads) {
   if (!net || !net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_net_backward: net not bound (grads required)");
   if (batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "batch out of range");
   cudaStream_t st = S(stream);
@@ -534,8 +547,9 @@ extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* ga
     if (t < 1 || t > nl) return fail(XTB_ERR_ARG, "bad head tensor %d", t);
     has_grad[t] = 1; written[t] = 1;
   }
-  CUDA_TRY(cudaMemsetAsync(net->grads, 0, net->n_params * sizeof(float), st));
+  if (zero_grads) CUDA_TRY(cudaMemsetAsync(net->grads, 0, net->n_params * sizeof(float), st));
   for (int i = nl - 1; i >= 0; i--) {
+    if (skip_mask & (1u << i)) continue;
     const LayerPlan& lp = net->L[i];
     int t = i + 1;
     if (!has_grad[t]) continue;   // tensor does not influence the loss
@@ -869,6 +883,7 @@ struct GraphKey {
 struct GraphVal { cudaGraphExec_t exec; long long kernels; };
 static std::map<GraphKey, GraphVal> g_graphs;
 
+static int g_fuse_heads = [] { const char* e = getenv("XTB_FUSE_HEADS"); return e ? atoi(e) : 1; }();
 static xtb_grad_hook g_grad_hook = nullptr;
 static void* g_grad_hook_user = nullptr;
 extern "C" int xtb_set_grad_hook(xtb_grad_hook hook, void* user) {
@@ -883,19 +898,49 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
   CUDA_TRY(cudaMemsetAsync(loss_per_step, 0, sizeof(float) * E * steps_per_epoch, S(stream)));
   int heads[2] = {pi_t, v_t};
   int adim = net->tsize[pi_t];
+  // fused heads: both heads are linear dense layers on hidden tensors of equal width
+  const LayerPlan& lpi = net->L[pi_t - 1];
+  const LayerPlan& lv = net->L[v_t - 1];
+  int kpl = lpi.K / 32;
+  bool fuse = g_fuse_heads && lpi.d.kind == XTB_DENSE && lv.d.kind == XTB_DENSE && lpi.d.act == 0 && lv.d.act == 0 &&
+              lpi.d.src != 0 && lv.d.src != 0 && lpi.K == lv.K && lpi.K % 32 == 0 && adim <= 8 &&
+              (kpl <= 8 || (kpl <= 16 && adim <= 4));
+  unsigned skip = fuse ? ((1u << (pi_t - 1)) | (1u << (v_t - 1))) : 0u;
   int step = 0;
   for (int e = 0; e < E; e++) {
     for (int s0 = 0; s0 < N; s0 += B, step++) {
       int mb = std::min(B, N - s0);
       const int32_t* idx = perm + (long long)e * N + s0;
-      int rc = xtb_net_forward(net, nullptr, ro->obs, idx, mb, stream);
+      int rc = net_forward_impl(net, nullptr, ro->obs, idx, mb, stream, skip);
       if (rc) return rc;
-      rc = xtb_ppo_loss_grad(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), idx, ro->action, ro->old_logp,
-                             ro->adv, ro->old_v, ro->target_v, mb, adim, hp, inv_world / mb,
-                             xtb_net_tensor_grad(net, pi_t), xtb_net_tensor_grad(net, v_t), loss_per_step + step, stream);
-      if (rc) return rc;
-      rc = xtb_net_backward(net, ro->obs, idx, mb, heads, 2, stream);
-      if (rc) return rc;
+      if (fuse) {
+        CUDA_TRY(cudaMemsetAsync(net->grads, 0, net->n_params * sizeof(float), S(stream)));
+        PpoHeadsArgs a;
+        a.h_pi = (const float*)(net->ws + net->out_off[lpi.d.src]); a.h_v = (const float*)(net->ws + net->out_off[lv.d.src]);
+        a.g_pi = (float*)(net->ws + net->gout_off[lpi.d.src]); a.g_v = (float*)(net->ws + net->gout_off[lv.d.src]);
+        a.w_pi = net->params + lpi.w_off; a.b_pi = net->params + lpi.b_off; a.w_v = net->params + lv.w_off; a.b_v = net->params + lv.b_off;
+        a.dw_pi = net->grads + lpi.w_off; a.db_pi = net->grads + lpi.b_off; a.dw_v = net->grads + lv.w_off; a.db_v = net->grads + lv.b_off;
+        a.idx = idx; a.action = ro->action; a.old_logp = ro->old_logp; a.adv = ro->adv; a.old_v = ro->old_v; a.target_v = ro->target_v;
+        a.logits_out = xtb_net_tensor(net, pi_t); a.v_out = xtb_net_tensor(net, v_t); a.loss_out = loss_per_step + step;
+        a.B = mb; a.K = lpi.K; a.A = adim; a.act_pi = lpi.src_act; a.act_v = lv.src_act; a.shared = lpi.d.src == lv.d.src ? 1 : 0;
+        a.hp = PpoHyperDev{hp->clip_ratio, hp->ent_coef, hp->vf_clip, hp->critic_coef}; a.inv_count = inv_world / mb;
+        int blocks = std::max(1, std::min(148, (mb + 15) / 16));
+        size_t shb = (size_t)(lpi.K * (adim + 1) + adim + 1) * sizeof(float);
+        if (kpl <= 2) ppo_heads_kernel<2, 8><<<blocks, 256, shb, S(stream)>>>(a);
+        else if (kpl <= 8) ppo_heads_kernel<8, 8><<<blocks, 256, shb, S(stream)>>>(a);
+        else ppo_heads_kernel<16, 4><<<blocks, 256, shb, S(stream)>>>(a);
+        LAUNCH_CHECK();
+        int srcs[2] = {lpi.d.src, lv.d.src};
+        rc = net_backward_impl(net, ro->obs, idx, mb, srcs, a.shared ? 1 : 2, stream, skip, false);
+        if (rc) return rc;
+      } else {
+        rc = xtb_ppo_loss_grad(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), idx, ro->action, ro->old_logp,
+                               ro->adv, ro->old_v, ro->target_v, mb, adim, hp, inv_world / mb,
+                               xtb_net_tensor_grad(net, pi_t), xtb_net_tensor_grad(net, v_t), loss_per_step + step, stream);
+        if (rc) return rc;
+        rc = xtb_net_backward(net, ro->obs, idx, mb, heads, 2, stream);
+        if (rc) return rc;
+      }
       if (g_grad_hook) {
         rc = g_grad_hook(g_grad_hook_user, net->grads, net->n_params, stream);
         if (rc) return fail(XTB_ERR_STATE, "gradient hook failed with %d", rc);
@@ -944,6 +989,66 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
     it = g_graphs.emplace(key, GraphVal{exec, captured}).first;
+  }
+  CUDA_TRY(cudaGraphLaunch(it->second.exec, S(stream)));
+  g_launches.fetch_add(it->second.kernels, std::memory_order_relaxed);
+  return XTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// rollout inference: T batched policy evaluations over the E stacked observations
+// ------------------------------------------------------------------------------------------
+struct InferKey {
+  const void* net; const void* obs; const void* idx; const void* act; int e, t;
+  bool operator<(const InferKey& o) const { return std::tie(net, obs, idx, act, e, t) < std::tie(o.net, o.obs, o.idx, o.act, o.e, o.t); }
+};
+static std::map<InferKey, GraphVal> g_infer_graphs;
+
+static int rollout_infer_launch(xtb_net* net, const void* obs, const int32_t* step_idx, int E, int T, int pi_t, int v_t,
+                                uint64_t seed, unsigned long long* offset_dev, int32_t* action, float* logp, float* value,
+                                void* stream) {
+  int adim = net->tsize[pi_t];
+  for (int t = 0; t < T; t++) {
+    int rc = xtb_net_forward(net, nullptr, obs, step_idx ? step_idx + (long long)t * E : nullptr, E, stream);
+    if (rc) return rc;
+    sample_rollout_kernel<<<(E + 127) / 128, 128, 0, S(stream)>>>(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), E, adim, seed,
+                                                                 offset_dev, t, action + (long long)t * E, logp + (long long)t * E,
+                                                                 value + (long long)t * E);
+    LAUNCH_CHECK();
+  }
+  bump_counter_kernel<<<1, 1, 0, S(stream)>>>(offset_dev, T);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+extern "C" int xtb_ppo_rollout_infer(xtb_net* net, const void* obs, const int32_t* step_idx, int n_env, int n_step,
+                                     int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
+                                     int32_t* action, float* logp, float* value, int use_graph, void* stream) {
+  if (!net || !net->ws || !obs || !offset_dev || !action || !logp || !value) return fail(XTB_ERR_ARG, "xtb_ppo_rollout_infer: null pointer");
+  int nl = (int)net->L.size();
+  if (n_env <= 0 || n_env > net->max_batch || n_step <= 0) return fail(XTB_ERR_ARG, "xtb_ppo_rollout_infer: bad sizes");
+  if (pi_tensor < 1 || pi_tensor > nl || v_tensor < 1 || v_tensor > nl || net->tsize[v_tensor] != 1 || net->tsize[pi_tensor] > MAX_ADIM)
+    return fail(XTB_ERR_ARG, "xtb_ppo_rollout_infer: bad head tensors");
+  if (!use_graph || !stream)
+    return rollout_infer_launch(net, obs, step_idx, n_env, n_step, pi_tensor, v_tensor, seed, offset_dev, action, logp, value, stream);
+  InferKey key{net, obs, step_idx, action, n_env, n_step};
+  auto it = g_infer_graphs.find(key);
+  if (it == g_infer_graphs.end()) {
+    cudaStream_t st = S(stream);
+    long long before = g_launches.load();
+    CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = rollout_infer_launch(net, obs, step_idx, n_env, n_step, pi_tensor, v_tensor, seed, offset_dev, action, logp, value, stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    long long captured = g_launches.load() - before;
+    g_launches.store(before);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    it = g_infer_graphs.emplace(key, GraphVal{exec, captured}).first;
   }
   CUDA_TRY(cudaGraphLaunch(it->second.exec, S(stream)));
   g_launches.fetch_add(it->second.kernels, std::memory_order_relaxed);

@@ -162,6 +162,16 @@ class PPO(XTModel):
         v = vout if vout is not None else net.tensor("output_value")[:batch]
         return action[:batch], logp[:batch], v
 
+    def rollout_infer_device(self, obs_dev, step_idx, n_env, n_step, action, logp, value):
+        """T batched policy evaluations on device-resident observations (one CUDA graph): time-major
+        outputs action/logp/value [n_step, n_env]."""
+        if getattr(self, "_offset_dev", None) is None:
+            self._offset_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.net.ensure_batch(n_env)
+        check(self.net.lib.xtb_ppo_rollout_infer(self.net.handle, _ptr(obs_dev), _ptr(step_idx), int(n_env), int(n_step),
+                                                 self.pi_t, self.v_t, C.c_uint64(self._sample_seed), _ptr(self._offset_dev),
+                                                 _ptr(action), _ptr(logp), _ptr(value), 1 if self.use_graph else 0, stream_ptr()))
+
     def predict(self, state, uniforms=None):
         """xt/model/ppo/ppo.py:104-109: (action [B] int32, logp [B,1], v [B,1])."""
         state = np.ascontiguousarray(state, dtype=np.uint8 if self.input_dtype == "uint8" else np.float32)
