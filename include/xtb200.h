@@ -217,6 +217,9 @@ int xtb_net_bench_layer(xtb_net* net, int layer, int which, const void* obs, con
 /* Kernel-path selection: 1 (default) = tcgen05 tensor-core kernels wherever the shape is covered,
  * 0 = fp32 CUDA-core kernels only (also XTB_TC=0 in the environment).  For A/B parity tests. */
 int xtb_set_tc_mode(int mode);
+/* 1 (default): xtb_ppo_train evaluates both heads, the loss and their backward in one fused kernel;
+ * 0: layer-by-layer (also XTB_FUSE_HEADS=0).  Affects graphs captured after the call. */
+int xtb_set_fuse_heads(int on);
 int xtb_get_tc_mode(void);
 /* Self-test of the tcgen05 GEMM core on plain fp32 matrices (sizes multiples of 8):
  * mode 0: C = A[M,K] B[K,N]; mode 1: C = A[M,K] Bt[N,K]^T; mode 2: C = At[K,M]^T B[K,N]. */

@@ -74,6 +74,7 @@ _SIGS = {
     "xtb_ppo_rollout_infer": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, _P, C.c_int, _P]),
     "xtb_set_grad_hook": (C.c_int, [GRAD_HOOK, _P]),
     "xtb_net_bench_layer": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "xtb_set_fuse_heads": (C.c_int, [C.c_int]),
     "xtb_set_tc_mode": (C.c_int, [C.c_int]),
     "xtb_get_tc_mode": (C.c_int, []),
     "xtb_tc_gemm_test": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -884,6 +884,7 @@ struct GraphVal { cudaGraphExec_t exec; long long kernels; };
 static std::map<GraphKey, GraphVal> g_graphs;
 
 static int g_fuse_heads = [] { const char* e = getenv("XTB_FUSE_HEADS"); return e ? atoi(e) : 1; }();
+extern "C" int xtb_set_fuse_heads(int on) { g_fuse_heads = on; return XTB_OK; }
 static xtb_grad_hook g_grad_hook = nullptr;
 static void* g_grad_hook_user = nullptr;
 extern "C" int xtb_set_grad_hook(xtb_grad_hook hook, void* user) {
