@@ -84,6 +84,11 @@ int xtb_net_tensor_size(const xtb_net* net, int t);
 size_t xtb_net_workspace_bytes(const xtb_net* net);
 /* params/grads: [param_count] floats; workspace: xtb_net_workspace_bytes() bytes */
 int xtb_net_bind(xtb_net* net, float* params, float* grads, void* workspace, size_t workspace_bytes);
+/* Every tensor the tensor-core kernels read is kept as two bf16 planes (hi = bf16(x), lo = bf16(x-hi)) next
+ * to its fp32 copy.  The planes of the bound parameters are refreshed by xtb_net_bind, by the fused training
+ * loops after each optimiser step, and by this call -- which a host that writes the parameter buffer itself
+ * (set_weights, target-network sync, an external optimiser step) must make before the next forward. */
+int xtb_net_sync_weights(xtb_net* net, void* stream);
 /* activation / activation-gradient buffer of tensor t (t>=1), [batch, tensor_size] floats */
 float* xtb_net_tensor(xtb_net* net, int t);
 float* xtb_net_tensor_grad(xtb_net* net, int t);

@@ -16,7 +16,7 @@ lib = capi.lib()
 arch = {"ppo": lambda: archs.ppo_cnn((84, 84, 4), 4, [256], "relu", True), "impala": lambda: archs.impala_cnn((84, 84, 4), 4),
         "dqn": lambda: archs.dqn_cnn((84, 84, 4), 4)}[arch_name]()
 net = Net(arch, max_batch=B)
-net.params.normal_(0, 0.05)
+net.params.normal_(0, 0.05); net.params_changed()
 obs = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8, device="cuda")
 net.forward(obs, B)
 for n, _, _, _ in arch["layers"]:

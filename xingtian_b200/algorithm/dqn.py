@@ -62,4 +62,4 @@ class DQN(Algorithm):
 
     def update_target(self):
         """dqn.py:140-148: hard copy (device to device)."""
-        self.target_actor.net.params.copy_(self.actor.net.params)
+        self.target_actor.net.load_flat(self.actor.net.params)

@@ -49,6 +49,7 @@ _SIGS = {
     "xtb_net_tensor_size": (C.c_int, [_P, C.c_int]),
     "xtb_net_workspace_bytes": (C.c_size_t, [_P]),
     "xtb_net_bind": (C.c_int, [_P, _P, _P, _P, C.c_size_t]),
+    "xtb_net_sync_weights": (C.c_int, [_P, _P]),
     "xtb_net_tensor": (_P, [_P, C.c_int]),
     "xtb_net_tensor_grad": (_P, [_P, C.c_int]),
     "xtb_net_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),

@@ -8,10 +8,19 @@
 // tensor cores; this file is the numerically straightforward fp32 version they are checked
 // against on the device, and the fallback for shapes the tensor-core path does not cover.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace xtb {
+
+// keep the bf16 hi/lo planes of a tensor current (hi == NULL: tensor has no tensor-core consumer)
+__device__ __forceinline__ void f32_store_plane(__nv_bfloat16* hi, long long lo_off, long long e, float x) {
+  if (!hi) return;
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  hi[e] = h;
+  hi[lo_off + e] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
 
 struct ConvGeom {
   int H, W, C;        // input
@@ -198,17 +207,22 @@ struct BConvDgrad {    // B(k=(ky,kx,co), n=ci) = W[ky,kx,ci,co]
 // Epilogues: __device__ void store(int m,int n,float acc)
 // ------------------------------------------------------------------------------------------
 struct EpiBiasAct {    // out = act(alpha*acc + bias[n])
-  float* out; const float* bias; float alpha; int act; int ld;
+  float* out; const float* bias; float alpha; int act; int ld; __nv_bfloat16* hi; long long lo_off;
   __device__ void store(int m, int n, float acc) const {
-    out[(long long)m * ld + n] = act_apply(act, alpha * acc + bias[n]);
+    long long o = (long long)m * ld + n;
+    float r = act_apply(act, alpha * acc + bias[n]);
+    out[o] = r;
+    f32_store_plane(hi, lo_off, o, r);
   }
 };
 struct EpiDgrad {      // gout (+)= acc * act'(srcout)
-  float* gout; const float* srcout; int act; int ld; int accumulate;
+  float* gout; const float* srcout; int act; int ld; int accumulate; __nv_bfloat16* hi; long long lo_off;
   __device__ void store(int m, int n, float acc) const {
     long long o = (long long)m * ld + n;
     float g = acc * act_grad_from_out(act, srcout[o]);
-    gout[o] = accumulate ? gout[o] + g : g;
+    float r = accumulate ? gout[o] + g : g;
+    gout[o] = r;
+    f32_store_plane(hi, lo_off, o, r);
   }
 };
 struct EpiAtomic {     // dW += alpha*acc  (split-K)

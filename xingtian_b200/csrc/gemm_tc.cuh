@@ -4,14 +4,17 @@
 //
 // One warp-specialised kernel serves every conv / dense layer in forward, data-gradient and
 // weight-gradient form:
-//   warps 0-3 : producers.  Each operand tile is a 2-D array of 16-byte chunks [rows][chunks]
-//               gathered straight from the fp32 / uint8 tensors in global memory (im2col with
-//               the minibatch gather and uint8 decode folded in, transposed-conv gather, plain
-//               rows) and written to shared memory in the UMMA canonical no-swizzle layout.
-//               fp32 values are split on the fly into bf16 hi + bf16 lo ("bf16x3"): the tensor
-//               core computes hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM, which
-//               reproduces fp32 products to ~2^-17 -- the parity contract (1e-3) is met with
-//               margin while the math runs on tcgen05.  uint8 frames are exact in bf16 (no lo).
+//   warps 0-3 : producers.  Every tensor a GEMM consumes exists in HBM/L2 as two bf16 planes,
+//               hi = bf16(x) and lo = bf16(x - hi) ("bf16x3": the tensor core computes
+//               hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM, reproducing fp32 products to
+//               ~2^-17, so the 1e-3 parity contract is met with margin while the math runs on
+//               tcgen05).  The planes are written once by the kernel that produces the tensor
+//               (GEMM epilogues, the uint8 frame decode, the optimiser for the weights), so a
+//               producer thread only issues 16-byte cp.async copies (zero-filled where the im2col /
+//               transposed-conv window leaves the image) into the UMMA canonical no-swizzle layout
+//               and lets the copies arrive on the stage mbarrier asynchronously
+//               (cp.async.mbarrier.arrive.noinc): no conversion work, no register staging, many
+//               copies in flight per thread.  uint8 frames are exact in bf16 (no lo plane).
 //   warp 4    : allocates TMEM, issues the MMAs (one elected lane), tcgen05.commit -> mbarriers.
 //   warps 0-3 : epilogue after the K loop: tcgen05.ld (32 lanes x 16 columns per instruction),
 //               bias+activation / activation-gradient mask / split-K atomic accumulation.
@@ -63,6 +66,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
+// 16-byte async copy global -> shared, zero-filled when src_bytes == 0
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its prior cp.async have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -113,177 +124,161 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-// fp32 x8 -> bf16 hi (and residual lo) packed as 16-byte chunks
+// fp32 -> bf16 hi / residual lo
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-__device__ __forceinline__ void split8(const float v[8], uint4& hi, uint4& lo) {
-  float r[8];
-  uint32_t h[4], l[4];
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  hi = pack_bf16(a, b);
+  lo = pack_bf16(a - __bfloat162float(ha), b - __bfloat162float(hb));
+}
+// write 16 fp32 values as bf16 hi/lo planes (32 B each); hi_plane may be NULL (tensor has no TC consumer)
+__device__ __forceinline__ void store_planes16(__nv_bfloat16* hi_plane, long long lo_off, long long elem, const float v[16]) {
+  if (!hi_plane) return;
+  uint32_t h[8], l[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    __nv_bfloat16 b = __float2bfloat16_rn(v[i]);
-    r[i] = v[i] - __bfloat162float(b);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) { h[i] = pack_bf16(v[2 * i], v[2 * i + 1]); l[i] = pack_bf16(r[2 * i], r[2 * i + 1]); }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
+  for (int i = 0; i < 8; i++) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  uint4* ph = reinterpret_cast<uint4*>(hi_plane + elem);
+  uint4* pl = reinterpret_cast<uint4*>(hi_plane + lo_off + elem);
+  ph[0] = make_uint4(h[0], h[1], h[2], h[3]); ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  pl[0] = make_uint4(l[0], l[1], l[2], l[3]); pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+__device__ __forceinline__ void store_plane1(__nv_bfloat16* hi_plane, long long lo_off, long long elem, float x) {
+  if (!hi_plane) return;
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  hi_plane[elem] = h;
+  hi_plane[lo_off + elem] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
 // ------------------------------------------------------------------------------------------
-// Row-gather sources.  A source is a logical 2-D array [n_rows][n_cols] whose rows are gathered
-// independently and whose columns come in contiguous groups of 8.
-//   struct Row;  void init_row(int row, Row&) const;  void load8(const Row&, int col, float v[8]) const;
-// load8 must return zeros for row >= n_rows (Row::valid == 0); the caller guards col < n_cols.
+// Chunk sources.  A source is a logical 2-D array [n_rows][n_cols] of bf16 whose rows are gathered
+// independently and whose columns come in contiguous, 16-byte aligned groups of 8.
+//   struct Row;  void init_row(int row, Row&) const;
+//   const bf16* chunk(const Row&, int col) const;    -> hi-plane address of the 8 elements, or NULL = zeros
+//   lo plane address = hi address + lo_off;  any() = some valid address for zero-size copies
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void zero8(float v[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; i++) v[i] = 0.f;
-}
-__device__ __forceinline__ void ld8(const float* p, float v[8]) {
-  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void ld4(const float* p, float* v) {
-  float4 a = *reinterpret_cast<const float4*>(p);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-}
-__device__ __forceinline__ void ld4(const uint8_t* p, float* v) {
-  uchar4 a = *reinterpret_cast<const uchar4*>(p);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-}
-__device__ __forceinline__ void ld8(const uint8_t* p, float v[8]) {
-  uint2 a = *reinterpret_cast<const uint2*>(p);
-  v[0] = a.x & 0xff; v[1] = (a.x >> 8) & 0xff; v[2] = (a.x >> 16) & 0xff; v[3] = a.x >> 24;
-  v[4] = a.y & 0xff; v[5] = (a.y >> 8) & 0xff; v[6] = (a.y >> 16) & 0xff; v[7] = a.y >> 24;
-}
+typedef __nv_bfloat16 bf16;
 
-// plain rows: X[row(m)*ld + col], optional row gather.  Requires ld % 4 == 0 (fp32) / ld % 8 == 0 (u8).
-template <typename T>
+// plain rows: X[row(m)*ld + col], optional row gather.  ld % 8 == 0.
 struct SrcDense {
-  const T* x; const int32_t* idx; int ld; int n_rows;
+  const bf16* x; long long lo_off; const int32_t* idx; int ld; int n_rows;
   struct Row { long long base; int valid; };
+  __device__ __forceinline__ const bf16* any() const { return x; }
   __device__ __forceinline__ void init_row(int m, Row& r) const {
     r.valid = m < n_rows;
     r.base = r.valid ? (long long)(idx ? idx[m] : m) * ld : 0;
   }
-  __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
-    if (!r.valid) { zero8(v); return; }
-    ld8(x + r.base + col, v);
-  }
+  __device__ __forceinline__ const bf16* chunk(const Row& r, int col) const { return r.valid ? x + r.base + col : nullptr; }
 };
 
-// im2col rows: row = output position (b,oy,ox) [sample gathered through idx], col = (ky,kx,ci).
-// C is a power of two (cshift = log2 C).  C >= 8: a chunk is 8 channels of one pixel;  C == 4: a chunk is
-// 2 horizontally adjacent taps.  Column -> (ky,kx,ci) is decoded arithmetically (no table loads).
-template <typename T, bool PAD>
+// im2col rows: row = output position (b,oy,ox), col = (ky,kx,ci).  C is a power of two (cshift = log2 C).
+// C >= 8: a chunk is 8 channels of one tap;  C == 4: a chunk is 2 horizontally adjacent taps (KW, padL and the
+// stride are even so both taps are inside or both outside the image, and the 8 values are contiguous).
+template <bool PAD>
 struct SrcIm2col {
-  const T* x; const int32_t* idx; ConvGeom g; int cshift; int n_rows;
+  const bf16* x; long long lo_off; ConvGeom g; int cshift; int n_rows;
   struct Row { long long base; int iy0, ix0, valid; };
+  __device__ __forceinline__ const bf16* any() const { return x; }
   __device__ __forceinline__ void init_row(int m, Row& r) const {
     r.valid = m < n_rows;
     if (!r.valid) { r.base = 0; r.iy0 = r.ix0 = 0; return; }
     int b = m / g.P; int p = m - b * g.P; int oy = p / g.OW; int ox = p - oy * g.OW;
-    long long sb = idx ? idx[b] : b;
     r.iy0 = oy * g.S - g.padT; r.ix0 = ox * g.S - g.padL;
-    r.base = ((sb * g.H + r.iy0) * g.W + r.ix0) * g.C;
+    r.base = (((long long)b * g.H + r.iy0) * g.W + r.ix0) * g.C;
   }
-  // offset of tap `tap` (= ky*KW+kx) relative to the patch origin, or -1 when it falls in the padding
-  __device__ __forceinline__ int tap_off(const Row& r, int tap) const {
+  __device__ __forceinline__ const bf16* chunk(const Row& r, int col) const {
+    if (!r.valid) return nullptr;
+    int tap = col >> cshift, ci = col & (g.C - 1);
     int ky = tap / g.KW, kx = tap - ky * g.KW;
     if (PAD) {
       int iy = r.iy0 + ky, ix = r.ix0 + kx;
-      if ((unsigned)iy >= (unsigned)g.H || (unsigned)ix >= (unsigned)g.W) return -1;
+      if ((unsigned)iy >= (unsigned)g.H || (unsigned)ix >= (unsigned)g.W) return nullptr;
     }
-    return (ky * g.W + kx) << cshift;
-  }
-  __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
-    if (!r.valid) { zero8(v); return; }
-    int tap = col >> cshift, ci = col & (g.C - 1);
-    if (g.C == 4) {
-      int o0 = tap_off(r, tap), o1 = tap_off(r, tap + 1);
-      if (o0 >= 0) ld4(x + r.base + o0, v); else { v[0] = v[1] = v[2] = v[3] = 0.f; }
-      if (o1 >= 0) ld4(x + r.base + o1, v + 4); else { v[4] = v[5] = v[6] = v[7] = 0.f; }
-    } else {
-      int o = tap_off(r, tap);
-      if (o >= 0) ld8(x + r.base + o + ci, v); else zero8(v);
-    }
+    return x + r.base + ((ky * g.W + kx) << cshift) + ci;
   }
 };
 
 // transposed-conv gather: row = input position (b,iy,ix), col = (ky,kx,co); value = dY[b,oy,ox,co]
 // with oy=(iy+padT-ky)/S when divisible and in range.  Cout is a power of two >= 8 (oshift = log2 Cout).
 struct SrcDgrad {
-  const float* dy; ConvGeom g; int oshift; int sshift; int n_rows;
+  const bf16* dy; long long lo_off; ConvGeom g; int oshift; int sshift; int n_rows;
   struct Row { long long base; int iy0, ix0, valid; };
+  __device__ __forceinline__ const bf16* any() const { return dy; }
   __device__ __forceinline__ void init_row(int m, Row& r) const {
     r.valid = m < n_rows;
     if (!r.valid) { r.base = 0; r.iy0 = r.ix0 = 0; return; }
     int HW = g.H * g.W; int b = m / HW; int p = m - b * HW; int iy = p / g.W; int ix = p - iy * g.W;
     r.base = (long long)b * g.P * g.Cout; r.iy0 = iy + g.padT; r.ix0 = ix + g.padL;
   }
-  __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
-    if (!r.valid) { zero8(v); return; }
+  __device__ __forceinline__ const bf16* chunk(const Row& r, int col) const {
+    if (!r.valid) return nullptr;
     int tap = col >> oshift, co = col & (g.Cout - 1);
     int ky = tap / g.KW, kx = tap - ky * g.KW;
     int ty = r.iy0 - ky, tx = r.ix0 - kx;
     int mask = g.S - 1;
-    if (ty < 0 || tx < 0 || (ty & mask) || (tx & mask)) { zero8(v); return; }
+    if (ty < 0 || tx < 0 || (ty & mask) || (tx & mask)) return nullptr;
     int oy = ty >> sshift, ox = tx >> sshift;
-    if (oy >= g.OH || ox >= g.OW) { zero8(v); return; }
-    ld8(dy + r.base + (((long long)(oy * g.OW + ox)) << oshift) + co, v);
+    if (oy >= g.OH || ox >= g.OW) return nullptr;
+    return dy + r.base + (((long long)(oy * g.OW + ox)) << oshift) + co;
   }
 };
 
 // conv weights for the data gradient: row = ci, col = (ky,kx,co) -> W[ky,kx,ci,co]
 struct SrcWDgrad {
-  const float* w; int Cin, Cout, oshift; int n_rows;
+  const bf16* w; long long lo_off; int Cin, Cout, oshift; int n_rows;
   struct Row { int ci, valid; };
+  __device__ __forceinline__ const bf16* any() const { return w; }
   __device__ __forceinline__ void init_row(int m, Row& r) const { r.valid = m < n_rows; r.ci = m; }
-  __device__ __forceinline__ void load8(const Row& r, int col, float v[8]) const {
-    if (!r.valid) { zero8(v); return; }
+  __device__ __forceinline__ const bf16* chunk(const Row& r, int col) const {
+    if (!r.valid) return nullptr;
     int tap = col >> oshift, co = col & (Cout - 1);
-    ld8(w + ((long long)(tap * Cin + r.ci) << oshift) + co, v);
+    return w + ((long long)(tap * Cin + r.ci) << oshift) + co;
   }
 };
 
 // ------------------------------------------------------------------------------------------
-// Epilogues: store16(row m, first column n, 16 accumulators)
+// Epilogues: store16(row m, first column n, 16 accumulators).  Besides the fp32 tensor they keep the
+// bf16 hi/lo planes of the result current (hi == NULL when nothing on the tensor-core path reads it).
 // ------------------------------------------------------------------------------------------
 struct TcEpiBiasAct {
-  float* out; const float* bias; float alpha; int act; int ld; int M, N;
+  float* out; const float* bias; float alpha; int act; int ld; int M, N; bf16* hi; long long lo_off;
   __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
     if (m >= M) return;
-    float* o = out + (long long)m * ld + n0;
+    long long e = (long long)m * ld + n0;
+    float r[16];
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      if (n0 + j + 3 < N) {
-        float4 r;
-        r.x = act_apply(act, alpha * v[j] + bias[n0 + j]);
-        r.y = act_apply(act, alpha * v[j + 1] + bias[n0 + j + 1]);
-        r.z = act_apply(act, alpha * v[j + 2] + bias[n0 + j + 2]);
-        r.w = act_apply(act, alpha * v[j + 3] + bias[n0 + j + 3]);
-        *reinterpret_cast<float4*>(o + j) = r;
-      } else {
-        for (int t = 0; t < 4; t++)
-          if (n0 + j + t < N) o[j + t] = act_apply(act, alpha * v[j + t] + bias[n0 + j + t]);
-      }
+    for (int j = 0; j < 16; j++) r[j] = (n0 + j < N) ? act_apply(act, alpha * v[j] + bias[n0 + j]) : 0.f;
+    if (n0 + 15 < N) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + e + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      store_planes16(hi, lo_off, e, r);
+    } else {
+      for (int j = 0; j < 16; j++) if (n0 + j < N) { out[e + j] = r[j]; store_plane1(hi, lo_off, e + j, r[j]); }
     }
   }
 };
 struct TcEpiDgrad {
-  float* gout; const float* srcout; int act; int ld; int accumulate; int M, N;
+  float* gout; const float* srcout; int act; int ld; int accumulate; int M, N; bf16* hi; long long lo_off;
   __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
     if (m >= M) return;
-    long long o = (long long)m * ld + n0;
+    long long e = (long long)m * ld + n0;
+    float r[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
+      r[j] = 0.f;
       if (n0 + j < N) {
-        float gq = v[j] * act_grad_from_out(act, srcout[o + j]);
-        gout[o + j] = accumulate ? gout[o + j] + gq : gq;
+        float gq = v[j] * act_grad_from_out(act, srcout[e + j]);
+        r[j] = accumulate ? gout[e + j] + gq : gq;
       }
+    }
+    if (n0 + 15 < N) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(gout + e + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      store_planes16(hi, lo_off, e, r);
+    } else {
+      for (int j = 0; j < 16; j++) if (n0 + j < N) { gout[e + j] = r[j]; store_plane1(hi, lo_off, e + j, r[j]); }
     }
   }
 };
@@ -312,7 +307,7 @@ struct TcEpiAtomic {
 //   A_MN / B_MN : operand is MN-major (its tile rows are the K entity) instead of K-major.
 //   KT          : reduction elements per pipeline stage (multiple of 16)
 //   NT          : N tile (16..256, multiple of 16) = UMMA N
-//   A_SPLIT / B_SPLIT : operand carries a bf16 residual (bf16x3); false = exact in bf16
+//   A_SPLIT / B_SPLIT : operand carries a bf16 residual plane (bf16x3); false = exact in bf16
 // grid = (ceil(Mext/128), ceil(Next/NT), ksplit);  block = 160 threads
 // ------------------------------------------------------------------------------------------
 constexpr int TC_THREADS = 160;
@@ -327,59 +322,39 @@ struct TcCfg {
   static constexpr int A_BYTES = A_ROWS * A_CHUNKS * 16;
   static constexpr int B_BYTES = B_ROWS * B_CHUNKS * 16;
   static constexpr int STAGE_BYTES = A_BYTES * (A_SPLIT ? 2 : 1) + B_BYTES * (B_SPLIT ? 2 : 1);
-  static constexpr int STAGES = (STAGE_BYTES * 3 <= 96 * 1024) ? 3 : 2;
+  static constexpr int STAGES = (STAGE_BYTES * 4 <= 100 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 100 * 1024) ? 3 : 2);
   static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + 1024;
   static constexpr int TMEM_COLS = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));
 };
 
 template <int ROWS, int CHUNKS, bool MN, bool SPLIT, class SRC>
-__device__ __forceinline__ void produce_tile(const SRC& src, uint8_t* hi, uint8_t* lo, int mn0, int k0,
+__device__ __forceinline__ void produce_tile(const SRC& src, uint32_t hi_smem, uint32_t lo_smem, int mn0, int k0,
                                              int mn_ext, int k_end, int tid) {
   // slot s -> (row = s % ROWS, chunk = s / ROWS); K-major: row is an MN entity (mn0+row), chunk along K
   // (k0+8*chunk); MN-major: row is a K entity (k0+row), chunk along MN (mn0+8*chunk).
-  // Loads of U slots are issued back to back before any conversion so that U independent global loads are
-  // in flight per thread (the gather is latency bound otherwise).
   constexpr int SLOTS = ROWS * CHUNKS;
   static_assert(SLOTS % TC_PRODUCERS == 0, "tile slots must tile the producer threads");
   constexpr int PER = SLOTS / TC_PRODUCERS;
-  constexpr int U = PER >= 8 ? 8 : PER;
-  static_assert(PER % U == 0, "slots per thread must be a multiple of the load batch");
   const int row_lim = MN ? k_end : mn_ext;
   const int col_lim = MN ? mn_ext : k_end;
   typename SRC::Row row;
   int cur_row = -1;
-#pragma unroll 1
-  for (int i0 = 0; i0 < PER; i0 += U) {
-    float v[U][8];
+  const bf16* dummy = src.any();
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      int s = tid + (i0 + u) * TC_PRODUCERS;
-      int r = s % ROWS, c = s / ROWS;
-      int grow = MN ? k0 + r : mn0 + r;
-      int gcol = MN ? mn0 + 8 * c : k0 + 8 * c;
-      if (r != cur_row) {
-        src.init_row(grow, row);
-        if (grow >= row_lim) row.valid = 0;
-        cur_row = r;
-      }
-      if (gcol < col_lim) src.load8(row, gcol, v[u]); else zero8(v[u]);
+  for (int i = 0; i < PER; i++) {
+    int s = tid + i * TC_PRODUCERS;
+    int r = s % ROWS, c = s / ROWS;
+    int grow = MN ? k0 + r : mn0 + r;
+    int gcol = MN ? mn0 + 8 * c : k0 + 8 * c;
+    if (r != cur_row) {
+      src.init_row(grow, row);
+      if (grow >= row_lim) row.valid = 0;
+      cur_row = r;
     }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      int s = tid + (i0 + u) * TC_PRODUCERS;
-      int r = s % ROWS, c = s / ROWS;
-      uint32_t off = (uint32_t)c * ROWS * 16 + (uint32_t)r * 16;
-      if (SPLIT) {
-        uint4 h, l;
-        split8(v[u], h, l);
-        *reinterpret_cast<uint4*>(hi + off) = h;
-        *reinterpret_cast<uint4*>(lo + off) = l;
-      } else {
-        uint4 h = make_uint4(pack_bf16(v[u][0], v[u][1]), pack_bf16(v[u][2], v[u][3]), pack_bf16(v[u][4], v[u][5]),
-                             pack_bf16(v[u][6], v[u][7]));
-        *reinterpret_cast<uint4*>(hi + off) = h;
-      }
-    }
+    const bf16* p = (gcol < col_lim) ? src.chunk(row, gcol) : nullptr;
+    uint32_t off = (uint32_t)c * ROWS * 16 + (uint32_t)r * 16;
+    cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
+    if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
   }
 }
 
@@ -389,7 +364,6 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   using Cfg = TcCfg<NT, KT, A_MN, B_MN, A_SPLIT, B_SPLIT>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte aligned carve-up
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
   __shared__ uint32_t tmem_slot;
@@ -411,21 +385,21 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
 
   if (warp < 4) {
-    // ================= producers =================
+    // ================= producers: asynchronous 16-byte copies, completion signalled on the stage barrier ====
     int stage = 0; uint32_t phase = 0;
     for (int t = 0; t < n_tiles; t++) {
       mbar_wait(empty0 + 8 * stage, phase ^ 1);
-      uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-      uint8_t* sa_lo = sa + Cfg::A_BYTES;
-      uint8_t* sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
-      uint8_t* sb_lo = sb + Cfg::B_BYTES;
+      uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+      uint32_t sa_lo = sa + Cfg::A_BYTES;
+      uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
+      uint32_t sb_lo = sb + Cfg::B_BYTES;
       int k0 = kbeg + t * KT;
       produce_tile<Cfg::A_ROWS, Cfg::A_CHUNKS, A_MN, A_SPLIT>(asrc, sa, sa_lo, m0, k0, m_ext, kend, tid);
       produce_tile<Cfg::B_ROWS, Cfg::B_CHUNKS, B_MN, B_SPLIT>(bsrc, sb, sb_lo, n0, k0, n_ext, kend, tid);
-      fence_proxy_async();
-      mbar_arrive(full0 + 8 * stage);
+      cp_async_mbar_arrive_noinc(full0 + 8 * stage);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
     // ================= epilogue =================
@@ -443,7 +417,6 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   } else {
     // ================= MMA issuer =================
     constexpr uint32_t IDESC = make_idesc(NT, A_MN, B_MN);
-    // per-k-step descriptor geometry (bytes)
     constexpr uint32_t A_LBO = A_MN ? 128 : Cfg::A_ROWS * 16, A_SBO = A_MN ? Cfg::A_ROWS * 16 : 128;
     constexpr uint32_t B_LBO = B_MN ? 128 : Cfg::B_ROWS * 16, B_SBO = B_MN ? Cfg::B_ROWS * 16 : 128;
     constexpr uint32_t A_KSTEP = A_MN ? 256 : 2 * Cfg::A_ROWS * 16;   // advance of one K=16 step
@@ -451,9 +424,10 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
     int stage = 0; uint32_t phase = 0;
     for (int t = 0; t < n_tiles; t++) {
       mbar_wait(full0 + 8 * stage, phase);
-      tc_fence_after();
       if (lane == 0) {
-        uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        fence_proxy_async();      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+        tc_fence_after();
+        uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         uint32_t sa_lo = sa + Cfg::A_BYTES;
         uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
         uint32_t sb_lo = sb + Cfg::B_BYTES;
@@ -478,6 +452,47 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// plane maintenance kernels
+// ------------------------------------------------------------------------------------------
+// fp32 -> bf16 hi / lo planes (weights after an optimiser step or set_weights; any fp32 tensor)
+__global__ void split_planes_kernel(const float* __restrict__ src, bf16* __restrict__ hi, long long lo_off, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(src + i);
+    uint32_t h0, l0, h1, l1;
+    split2(v.x, v.y, h0, l0); split2(v.z, v.w, h1, l1);
+    *reinterpret_cast<uint2*>(hi + i) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(hi + lo_off + i) = make_uint2(l0, l1);
+  } else {
+    for (long long j = i; j < n; j++) store_plane1(hi, lo_off, j, src[j]);
+  }
+}
+// uint8 frame decode with the minibatch gather folded in: dst[b, :] = bf16(obs[idx[b], :])   (exact)
+__global__ void decode_u8_kernel(const uint8_t* __restrict__ obs, const int32_t* __restrict__ idx, int per_sample,
+                                 bf16* __restrict__ dst) {
+  int b = blockIdx.y;
+  long long srow = idx ? idx[b] : b;
+  const uint8_t* s = obs + srow * per_sample;
+  bf16* d = dst + (long long)b * per_sample;
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i + 15 < per_sample) {
+    uint4 v = *reinterpret_cast<const uint4*>(s + i);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      o[2 * q] = pack_bf16((float)(w[q] & 0xff), (float)((w[q] >> 8) & 0xff));
+      o[2 * q + 1] = pack_bf16((float)((w[q] >> 16) & 0xff), (float)(w[q] >> 24));
+    }
+    uint4* dp = reinterpret_cast<uint4*>(d + i);
+    dp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  } else {
+    for (int j = i; j < per_sample; j++) d[j] = __float2bfloat16_rn((float)s[j]);
   }
 }
 

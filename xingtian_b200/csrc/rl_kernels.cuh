@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gemm_f32.cuh"
+
 namespace xtb {
 
 constexpr int MAX_ADIM = 32;
@@ -394,6 +396,7 @@ __global__ void dqn_loss_kernel(const float* __restrict__ q, const float* __rest
 struct PpoHeadsArgs {
   const float* h_pi; const float* h_v;     // [B,K] hidden activations (may alias)
   float* g_pi; float* g_v;                 // [B,K] gradient wrt hidden pre-activation (may alias)
+  __nv_bfloat16* gp_hi; long long gp_lo; __nv_bfloat16* gv_hi; long long gv_lo;   // their bf16 planes
   const float* w_pi; const float* b_pi; const float* w_v; const float* b_v;
   float* dw_pi; float* db_pi; float* dw_v; float* db_v;
   const int32_t* idx; const int32_t* action; const float* old_logp; const float* adv; const float* old_v; const float* target_v;
@@ -503,11 +506,14 @@ __global__ void __launch_bounds__(256) ppo_heads_kernel(PpoHeadsArgs a) {
         for (int i = 0; i < HEAD_AMAX; i++) { dwp[j][i] = fmaf(hp_[j], dl[i], dwp[j][i]); gp = fmaf(dl[i], wpi[j][i], gp); }
         dwv[j] = fmaf(hv_[j], dv, dwv[j]);
         float gv = dv * wv[j];
+        long long eo = (long long)b * K + k;
         if (a.shared) {
-          a.g_pi[(long long)b * K + k] = (gp + gv) * act_grad_from_out(a.act_pi, hp_[j]);
+          float r = (gp + gv) * act_grad_from_out(a.act_pi, hp_[j]);
+          a.g_pi[eo] = r; f32_store_plane(a.gp_hi, a.gp_lo, eo, r);
         } else {
-          a.g_pi[(long long)b * K + k] = gp * act_grad_from_out(a.act_pi, hp_[j]);
-          a.g_v[(long long)b * K + k] = gv * act_grad_from_out(a.act_v, hv_[j]);
+          float r1 = gp * act_grad_from_out(a.act_pi, hp_[j]), r2 = gv * act_grad_from_out(a.act_v, hv_[j]);
+          a.g_pi[eo] = r1; f32_store_plane(a.gp_hi, a.gp_lo, eo, r1);
+          a.g_v[eo] = r2; f32_store_plane(a.gv_hi, a.gv_lo, eo, r2);
         }
       }
     }

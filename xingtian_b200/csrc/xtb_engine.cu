@@ -85,7 +85,12 @@ struct xtb_net {
   std::vector<int> tsize;       // per tensor floats/sample (0 = obs)
   long long n_params = 0;
   size_t ws_bytes = 0;
-  std::vector<size_t> out_off, gout_off;  // byte offsets in workspace per tensor
+  std::vector<size_t> out_off, gout_off;  // byte offsets in workspace per tensor (fp32)
+  std::vector<size_t> ohi_off, ghi_off;   // byte offsets of the bf16 hi planes (lo plane follows at plane_elems)
+  std::vector<long long> plane_elems;     // elements per bf16 plane of tensor t (max_batch*tsize rounded to 8)
+  size_t obs_hi_off = 0, w_hi_off = 0;    // decoded-frame plane, weight planes
+  long long w_plane_elems = 0;
+  bool gout_planes_fresh = false;         // set while a caller guarantees head-gradient planes are current
   float* params = nullptr; float* grads = nullptr; char* ws = nullptr;
 };
 
@@ -188,11 +193,22 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
   size_t w = 0;
   net->out_off.assign(desc->n_layers + 1, 0);
   net->gout_off.assign(desc->n_layers + 1, 0);
+  net->ohi_off.assign(desc->n_layers + 1, 0);
+  net->ghi_off.assign(desc->n_layers + 1, 0);
+  net->plane_elems.assign(desc->n_layers + 1, 0);
   for (int t = 1; t <= desc->n_layers; t++) {
     size_t bytes = align_up((size_t)max_batch * net->tsize[t] * sizeof(float), 256);
     net->out_off[t] = w; w += bytes;
     net->gout_off[t] = w; w += bytes;
+    long long pe = (long long)align_up((size_t)max_batch * net->tsize[t], 128);
+    net->plane_elems[t] = pe;
+    size_t pbytes = align_up((size_t)pe * 2 * sizeof(uint16_t), 256);   // hi + lo
+    net->ohi_off[t] = w; w += pbytes;
+    net->ghi_off[t] = w; w += pbytes;
   }
+  net->obs_hi_off = w; w += align_up((size_t)max_batch * net->tsize[0] * sizeof(uint16_t), 256);
+  net->w_plane_elems = (long long)align_up((size_t)net->n_params, 128);
+  net->w_hi_off = w; w += align_up((size_t)net->w_plane_elems * 2 * sizeof(uint16_t), 256);
   net->ws_bytes = w;
   *out = net;
   return XTB_OK;
@@ -226,11 +242,12 @@ extern "C" int xtb_net_tensor_size(const xtb_net* net, int t) {
 
 extern "C" size_t xtb_net_workspace_bytes(const xtb_net* net) { return net ? net->ws_bytes : 0; }
 
+extern "C" int xtb_net_sync_weights(xtb_net* net, void* stream);
 extern "C" int xtb_net_bind(xtb_net* net, float* params, float* grads, void* workspace, size_t workspace_bytes) {
   if (!net || !params || !workspace) return fail(XTB_ERR_ARG, "xtb_net_bind: null pointer");
   if (workspace_bytes < net->ws_bytes) return fail(XTB_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, net->ws_bytes);
   net->params = params; net->grads = grads; net->ws = (char*)workspace;
-  return XTB_OK;
+  return xtb_net_sync_weights(net, nullptr);
 }
 
 extern "C" float* xtb_net_tensor(xtb_net* net, int t) {
@@ -290,109 +307,132 @@ static int g_tc_mode = [] { const char* e = getenv("XTB_TC"); return e ? atoi(e)
 extern "C" int xtb_set_tc_mode(int mode) { g_tc_mode = mode; return XTB_OK; }
 extern "C" int xtb_get_tc_mode(void) { return g_tc_mode; }
 
+struct Planes { tc::bf16* hi; long long lo_off; };   // lo plane = hi + lo_off (elements)
+static inline Planes out_planes(const xtb_net* n, int t) { return Planes{(tc::bf16*)(n->ws + n->ohi_off[t]), n->plane_elems[t]}; }
+static inline Planes gout_planes(const xtb_net* n, int t) { return Planes{(tc::bf16*)(n->ws + n->ghi_off[t]), n->plane_elems[t]}; }
+static inline Planes obs_planes(const xtb_net* n) { return Planes{(tc::bf16*)(n->ws + n->obs_hi_off), 0}; }
+static inline Planes w_planes(const xtb_net* n) { return Planes{(tc::bf16*)(n->ws + n->w_hi_off), n->w_plane_elems}; }
+
+// bias + activation after a split-K forward (fp32 sums are already in `out`), planes kept current
 __global__ void bias_act_kernel(float* __restrict__ out, const float* __restrict__ bias, long long total, int N,
-                                float alpha, int act) {
+                                float alpha, int act, tc::bf16* hi, long long lo_off) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) out[i] = act_apply(act, alpha * out[i] + bias[i % N]);
+  if (i < total) {
+    float r = act_apply(act, alpha * out[i] + bias[i % N]);
+    out[i] = r;
+    tc::store_plane1(hi, lo_off, i, r);
+  }
 }
 
-static bool tc_conv_ok(const LayerPlan& lp) {
-  return g_tc_mode && lp.cshift >= 2 && lp.N % 8 == 0 && lp.N <= 64 && lp.K % 8 == 0;
+// first-layer convs read the decoded uint8 frames: 2 taps per 16-byte chunk need even geometry
+static bool tc_conv_ok(const xtb_net* net, const LayerPlan& lp) {
+  if (!g_tc_mode || lp.d.kind != XTB_CONV || lp.N % 8 || lp.N > 64 || lp.K % 8) return false;
+  if (lp.d.src == 0) {
+    if (!net->desc.input_u8 || lp.cshift != 2) return false;
+    return lp.g.KW % 2 == 0 && lp.g.padL % 2 == 0 && lp.g.S % 2 == 0 && lp.g.W % 2 == 0;
+  }
+  return lp.cshift >= 3;
 }
-static bool tc_dense_ok(const LayerPlan& lp) { return g_tc_mode && lp.K % 8 == 0 && lp.N % 8 == 0 && lp.K >= 64 && lp.N >= 16; }
+static bool tc_dense_ok(const LayerPlan& lp) {
+  return g_tc_mode && lp.d.kind == XTB_DENSE && lp.d.src != 0 && lp.K % 8 == 0 && lp.N % 8 == 0 && lp.K >= 64 && lp.N >= 16;
+}
+static bool tc_conv_dgrad_ok(const LayerPlan& lp) {
+  return g_tc_mode && lp.d.kind == XTB_CONV && lp.d.src != 0 && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.oshift >= 3;
+}
 
-template <typename T, bool PAD>
-static cudaError_t tc_conv_fwd_t(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
-                                 float alpha, float* out, int B, cudaStream_t st) {
+template <bool PAD>
+static cudaError_t tc_conv_fwd_t(const LayerPlan& lp, Planes x, bool x_split, Planes w, const float* b, float alpha,
+                                 float* out, Planes po, int B, cudaStream_t st) {
   int M = B * lp.g.P;
-  tc::SrcIm2col<T, PAD> a{x, idx, lp.g, lp.cshift, M};
-  tc::SrcDense<float> bs{w, nullptr, lp.N, lp.K};
-  tc::TcEpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, M, lp.N};
-  constexpr bool AS = !std::is_same<T, uint8_t>::value;
-  if (lp.N <= 16) return tc::launch_tc<16, 64, false, true, AS, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
-  if (lp.N <= 32) return tc::launch_tc<32, 64, false, true, AS, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
-  return tc::launch_tc<64, 64, false, true, AS, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
-}
-template <typename T>
-static cudaError_t tc_conv_fwd(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
-                               float alpha, float* out, int B, cudaStream_t st) {
-  return lp.pad ? tc_conv_fwd_t<T, true>(lp, x, idx, w, b, alpha, out, B, st)
-                : tc_conv_fwd_t<T, false>(lp, x, idx, w, b, alpha, out, B, st);
+  tc::SrcIm2col<PAD> a{x.hi, x.lo_off, lp.g, lp.cshift, M};
+  tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K};
+  tc::TcEpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, M, lp.N, po.hi, po.lo_off};
+  if (x_split) {
+    if (lp.N <= 16) return tc::launch_tc<16, 64, false, true, true, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+    if (lp.N <= 32) return tc::launch_tc<32, 64, false, true, true, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+    return tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+  }
+  if (lp.N <= 16) return tc::launch_tc<16, 64, false, true, false, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+  if (lp.N <= 32) return tc::launch_tc<32, 64, false, true, false, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+  return tc::launch_tc<64, 64, false, true, false, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
 }
 
-static cudaError_t tc_dense_fwd(const LayerPlan& lp, const float* x, const float* w, const float* b, float* out,
-                                int B, cudaStream_t st) {
-  tc::SrcDense<float> a{x, nullptr, lp.K, B};
-  tc::SrcDense<float> bs{w, nullptr, lp.N, lp.K};
-  int nt = 64;
-  long long ctas = (long long)((B + 127) / 128) * ((lp.N + nt - 1) / nt);
+static cudaError_t tc_dense_fwd(const LayerPlan& lp, Planes x, Planes w, const float* b, float* out, Planes po, int B,
+                                cudaStream_t st) {
+  tc::SrcDense a{x.hi, x.lo_off, nullptr, lp.K, B};
+  tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K};
+  long long ctas = (long long)((B + 127) / 128) * ((lp.N + 63) / 64);
   int ks = lp.K >= 1024 ? tc::pick_ksplit(ctas, lp.K, 64, 148) : 1;
-  if (ks > 1) {   // split-K: atomics into a zeroed buffer, then bias + activation in place
+  if (ks > 1) {   // split-K: atomics into a zeroed buffer, then bias + activation (+ planes) in place
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * lp.N * sizeof(float), st);
     if (e != cudaSuccess) return e;
     tc::TcEpiAtomic ep{out, 1.f, lp.N, B, lp.N};
-    e = nt == 64 ? tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, ks, st)
-                 : tc::launch_tc<256, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, ks, st);
+    e = tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, ks, st);
     if (e != cudaSuccess) return e;
     long long total = (long long)B * lp.N;
-    bias_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, b, total, lp.N, 1.f, lp.d.act);
+    bias_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, b, total, lp.N, 1.f, lp.d.act, po.hi, po.lo_off);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaPeekAtLastError();
   }
-  tc::TcEpiBiasAct ep{out, b, 1.f, lp.d.act, lp.N, B, lp.N};
-  return nt == 64 ? tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, 1, st)
-                  : tc::launch_tc<256, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, 1, st);
+  tc::TcEpiBiasAct ep{out, b, 1.f, lp.d.act, lp.N, B, lp.N, po.hi, po.lo_off};
+  return tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, 1, st);
 }
 
-template <typename T, bool PAD>
-static cudaError_t tc_conv_wgrad_t(const LayerPlan& lp, const T* x, const int32_t* idx, const float* dy, float alpha,
-                                   float* dw, int B, cudaStream_t st) {
+template <bool PAD>
+static cudaError_t tc_conv_wgrad_t(const LayerPlan& lp, Planes x, bool x_split, Planes dy, float alpha, float* dw, int B,
+                                   cudaStream_t st) {
   int Mr = B * lp.g.P;
-  tc::SrcIm2col<T, PAD> a{x, idx, lp.g, lp.cshift, Mr};
-  tc::SrcDense<float> bs{dy, nullptr, lp.N, Mr};
+  tc::SrcIm2col<PAD> a{x.hi, x.lo_off, lp.g, lp.cshift, Mr};
+  tc::SrcDense bs{dy.hi, dy.lo_off, nullptr, lp.N, Mr};
   tc::TcEpiAtomic ep{dw, alpha, lp.N, lp.K, lp.N};
-  constexpr bool AS = !std::is_same<T, uint8_t>::value;
   long long ctas = (long long)((lp.K + 127) / 128);
   int ks = tc::pick_ksplit(ctas, Mr, 64, 148);
-  if (lp.N <= 16) return tc::launch_tc<16, 64, true, true, AS, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
-  if (lp.N <= 32) return tc::launch_tc<32, 64, true, true, AS, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
-  return tc::launch_tc<64, 64, true, true, AS, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
-}
-template <typename T>
-static cudaError_t tc_conv_wgrad(const LayerPlan& lp, const T* x, const int32_t* idx, const float* dy, float alpha,
-                                 float* dw, int B, cudaStream_t st) {
-  return lp.pad ? tc_conv_wgrad_t<T, true>(lp, x, idx, dy, alpha, dw, B, st)
-                : tc_conv_wgrad_t<T, false>(lp, x, idx, dy, alpha, dw, B, st);
+  if (x_split) {
+    if (lp.N <= 16) return tc::launch_tc<16, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
+    if (lp.N <= 32) return tc::launch_tc<32, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
+    return tc::launch_tc<64, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
+  }
+  if (lp.N <= 16) return tc::launch_tc<16, 64, true, true, false, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
+  if (lp.N <= 32) return tc::launch_tc<32, 64, true, true, false, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
+  return tc::launch_tc<64, 64, true, true, false, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
 }
 
-static cudaError_t tc_dense_wgrad(const LayerPlan& lp, const float* x, const float* dy, float* dw, int B, cudaStream_t st) {
-  tc::SrcDense<float> a{x, nullptr, lp.K, B};
-  tc::SrcDense<float> bs{dy, nullptr, lp.N, B};
+static cudaError_t tc_dense_wgrad(const LayerPlan& lp, Planes x, Planes dy, float* dw, int B, cudaStream_t st) {
+  tc::SrcDense a{x.hi, x.lo_off, nullptr, lp.K, B};
+  tc::SrcDense bs{dy.hi, dy.lo_off, nullptr, lp.N, B};
   tc::TcEpiAtomic ep{dw, 1.f, lp.N, lp.K, lp.N};
-  int nt = 64;
-  long long ctas = (long long)((lp.K + 127) / 128) * ((lp.N + nt - 1) / nt);
+  long long ctas = (long long)((lp.K + 127) / 128) * ((lp.N + 63) / 64);
   int ks = tc::pick_ksplit(ctas, B, 64, 148);
-  return nt == 64 ? tc::launch_tc<64, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st)
-                  : tc::launch_tc<256, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st);
+  return tc::launch_tc<64, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st);
 }
 
-static cudaError_t tc_conv_dgrad(const LayerPlan& lp, const float* dy, const float* w, float* gsrc, const float* xsrc,
-                                 int acc, int B, cudaStream_t st) {
+static cudaError_t tc_conv_dgrad(const LayerPlan& lp, Planes dy, Planes w, float* gsrc, const float* xsrc, Planes pg, int acc,
+                                 int B, cudaStream_t st) {
   int M = B * lp.g.H * lp.g.W;
-  tc::SrcDgrad a{dy, lp.g, lp.oshift, lp.sshift, M};
-  tc::SrcWDgrad bs{w, lp.g.C, lp.N, lp.oshift, lp.g.C};
-  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc, M, lp.g.C};
+  tc::SrcDgrad a{dy.hi, dy.lo_off, lp.g, lp.oshift, lp.sshift, M};
+  tc::SrcWDgrad bs{w.hi + lp.w_off, w.lo_off, lp.g.C, lp.N, lp.oshift, lp.g.C};
+  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc, M, lp.g.C, pg.hi, pg.lo_off};
   if (lp.g.C <= 16) return tc::launch_tc<16, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
   if (lp.g.C <= 32) return tc::launch_tc<32, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
   return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
 }
 
-static cudaError_t tc_dense_dgrad(const LayerPlan& lp, const float* dy, const float* w, float* gsrc, const float* xsrc,
-                                  int acc, int B, cudaStream_t st) {
-  tc::SrcDense<float> a{dy, nullptr, lp.N, B};
-  tc::SrcDense<float> bs{w, nullptr, lp.N, lp.K};          // rows = kw (N' entity), cols = n (K')
-  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc, B, lp.K};
+static cudaError_t tc_dense_dgrad(const LayerPlan& lp, Planes dy, Planes w, float* gsrc, const float* xsrc, Planes pg, int acc,
+                                  int B, cudaStream_t st) {
+  tc::SrcDense a{dy.hi, dy.lo_off, nullptr, lp.N, B};
+  tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K};          // rows = kw (N' entity), cols = n (K')
+  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc, B, lp.K, pg.hi, pg.lo_off};
   return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, B, lp.K, lp.N, 1, st);
+}
+
+// keep the bf16 hi/lo planes of the bound parameters current (after an optimiser step / set_weights)
+extern "C" int xtb_net_sync_weights(xtb_net* net, void* stream) {
+  if (!net || !net->ws || !net->params) return fail(XTB_ERR_STATE, "xtb_net_sync_weights: net not bound");
+  Planes w = w_planes(net);
+  long long n = net->n_params;
+  tc::split_planes_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, S(stream)>>>(net->params, w.hi, w.lo_off, n);
+  LAUNCH_CHECK();
+  return XTB_OK;
 }
 
 // Self-test of the three operand-major combinations on plain matrices (see tests/test_gpu_tc.py):
@@ -404,42 +444,53 @@ extern "C" int xtb_tc_gemm_test(int mode, const float* a, const float* b, float*
   if (!a || !b || !c || M <= 0 || N <= 0 || K <= 0) return fail(XTB_ERR_ARG, "xtb_tc_gemm_test: bad argument");
   if (M % 8 || N % 8 || K % 8) return fail(XTB_ERR_ARG, "xtb_tc_gemm_test: sizes must be multiples of 8");
   cudaStream_t st = S(stream);
+  long long na = (long long)M * K, nb = (long long)N * K;
+  tc::bf16 *pa = nullptr, *pb = nullptr;
+  CUDA_TRY(cudaMalloc(&pa, 2 * na * sizeof(tc::bf16)));
+  CUDA_TRY(cudaMalloc(&pb, 2 * nb * sizeof(tc::bf16)));
+  tc::split_planes_kernel<<<(unsigned)((na / 4 + 255) / 256 + 1), 256, 0, st>>>(a, pa, na, na);
+  tc::split_planes_kernel<<<(unsigned)((nb / 4 + 255) / 256 + 1), 256, 0, st>>>(b, pb, nb, nb);
   cudaError_t e;
+  tc::SrcDense as{pa, na, nullptr, mode == 2 ? M : K, mode == 2 ? K : M};
+  tc::SrcDense bs{pb, nb, nullptr, mode == 1 ? K : N, mode == 1 ? N : K};
   if (ksplit > 1) {
     CUDA_TRY(cudaMemsetAsync(c, 0, (size_t)M * N * sizeof(float), st));
     tc::TcEpiAtomic ep{c, 1.f, N, M, N};
-    if (mode == 0) { tc::SrcDense<float> as{a, nullptr, K, M}, bs{b, nullptr, N, K}; e = tc::launch_tc<64, 64, false, true, true, true>(as, bs, ep, M, N, K, ksplit, st); }
-    else if (mode == 1) { tc::SrcDense<float> as{a, nullptr, K, M}, bs{b, nullptr, K, N}; e = tc::launch_tc<64, 64, false, false, true, true>(as, bs, ep, M, N, K, ksplit, st); }
-    else { tc::SrcDense<float> as{a, nullptr, M, K}, bs{b, nullptr, N, K}; e = tc::launch_tc<64, 64, true, true, true, true>(as, bs, ep, M, N, K, ksplit, st); }
+    if (mode == 0) e = tc::launch_tc<64, 64, false, true, true, true>(as, bs, ep, M, N, K, ksplit, st);
+    else if (mode == 1) e = tc::launch_tc<64, 64, false, false, true, true>(as, bs, ep, M, N, K, ksplit, st);
+    else e = tc::launch_tc<64, 64, true, true, true, true>(as, bs, ep, M, N, K, ksplit, st);
   } else {
     tc::TcEpiStore ep{c, N, M, N};
-    if (mode == 0) { tc::SrcDense<float> as{a, nullptr, K, M}, bs{b, nullptr, N, K}; e = tc::launch_tc<32, 64, false, true, true, true>(as, bs, ep, M, N, K, 1, st); }
-    else if (mode == 1) { tc::SrcDense<float> as{a, nullptr, K, M}, bs{b, nullptr, K, N}; e = tc::launch_tc<32, 64, false, false, true, true>(as, bs, ep, M, N, K, 1, st); }
-    else { tc::SrcDense<float> as{a, nullptr, M, K}, bs{b, nullptr, N, K}; e = tc::launch_tc<32, 64, true, true, true, true>(as, bs, ep, M, N, K, 1, st); }
+    if (mode == 0) e = tc::launch_tc<32, 64, false, true, true, true>(as, bs, ep, M, N, K, 1, st);
+    else if (mode == 1) e = tc::launch_tc<32, 64, false, false, true, true>(as, bs, ep, M, N, K, 1, st);
+    else e = tc::launch_tc<32, 64, true, true, true, true>(as, bs, ep, M, N, K, 1, st);
   }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_launches.fetch_add(3, std::memory_order_relaxed);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  cudaFree(pa); cudaFree(pb);
   if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "tc gemm launch: %s", cudaGetErrorString(e));
+  if (e2 != cudaSuccess) return fail(XTB_ERR_CUDA, "tc gemm run: %s", cudaGetErrorString(e2));
   return XTB_OK;
 }
 
 // ------------------------------------------------------------------------------------------
-// forward / backward
+// fp32 CUDA-core layer ops
 // ------------------------------------------------------------------------------------------
 template <typename T>
 static void conv_fwd(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
-                     float alpha, float* out, int B, cudaStream_t st) {
+                     float alpha, float* out, Planes po, int B, cudaStream_t st) {
   int M = B * lp.g.P;
   BRowMajor bl{w, lp.N};
-  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N};
+  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, po.hi, po.lo_off};
   if (lp.pad) { AIm2col<T, true> al{x, idx, lp.g, lp.koff, lp.kyx}; launch_gemm(al, bl, ep, M, lp.N, lp.K, false, st); }
   else { AIm2col<T, false> al{x, idx, lp.g, lp.koff, lp.kyx}; launch_gemm(al, bl, ep, M, lp.N, lp.K, false, st); }
 }
 template <typename T>
 static void dense_fwd(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
-                      float alpha, float* out, int B, cudaStream_t st) {
+                      float alpha, float* out, Planes po, int B, cudaStream_t st) {
   ADense<T> al{x, idx, lp.K};
   BRowMajor bl{w, lp.N};
-  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N};
+  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, po.hi, po.lo_off};
   launch_gemm(al, bl, ep, B, lp.N, lp.K, false, st);
 }
 template <typename T>
@@ -449,7 +500,7 @@ static void conv_wgrad(const LayerPlan& lp, const T* x, const int32_t* idx, cons
   BRowMajor bl{dy, lp.N};
   EpiAtomic ep{dw, alpha, lp.N};
   // rows 0..K-1 scaled by alpha (input decode scale); the bias row (K) must not be scaled:
-  // handled by launching it as part of the same GEMM only when alpha == 1, else separately.
+  // it rides in the same GEMM only when alpha == 1, else colsum_kernel computes it.
   if (lp.pad) { AIm2colT<T, true> al{x, idx, lp.g, lp.koff, lp.kyx, Mr}; launch_gemm(al, bl, ep, lp.K + (alpha == 1.f ? 1 : 0), lp.N, Mr, true, st); }
   else { AIm2colT<T, false> al{x, idx, lp.g, lp.koff, lp.kyx, Mr}; launch_gemm(al, bl, ep, lp.K + (alpha == 1.f ? 1 : 0), lp.N, Mr, true, st); }
 }
@@ -462,8 +513,7 @@ static void dense_wgrad(const LayerPlan& lp, const T* x, const int32_t* idx, con
   launch_gemm(al, bl, ep, lp.K + (alpha == 1.f ? 1 : 0), lp.N, B, true, st);
 }
 
-// bias gradient alone (used when the input scale alpha != 1 so the ones-row trick cannot share
-// the epilogue scale): db[n] = sum_m dy[m,n]
+// bias gradient: db[n] = sum_m dy[m,n]
 __global__ void colsum_kernel(const float* __restrict__ dy, int M, int N, float* __restrict__ db) {
   int n = blockIdx.x * 32 + (threadIdx.x & 31);
   int r0 = blockIdx.y * 1024 + (threadIdx.x >> 5);
@@ -480,6 +530,146 @@ __global__ void colsum_kernel(const float* __restrict__ dy, int M, int N, float*
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// per-layer operations (tensor-core kernel when the shape is covered, fp32 kernel otherwise)
+// ------------------------------------------------------------------------------------------
+// forward of layer i; tc_allowed = parameters are the bound ones (their bf16 planes are current)
+static int op_forward(xtb_net* net, int i, const float* P, bool tc_allowed, const void* obs, const int32_t* idx, int B,
+                      cudaStream_t st) {
+  const LayerPlan& lp = net->L[i];
+  float* out = (float*)(net->ws + net->out_off[i + 1]);
+  Planes po = out_planes(net, i + 1);
+  const float* w = P + lp.w_off;
+  const float* b = P + lp.b_off;
+  cudaError_t te = cudaSuccess;
+  if (lp.d.src == 0) {
+    float alpha = net->desc.scale;
+    if (tc_allowed && tc_conv_ok(net, lp)) {
+      // the decoded frames of this minibatch are in the observation plane (op_decode ran before)
+      te = lp.pad ? tc_conv_fwd_t<true>(lp, obs_planes(net), false, w_planes(net), b, alpha, out, po, B, st)
+                  : tc_conv_fwd_t<false>(lp, obs_planes(net), false, w_planes(net), b, alpha, out, po, B, st);
+    } else if (net->desc.input_u8) {
+      if (lp.d.kind == XTB_CONV) conv_fwd<uint8_t>(lp, (const uint8_t*)obs, idx, w, b, alpha, out, po, B, st);
+      else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, idx, w, b, alpha, out, po, B, st);
+    } else {
+      if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, (const float*)obs, idx, w, b, alpha, out, po, B, st);
+      else dense_fwd<float>(lp, (const float*)obs, idx, w, b, alpha, out, po, B, st);
+    }
+  } else {
+    const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
+    Planes px = out_planes(net, lp.d.src);
+    if (lp.d.kind == XTB_CONV) {
+      if (tc_allowed && tc_conv_ok(net, lp))
+        te = lp.pad ? tc_conv_fwd_t<true>(lp, px, true, w_planes(net), b, 1.f, out, po, B, st)
+                    : tc_conv_fwd_t<false>(lp, px, true, w_planes(net), b, 1.f, out, po, B, st);
+      else conv_fwd<float>(lp, x, nullptr, w, b, 1.f, out, po, B, st);
+    } else {
+      if (tc_allowed && tc_dense_ok(lp)) te = tc_dense_fwd(lp, px, w_planes(net), b, out, po, B, st);
+      else dense_fwd<float>(lp, x, nullptr, w, b, 1.f, out, po, B, st);
+    }
+  }
+  if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 forward launch (layer %d): %s", i, cudaGetErrorString(te));
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+// uint8 frame decode (+ minibatch gather) into the observation plane when a tensor-core first layer reads it
+static int op_decode(xtb_net* net, const void* obs, const int32_t* idx, int B, cudaStream_t st) {
+  bool need = false;
+  for (const auto& lp : net->L) if (lp.d.src == 0 && tc_conv_ok(net, lp)) need = true;
+  if (!need) return XTB_OK;
+  int per = net->tsize[0];
+  dim3 grid((per / 16 + 255) / 256, B);
+  tc::decode_u8_kernel<<<grid, 256, 0, st>>>((const uint8_t*)obs, idx, per, obs_planes(net).hi);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, int B, cudaStream_t st) {
+  const LayerPlan& lp = net->L[i];
+  int t = i + 1;
+  const float* dy = (const float*)(net->ws + net->gout_off[t]);
+  Planes pdy = gout_planes(net, t);
+  float* dw = net->grads + lp.w_off;
+  float* db = net->grads + lp.b_off;
+  cudaError_t te = cudaSuccess;
+  bool need_colsum = false;
+  if (lp.d.src == 0) {
+    float alpha = net->desc.scale;
+    if (tc_conv_ok(net, lp)) {
+      te = lp.pad ? tc_conv_wgrad_t<true>(lp, obs_planes(net), false, pdy, alpha, dw, B, st)
+                  : tc_conv_wgrad_t<false>(lp, obs_planes(net), false, pdy, alpha, dw, B, st);
+      need_colsum = true;
+    } else {
+      if (net->desc.input_u8) {
+        if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st);
+        else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st);
+      } else {
+        if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st);
+        else dense_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st);
+      }
+      need_colsum = alpha != 1.f;
+    }
+  } else {
+    const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
+    Planes px = out_planes(net, lp.d.src);
+    if (lp.d.kind == XTB_CONV) {
+      if (tc_conv_ok(net, lp)) {
+        te = lp.pad ? tc_conv_wgrad_t<true>(lp, px, true, pdy, 1.f, dw, B, st) : tc_conv_wgrad_t<false>(lp, px, true, pdy, 1.f, dw, B, st);
+        need_colsum = true;
+      } else conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st);
+    } else {
+      if (tc_dense_ok(lp)) { te = tc_dense_wgrad(lp, px, pdy, dw, B, st); need_colsum = true; }
+      else dense_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st);
+    }
+  }
+  if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 wgrad launch (layer %d): %s", i, cudaGetErrorString(te));
+  LAUNCH_CHECK();
+  if (need_colsum) {   // bias gradient = column sums of dY
+    int Mb = lp.d.kind == XTB_CONV ? B * lp.g.P : B;
+    dim3 gridb((lp.N + 31) / 32, (Mb + 1023) / 1024);
+    colsum_kernel<<<gridb, 256, 0, st>>>(dy, Mb, lp.N, db);
+    LAUNCH_CHECK();
+  }
+  return XTB_OK;
+}
+
+// data gradient of layer i into its source tensor (gradient wrt the source's pre-activation)
+static int op_dgrad(xtb_net* net, int i, int acc, int B, cudaStream_t st) {
+  const LayerPlan& lp = net->L[i];
+  int t = i + 1, s = lp.d.src;
+  const float* dy = (const float*)(net->ws + net->gout_off[t]);
+  Planes pdy = gout_planes(net, t);
+  const float* x = (const float*)(net->ws + net->out_off[s]);
+  float* gsrc = (float*)(net->ws + net->gout_off[s]);
+  Planes pg = gout_planes(net, s);
+  const float* w = net->params + lp.w_off;
+  cudaError_t te = cudaSuccess;
+  if (lp.d.kind == XTB_CONV) {
+    if (tc_conv_dgrad_ok(lp)) te = tc_conv_dgrad(lp, pdy, w_planes(net), gsrc, x, pg, acc, B, st);
+    else {
+      ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
+      BConvDgrad bl{w, lp.wk, lp.N};
+      EpiDgrad ep{gsrc, x, lp.src_act, lp.g.C, acc, pg.hi, pg.lo_off};
+      launch_gemm(al, bl, ep, B * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
+    }
+  } else {
+    if (tc_dense_ok(lp)) te = tc_dense_dgrad(lp, pdy, w_planes(net), gsrc, x, pg, acc, B, st);
+    else {
+      ADense<float> al{dy, nullptr, lp.N};
+      BTransposed bl{w, lp.N};
+      EpiDgrad ep{gsrc, x, lp.src_act, lp.K, acc, pg.hi, pg.lo_off};
+      launch_gemm(al, bl, ep, B, lp.K, lp.N, false, st);
+    }
+  }
+  if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 dgrad launch (layer %d): %s", i, cudaGetErrorString(te));
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward / backward
+// ------------------------------------------------------------------------------------------
 static int net_forward_impl(xtb_net* net, const float* params, const void* obs, const int32_t* gather_idx,
                             int batch, void* stream, unsigned skip_mask);
 extern "C" int xtb_net_forward(xtb_net* net, const float* params, const void* obs, const int32_t* gather_idx,
@@ -492,38 +682,13 @@ static int net_forward_impl(xtb_net* net, const float* params, const void* obs, 
   if (batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "batch %d out of range (max %d)", batch, net->max_batch);
   if (!obs) return fail(XTB_ERR_ARG, "obs is null");
   const float* P = params ? params : net->params;
+  const bool tc_allowed = (P == net->params);   // foreign parameters have no bf16 planes: fp32 kernels
   cudaStream_t st = S(stream);
+  if (tc_allowed) { int rc = op_decode(net, obs, gather_idx, batch, st); if (rc) return rc; }
   for (size_t i = 0; i < net->L.size(); i++) {
     if (skip_mask & (1u << i)) continue;
-    const LayerPlan& lp = net->L[i];
-    float* out = (float*)(net->ws + net->out_off[i + 1]);
-    const float* w = P + lp.w_off;
-    const float* b = P + lp.b_off;
-    cudaError_t te = cudaSuccess;
-    if (lp.d.src == 0) {
-      if (net->desc.input_u8) {
-        if (lp.d.kind == XTB_CONV) {
-          if (tc_conv_ok(lp)) te = tc_conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
-          else conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
-        } else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
-      } else {
-        if (lp.d.kind == XTB_CONV) {
-          if (tc_conv_ok(lp)) te = tc_conv_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
-          else conv_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
-        } else dense_fwd<float>(lp, (const float*)obs, gather_idx, w, b, net->desc.scale, out, batch, st);
-      }
-    } else {
-      const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
-      if (lp.d.kind == XTB_CONV) {
-        if (tc_conv_ok(lp)) te = tc_conv_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
-        else conv_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
-      } else {
-        if (tc_dense_ok(lp)) te = tc_dense_fwd(lp, x, w, b, out, batch, st);
-        else dense_fwd<float>(lp, x, nullptr, w, b, 1.f, out, batch, st);
-      }
-    }
-    if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 forward launch (layer %zu): %s", i, cudaGetErrorString(te));
-    LAUNCH_CHECK();
+    int rc = op_forward(net, (int)i, P, tc_allowed, obs, gather_idx, batch, st);
+    if (rc) return rc;
   }
   return XTB_OK;
 }
@@ -534,7 +699,7 @@ extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* ga
                                 const int32_t* head_tensors, int n_heads, void* stream) {
   return net_backward_impl(net, obs, gather_idx, batch, head_tensors, n_heads, stream, 0u, true);
 }
-// head_tensors: tensors whose gradient buffers were filled by the caller; skip_mask: layers handled elsewhere
+// head_tensors: tensors whose gradient buffers (fp32 AND planes) were filled by the caller / by a fp32 kernel
 static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
                              const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads) {
   if (!net || !net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_net_backward: net not bound (grads required)");
@@ -546,6 +711,16 @@ static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gathe
     int t = head_tensors[h];
     if (t < 1 || t > nl) return fail(XTB_ERR_ARG, "bad head tensor %d", t);
     has_grad[t] = 1; written[t] = 1;
+    // gradients written from outside (loss kernels, python) only touch the fp32 buffer: refresh the planes
+    // when a tensor-core kernel of this layer will read them
+    const LayerPlan& lp = net->L[t - 1];
+    if (!(skip_mask & (1u << (t - 1))) && ((lp.d.kind == XTB_CONV && (tc_conv_ok(net, lp) || tc_conv_dgrad_ok(lp))) || tc_dense_ok(lp)) &&
+        !net->gout_planes_fresh) {
+      Planes pg = gout_planes(net, t);
+      long long n = (long long)batch * net->tsize[t];
+      tc::split_planes_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st>>>((const float*)(net->ws + net->gout_off[t]), pg.hi, pg.lo_off, n);
+      LAUNCH_CHECK();
+    }
   }
   if (zero_grads) CUDA_TRY(cudaMemsetAsync(net->grads, 0, net->n_params * sizeof(float), st));
   for (int i = nl - 1; i >= 0; i--) {
@@ -553,79 +728,12 @@ static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gathe
     const LayerPlan& lp = net->L[i];
     int t = i + 1;
     if (!has_grad[t]) continue;   // tensor does not influence the loss
-    const float* dy = (const float*)(net->ws + net->gout_off[t]);
-    float* dw = net->grads + lp.w_off;
-    float* db = net->grads + lp.b_off;
-    // ---- weight + bias gradient
-    if (lp.d.src == 0) {
-      float alpha = net->desc.scale;
-      cudaError_t te = cudaSuccess;
-      bool tc_w = lp.d.kind == XTB_CONV && tc_conv_ok(lp);
-      if (net->desc.input_u8) {
-        if (lp.d.kind == XTB_CONV) {
-          if (tc_w) te = tc_conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
-          else conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
-        } else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
-      } else {
-        if (lp.d.kind == XTB_CONV) {
-          if (tc_w) te = tc_conv_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
-          else conv_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
-        } else dense_wgrad<float>(lp, (const float*)obs, gather_idx, dy, alpha, dw, batch, st);
-      }
-      if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 wgrad launch (layer %d): %s", i, cudaGetErrorString(te));
-      LAUNCH_CHECK();
-      if (alpha != 1.f || tc_w) {
-        int M = lp.d.kind == XTB_CONV ? batch * lp.g.P : batch;
-        dim3 grid((lp.N + 31) / 32, (M + 1023) / 1024);
-        colsum_kernel<<<grid, 256, 0, st>>>(dy, M, lp.N, db);
-        LAUNCH_CHECK();
-      }
-    } else {
-      const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
-      cudaError_t te = cudaSuccess;
-      bool tc_w = lp.d.kind == XTB_CONV ? tc_conv_ok(lp) : tc_dense_ok(lp);
-      if (lp.d.kind == XTB_CONV) {
-        if (tc_w) te = tc_conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
-        else conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
-      } else {
-        if (tc_w) te = tc_dense_wgrad(lp, x, dy, dw, batch, st);
-        else dense_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, batch, st);
-      }
-      if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 wgrad launch (layer %d): %s", i, cudaGetErrorString(te));
-      LAUNCH_CHECK();
-      if (tc_w) {   // the tensor-core wgrad has no ones-row: bias gradient = column sums of dY
-        int Mb = lp.d.kind == XTB_CONV ? batch * lp.g.P : batch;
-        dim3 gridb((lp.N + 31) / 32, (Mb + 1023) / 1024);
-        colsum_kernel<<<gridb, 256, 0, st>>>(dy, Mb, lp.N, db);
-        LAUNCH_CHECK();
-      }
-      // ---- data gradient into the source tensor
+    int rc = op_wgrad(net, i, obs, gather_idx, batch, st);
+    if (rc) return rc;
+    if (lp.d.src != 0) {
       int s = lp.d.src;
-      float* gsrc = (float*)(net->ws + net->gout_off[s]);
-      const float* xsrc = x;
-      const float* w = net->params + lp.w_off;
-      int acc = written[s] ? 1 : 0;
-      if (lp.d.kind == XTB_CONV) {
-        if (g_tc_mode && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.oshift >= 3) {
-          te = tc_conv_dgrad(lp, dy, w, gsrc, xsrc, acc, batch, st);
-        } else {
-          ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
-          BConvDgrad bl{w, lp.wk, lp.N};
-          EpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc};
-          launch_gemm(al, bl, ep, batch * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
-        }
-      } else {
-        if (tc_dense_ok(lp)) {
-          te = tc_dense_dgrad(lp, dy, w, gsrc, xsrc, acc, batch, st);
-        } else {
-          ADense<float> al{dy, nullptr, lp.N};
-          BTransposed bl{w, lp.N};
-          EpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc};
-          launch_gemm(al, bl, ep, batch, lp.K, lp.N, false, st);
-        }
-      }
-      if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 dgrad launch (layer %d): %s", i, cudaGetErrorString(te));
-      LAUNCH_CHECK();
+      rc = op_dgrad(net, i, written[s] ? 1 : 0, batch, st);
+      if (rc) return rc;
       written[s] = 1; has_grad[s] = 1;
     }
   }
@@ -638,69 +746,15 @@ extern "C" int xtb_net_bench_layer(xtb_net* net, int layer, int which, const voi
                                    int batch, void* stream) {
   if (!net || !net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_net_bench_layer: net not bound");
   if (layer < 0 || layer >= (int)net->L.size() || batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "bad layer/batch");
-  const LayerPlan& lp = net->L[layer];
   cudaStream_t st = S(stream);
-  float* out = (float*)(net->ws + net->out_off[layer + 1]);
-  const float* dy = (const float*)(net->ws + net->gout_off[layer + 1]);
-  const float* w = net->params + lp.w_off;
-  const float* b = net->params + lp.b_off;
-  bool from_obs = lp.d.src == 0;
-  const float* x = from_obs ? nullptr : (const float*)(net->ws + net->out_off[lp.d.src]);
-  float alpha = from_obs ? net->desc.scale : 1.f;
-  const bool tcc = lp.d.kind == XTB_CONV && tc_conv_ok(lp);
-  const bool tcd = lp.d.kind == XTB_DENSE && !from_obs && tc_dense_ok(lp);
-  if (which == 0) {
-    if (from_obs && net->desc.input_u8) {
-      if (tcc) tc_conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, alpha, out, batch, st);
-      else if (lp.d.kind == XTB_CONV) conv_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, alpha, out, batch, st);
-      else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, gather_idx, w, b, alpha, out, batch, st);
-    } else {
-      const float* xin = from_obs ? (const float*)obs : x;
-      if (tcc) tc_conv_fwd<float>(lp, xin, from_obs ? gather_idx : nullptr, w, b, alpha, out, batch, st);
-      else if (tcd) tc_dense_fwd(lp, xin, w, b, out, batch, st);
-      else if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, xin, from_obs ? gather_idx : nullptr, w, b, alpha, out, batch, st);
-      else dense_fwd<float>(lp, xin, from_obs ? gather_idx : nullptr, w, b, alpha, out, batch, st);
-    }
-  } else if (which == 1) {
-    float* dw = net->grads + lp.w_off;
-    if (from_obs && net->desc.input_u8) {
-      if (tcc) tc_conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
-      else if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
-      else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, gather_idx, dy, alpha, dw, batch, st);
-    } else {
-      const float* xin = from_obs ? (const float*)obs : x;
-      if (tcc) tc_conv_wgrad<float>(lp, xin, from_obs ? gather_idx : nullptr, dy, alpha, dw, batch, st);
-      else if (tcd) tc_dense_wgrad(lp, xin, dy, dw, batch, st);
-      else if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, xin, from_obs ? gather_idx : nullptr, dy, alpha, dw, batch, st);
-      else dense_wgrad<float>(lp, xin, from_obs ? gather_idx : nullptr, dy, alpha, dw, batch, st);
-    }
-  } else if (which == 2) {
-    if (from_obs) return fail(XTB_ERR_ARG, "layer reads the observation: no data gradient");
-    float* gsrc = (float*)(net->ws + net->gout_off[lp.d.src]);
-    cudaError_t te = cudaSuccess;
-    if (lp.d.kind == XTB_CONV) {
-      if (g_tc_mode && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.oshift >= 3) te = tc_conv_dgrad(lp, dy, w, gsrc, x, 0, batch, st);
-      else {
-        ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
-        BConvDgrad bl{w, lp.wk, lp.N};
-        EpiDgrad ep{gsrc, x, lp.src_act, lp.g.C, 0};
-        launch_gemm(al, bl, ep, batch * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
-      }
-    } else {
-      if (tc_dense_ok(lp)) te = tc_dense_dgrad(lp, dy, w, gsrc, x, 0, batch, st);
-      else {
-        ADense<float> al{dy, nullptr, lp.N};
-        BTransposed bl{w, lp.N};
-        EpiDgrad ep{gsrc, x, lp.src_act, lp.K, 0};
-        launch_gemm(al, bl, ep, batch, lp.K, lp.N, false, st);
-      }
-    }
-    if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "bench dgrad: %s", cudaGetErrorString(te));
-  } else {
-    return fail(XTB_ERR_ARG, "xtb_net_bench_layer: which must be 0, 1 or 2");
+  if (which == 0) return op_forward(net, layer, net->params, true, obs, gather_idx, batch, st);
+  if (which == 1) return op_wgrad(net, layer, obs, gather_idx, batch, st);
+  if (which == 2) {
+    if (net->L[layer].d.src == 0) return fail(XTB_ERR_ARG, "layer reads the observation: no data gradient");
+    return op_dgrad(net, layer, 0, batch, st);
   }
-  LAUNCH_CHECK();
-  return XTB_OK;
+  if (which == 3) return op_decode(net, obs, gather_idx, batch, st);
+  return fail(XTB_ERR_ARG, "xtb_net_bench_layer: which must be 0..3");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -919,6 +973,8 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         PpoHeadsArgs a;
         a.h_pi = (const float*)(net->ws + net->out_off[lpi.d.src]); a.h_v = (const float*)(net->ws + net->out_off[lv.d.src]);
         a.g_pi = (float*)(net->ws + net->gout_off[lpi.d.src]); a.g_v = (float*)(net->ws + net->gout_off[lv.d.src]);
+        a.gp_hi = gout_planes(net, lpi.d.src).hi; a.gp_lo = gout_planes(net, lpi.d.src).lo_off;
+        a.gv_hi = gout_planes(net, lv.d.src).hi; a.gv_lo = gout_planes(net, lv.d.src).lo_off;
         a.w_pi = net->params + lpi.w_off; a.b_pi = net->params + lpi.b_off; a.w_v = net->params + lv.w_off; a.b_v = net->params + lv.b_off;
         a.dw_pi = net->grads + lpi.w_off; a.db_pi = net->grads + lpi.b_off; a.dw_v = net->grads + lv.w_off; a.db_v = net->grads + lv.b_off;
         a.idx = idx; a.action = ro->action; a.old_logp = ro->old_logp; a.adv = ro->adv; a.old_v = ro->old_v; a.target_v = ro->target_v;
@@ -932,7 +988,9 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         else ppo_heads_kernel<16, 4><<<blocks, 256, shb, S(stream)>>>(a);
         LAUNCH_CHECK();
         int srcs[2] = {lpi.d.src, lv.d.src};
+        net->gout_planes_fresh = true;    // the fused kernel wrote fp32 and planes
         rc = net_backward_impl(net, ro->obs, idx, mb, srcs, a.shared ? 1 : 2, stream, skip, false);
+        net->gout_planes_fresh = false;
         if (rc) return rc;
       } else {
         rc = xtb_ppo_loss_grad(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), idx, ro->action, ro->old_logp,
@@ -947,6 +1005,8 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         if (rc) return fail(XTB_ERR_STATE, "gradient hook failed with %d", rc);
       }
       rc = xtb_adam_step(opt, net->params, net->grads, 1.f, stream);
+      if (rc) return rc;
+      rc = xtb_net_sync_weights(net, stream);
       if (rc) return rc;
     }
   }

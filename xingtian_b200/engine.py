@@ -89,6 +89,16 @@ class Net(object):
         check(self.lib.xtb_net_bind(self.handle, _ptr(self.params), _ptr(self.grads),
                                     C.c_void_p(self._ws_base), ws_bytes))
 
+    def params_changed(self):
+        """Must follow every host-side write into `self.params`: refreshes the bf16 hi/lo planes the
+        tensor-core kernels read (xtb_net_sync_weights)."""
+        check(self.lib.xtb_net_sync_weights(self.handle, stream_ptr()))
+
+    def load_flat(self, flat):
+        """Copy a flat parameter vector (e.g. another network's `params`) into this network."""
+        self.params.copy_(flat)
+        self.params_changed()
+
     def ensure_batch(self, batch):
         if batch > self.max_batch:
             torch.cuda.current_stream().synchronize()
@@ -150,6 +160,8 @@ class Net(object):
             raise KeyError("NO node's weights could assign in self.graph {} vs {}".format(
                 list(self.ptable.keys()), list(weights.keys())))
         flat.copy_(torch.from_numpy(host))
+        if flat is self.params:
+            self.params_changed()
 
     # ---- tensors ---------------------------------------------------------------------------
     def _wrap(self, ptr, t):
@@ -201,6 +213,7 @@ class Adam(object):
     def step(self, grad_scale=1.0):
         check(self.lib.xtb_adam_step(self.handle, _ptr(self.net.params), _ptr(self.net.grads),
                                      float(grad_scale), stream_ptr()))
+        self.net.params_changed()
 
     def grad_norm(self):
         p = self.lib.xtb_adam_grad_norm(self.handle)

@@ -24,6 +24,7 @@ def glorot_uniform_(net, rng):
         lim = math.sqrt(6.0 / (fan_in + fan_out))
         host[off:off + int(np.prod(shape))] = rng.uniform(-lim, lim, size=int(np.prod(shape))).astype(np.float32)
     net.params.copy_(torch.from_numpy(host))
+    net.params_changed()
 
 
 class XTModel(object):

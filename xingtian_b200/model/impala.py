@@ -57,6 +57,7 @@ class ImpalaCnnOpt(XTModel):
         o = rng.standard_normal(shape).astype(np.float32)
         o *= 0.01 / np.sqrt(np.square(o).sum(axis=0, keepdims=True))
         self.net.view(name).copy_(torch.from_numpy(o))
+        self.net.params_changed()
         self.opt = Adam(self.net, self.lr, eps=1e-8, clip_mode=capi.CLIP_GLOBAL_NORM, clip=self.grad_norm_clip)
         self._bufs = {}
         self._sample_seed = int(np.random.randint(0, 2 ** 31 - 1))
