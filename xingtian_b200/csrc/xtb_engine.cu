@@ -214,8 +214,10 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
   return XTB_OK;
 }
 
+static void drop_graphs_of(const void* obj);
 extern "C" void xtb_net_destroy(xtb_net* net) {
   if (!net) return;
+  drop_graphs_of(net);
   for (auto& lp : net->L) {
     cudaFree(lp.koff); cudaFree(lp.kyx); cudaFree(lp.dkyx); cudaFree(lp.dco); cudaFree(lp.wk);
   }
@@ -899,6 +901,7 @@ extern "C" int xtb_adam_create(long long count, float lr, float beta1, float bet
 
 extern "C" void xtb_adam_destroy(xtb_adam* o) {
   if (!o) return;
+  drop_graphs_of(o);
   cudaFree(o->blk_seg); cudaFree(o->blk_beg); cudaFree(o->blk_len);
   cudaFree(o->norm_sq); cudaFree(o->seg_scale); cudaFree(o->st);
   delete o;
@@ -928,11 +931,11 @@ extern "C" int xtb_adam_set_lr(xtb_adam* o, float lr) {
 // ------------------------------------------------------------------------------------------
 // fused PPO learner loop
 // ------------------------------------------------------------------------------------------
+// A captured graph bakes every kernel argument: the key carries everything that can change them.
 struct GraphKey {
   const void* net; const void* opt; const void* obs; const void* perm; const void* loss; int n, b, e;
-  bool operator<(const GraphKey& o) const {
-    return std::tie(net, opt, obs, perm, loss, n, b, e) < std::tie(o.net, o.opt, o.obs, o.perm, o.loss, o.n, o.b, o.e);
-  }
+  const void* ro[5]; float hp[4]; int pi_t, v_t, fuse, tc; const void* ws;
+  bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
 };
 struct GraphVal { cudaGraphExec_t exec; long long kernels; };
 static std::map<GraphKey, GraphVal> g_graphs;
@@ -1032,7 +1035,13 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
   }
   if (!use_graph || !stream || g_grad_hook)
     return ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, inv_world, stream);
-  GraphKey key{net, opt, ro->obs, perm, loss_per_step, n_sample, batch_size, n_epoch};
+  GraphKey key;
+  memset(&key, 0, sizeof key);
+  key.net = net; key.opt = opt; key.obs = ro->obs; key.perm = perm; key.loss = loss_per_step;
+  key.n = n_sample; key.b = batch_size; key.e = n_epoch;
+  key.ro[0] = ro->action; key.ro[1] = ro->old_logp; key.ro[2] = ro->adv; key.ro[3] = ro->old_v; key.ro[4] = ro->target_v;
+  key.hp[0] = hp->clip_ratio; key.hp[1] = hp->ent_coef; key.hp[2] = hp->vf_clip; key.hp[3] = hp->critic_coef;
+  key.pi_t = pi_tensor; key.v_t = v_tensor; key.fuse = g_fuse_heads; key.tc = g_tc_mode; key.ws = net->ws;
   auto it = g_graphs.find(key);
   if (it == g_graphs.end()) {
     cudaStream_t st = S(stream);
@@ -1060,10 +1069,21 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
 // rollout inference: T batched policy evaluations over the E stacked observations
 // ------------------------------------------------------------------------------------------
 struct InferKey {
-  const void* net; const void* obs; const void* idx; const void* act; int e, t;
-  bool operator<(const InferKey& o) const { return std::tie(net, obs, idx, act, e, t) < std::tie(o.net, o.obs, o.idx, o.act, o.e, o.t); }
+  const void* net; const void* obs; const void* idx; const void* act; const void* logp; const void* val; const void* ctr;
+  const void* ws; unsigned long long seed; int e, t, pi_t, v_t, tc;
+  bool operator<(const InferKey& o) const { return memcmp(this, &o, sizeof(InferKey)) < 0; }
 };
 static std::map<InferKey, GraphVal> g_infer_graphs;
+// cached graphs hold raw pointers into a network / optimiser: they die with the object (a later object may
+// be allocated at the same address)
+static void drop_graphs_of(const void* obj) {
+  for (auto it = g_graphs.begin(); it != g_graphs.end();) {
+    if (it->first.net == obj || it->first.opt == obj) { cudaGraphExecDestroy(it->second.exec); it = g_graphs.erase(it); } else ++it;
+  }
+  for (auto it = g_infer_graphs.begin(); it != g_infer_graphs.end();) {
+    if (it->first.net == obj) { cudaGraphExecDestroy(it->second.exec); it = g_infer_graphs.erase(it); } else ++it;
+  }
+}
 
 static int rollout_infer_launch(xtb_net* net, const void* obs, const int32_t* step_idx, int E, int T, int pi_t, int v_t,
                                 uint64_t seed, unsigned long long* offset_dev, int32_t* action, float* logp, float* value,
@@ -1092,7 +1112,10 @@ extern "C" int xtb_ppo_rollout_infer(xtb_net* net, const void* obs, const int32_
     return fail(XTB_ERR_ARG, "xtb_ppo_rollout_infer: bad head tensors");
   if (!use_graph || !stream)
     return rollout_infer_launch(net, obs, step_idx, n_env, n_step, pi_tensor, v_tensor, seed, offset_dev, action, logp, value, stream);
-  InferKey key{net, obs, step_idx, action, n_env, n_step};
+  InferKey key;
+  memset(&key, 0, sizeof key);
+  key.net = net; key.obs = obs; key.idx = step_idx; key.act = action; key.logp = logp; key.val = value; key.ctr = offset_dev;
+  key.ws = net->ws; key.seed = seed; key.e = n_env; key.t = n_step; key.pi_t = pi_tensor; key.v_t = v_tensor; key.tc = g_tc_mode;
   auto it = g_infer_graphs.find(key);
   if (it == g_infer_graphs.end()) {
     cudaStream_t st = S(stream);
