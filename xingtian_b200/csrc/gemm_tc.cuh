@@ -129,21 +129,43 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// hi = bf16x2(a,b); lo = bf16x2(a - float(hi.a), b - float(hi.b)); a bf16 widened to fp32 is its bits << 16
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
   hi = pack_bf16(a, b);
-  lo = pack_bf16(a - __bfloat162float(ha), b - __bfloat162float(hb));
+  float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16(a - ha, b - hb);
 }
-// write 16 fp32 values as bf16 hi/lo planes (32 B each); hi_plane may be NULL (tensor has no TC consumer)
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t r[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, float r[8]) {
+  uint32_t u[8];
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "l"(p));
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = __uint_as_float(u[i]);
+}
+// write 16 fp32 values (32-byte aligned run) with full-sector 256-bit stores
+__device__ __forceinline__ void store_f32x16(float* dst, const float v[16]) {
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = __float_as_uint(v[i]);
+  st_global_v8(dst, u);
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = __float_as_uint(v[8 + i]);
+  st_global_v8(dst + 8, u);
+}
+// ... and their bf16 hi/lo planes (32 B each); hi_plane may be NULL (tensor has no tensor-core consumer)
 __device__ __forceinline__ void store_planes16(__nv_bfloat16* hi_plane, long long lo_off, long long elem, const float v[16]) {
   if (!hi_plane) return;
   uint32_t h[8], l[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-  uint4* ph = reinterpret_cast<uint4*>(hi_plane + elem);
-  uint4* pl = reinterpret_cast<uint4*>(hi_plane + lo_off + elem);
-  ph[0] = make_uint4(h[0], h[1], h[2], h[3]); ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
-  pl[0] = make_uint4(l[0], l[1], l[2], l[3]); pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+  st_global_v8(hi_plane + elem, h);
+  st_global_v8(hi_plane + lo_off + elem, l);
 }
 __device__ __forceinline__ void store_plane1(__nv_bfloat16* hi_plane, long long lo_off, long long elem, float x) {
   if (!hi_plane) return;
@@ -155,14 +177,16 @@ __device__ __forceinline__ void store_plane1(__nv_bfloat16* hi_plane, long long 
 // ------------------------------------------------------------------------------------------
 // Chunk sources.  A source is a logical 2-D array [n_rows][n_cols] of bf16 whose rows are gathered
 // independently and whose columns come in contiguous, 16-byte aligned groups of 8.
-//   struct Row;  void init_row(int row, Row&) const;
-//   const bf16* chunk(const Row&, int col) const;    -> hi-plane address of the 8 elements, or NULL = zeros
-//   lo plane address = hi address + lo_off;  any() = some valid address for zero-size copies
+//   Row  : per-row state (init_row);  Col : per-column-group state (col_info holds the integer divisions;
+//          the kernel caches it in shared memory once per tile when TABLE is set)
+//   chunk(row, col) -> hi-plane address of the 8 elements, or NULL = zeros;  lo plane = hi + lo_off
 // ------------------------------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;
+struct Col { int a, b; };
 
 // plain rows: X[row(m)*ld + col], optional row gather.  ld % 8 == 0.
 struct SrcDense {
+  static constexpr bool TABLE = false;
   const bf16* x; long long lo_off; const int32_t* idx; int ld; int n_rows;
   struct Row { long long base; int valid; };
   __device__ __forceinline__ const bf16* any() const { return x; }
@@ -170,7 +194,8 @@ struct SrcDense {
     r.valid = m < n_rows;
     r.base = r.valid ? (long long)(idx ? idx[m] : m) * ld : 0;
   }
-  __device__ __forceinline__ const bf16* chunk(const Row& r, int col) const { return r.valid ? x + r.base + col : nullptr; }
+  __device__ __forceinline__ Col col_info(int col) const { return Col{col, 0}; }
+  __device__ __forceinline__ const bf16* chunk(const Row& r, const Col& c) const { return r.valid ? x + r.base + c.a : nullptr; }
 };
 
 // im2col rows: row = output position (b,oy,ox), col = (ky,kx,ci).  C is a power of two (cshift = log2 C).
@@ -178,6 +203,7 @@ struct SrcDense {
 // stride are even so both taps are inside or both outside the image, and the 8 values are contiguous).
 template <bool PAD>
 struct SrcIm2col {
+  static constexpr bool TABLE = true;
   const bf16* x; long long lo_off; ConvGeom g; int cshift; int n_rows;
   struct Row { long long base; int iy0, ix0, valid; };
   __device__ __forceinline__ const bf16* any() const { return x; }
@@ -188,21 +214,25 @@ struct SrcIm2col {
     r.iy0 = oy * g.S - g.padT; r.ix0 = ox * g.S - g.padL;
     r.base = (((long long)b * g.H + r.iy0) * g.W + r.ix0) * g.C;
   }
-  __device__ __forceinline__ const bf16* chunk(const Row& r, int col) const {
-    if (!r.valid) return nullptr;
+  __device__ __forceinline__ Col col_info(int col) const {
     int tap = col >> cshift, ci = col & (g.C - 1);
     int ky = tap / g.KW, kx = tap - ky * g.KW;
+    return Col{((ky * g.W + kx) << cshift) + ci, (ky << 16) | kx};
+  }
+  __device__ __forceinline__ const bf16* chunk(const Row& r, const Col& c) const {
+    if (!r.valid) return nullptr;
     if (PAD) {
-      int iy = r.iy0 + ky, ix = r.ix0 + kx;
+      int iy = r.iy0 + (c.b >> 16), ix = r.ix0 + (c.b & 0xffff);
       if ((unsigned)iy >= (unsigned)g.H || (unsigned)ix >= (unsigned)g.W) return nullptr;
     }
-    return x + r.base + ((ky * g.W + kx) << cshift) + ci;
+    return x + r.base + c.a;
   }
 };
 
 // transposed-conv gather: row = input position (b,iy,ix), col = (ky,kx,co); value = dY[b,oy,ox,co]
 // with oy=(iy+padT-ky)/S when divisible and in range.  Cout is a power of two >= 8 (oshift = log2 Cout).
 struct SrcDgrad {
+  static constexpr bool TABLE = true;
   const bf16* dy; long long lo_off; ConvGeom g; int oshift; int sshift; int n_rows;
   struct Row { long long base; int iy0, ix0, valid; };
   __device__ __forceinline__ const bf16* any() const { return dy; }
@@ -212,47 +242,51 @@ struct SrcDgrad {
     int HW = g.H * g.W; int b = m / HW; int p = m - b * HW; int iy = p / g.W; int ix = p - iy * g.W;
     r.base = (long long)b * g.P * g.Cout; r.iy0 = iy + g.padT; r.ix0 = ix + g.padL;
   }
-  __device__ __forceinline__ const bf16* chunk(const Row& r, int col) const {
-    if (!r.valid) return nullptr;
+  __device__ __forceinline__ Col col_info(int col) const {
     int tap = col >> oshift, co = col & (g.Cout - 1);
     int ky = tap / g.KW, kx = tap - ky * g.KW;
-    int ty = r.iy0 - ky, tx = r.ix0 - kx;
+    return Col{co, (ky << 16) | kx};
+  }
+  __device__ __forceinline__ const bf16* chunk(const Row& r, const Col& c) const {
+    if (!r.valid) return nullptr;
+    int ty = r.iy0 - (c.b >> 16), tx = r.ix0 - (c.b & 0xffff);
     int mask = g.S - 1;
     if (ty < 0 || tx < 0 || (ty & mask) || (tx & mask)) return nullptr;
     int oy = ty >> sshift, ox = tx >> sshift;
     if (oy >= g.OH || ox >= g.OW) return nullptr;
-    return dy + r.base + (((long long)(oy * g.OW + ox)) << oshift) + co;
+    return dy + r.base + (((long long)(oy * g.OW + ox)) << oshift) + c.a;
   }
 };
 
 // conv weights for the data gradient: row = ci, col = (ky,kx,co) -> W[ky,kx,ci,co]
 struct SrcWDgrad {
+  static constexpr bool TABLE = false;
   const bf16* w; long long lo_off; int Cin, Cout, oshift; int n_rows;
   struct Row { int ci, valid; };
   __device__ __forceinline__ const bf16* any() const { return w; }
   __device__ __forceinline__ void init_row(int m, Row& r) const { r.valid = m < n_rows; r.ci = m; }
-  __device__ __forceinline__ const bf16* chunk(const Row& r, int col) const {
+  __device__ __forceinline__ Col col_info(int col) const { return Col{col >> oshift, col & (Cout - 1)}; }
+  __device__ __forceinline__ const bf16* chunk(const Row& r, const Col& c) const {
     if (!r.valid) return nullptr;
-    int tap = col >> oshift, co = col & (Cout - 1);
-    return w + ((long long)(tap * Cin + r.ci) << oshift) + co;
+    return w + ((long long)(c.a * Cin + r.ci) << oshift) + c.b;
   }
 };
 
 // ------------------------------------------------------------------------------------------
 // Epilogues: store16(row m, first column n, 16 accumulators).  Besides the fp32 tensor they keep the
 // bf16 hi/lo planes of the result current (hi == NULL when nothing on the tensor-core path reads it).
+// Rows are written as 32-byte full-sector stores (ld % 16 == 0 on the fast path).
 // ------------------------------------------------------------------------------------------
 struct TcEpiBiasAct {
   float* out; const float* bias; float alpha; int act; int ld; int M, N; bf16* hi; long long lo_off;
   __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
-    if (m >= M) return;
+    if (m >= M || n0 >= N) return;
     long long e = (long long)m * ld + n0;
     float r[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) r[j] = (n0 + j < N) ? act_apply(act, alpha * v[j] + bias[n0 + j]) : 0.f;
-    if (n0 + 15 < N) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + e + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    if (n0 + 15 < N && (ld & 15) == 0) {
+      store_f32x16(out + e, r);
       store_planes16(hi, lo_off, e, r);
     } else {
       for (int j = 0; j < 16; j++) if (n0 + j < N) { out[e + j] = r[j]; store_plane1(hi, lo_off, e + j, r[j]); }
@@ -262,23 +296,26 @@ struct TcEpiBiasAct {
 struct TcEpiDgrad {
   float* gout; const float* srcout; int act; int ld; int accumulate; int M, N; bf16* hi; long long lo_off;
   __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
-    if (m >= M) return;
+    if (m >= M || n0 >= N) return;
     long long e = (long long)m * ld + n0;
     float r[16];
+    if (n0 + 15 < N && (ld & 15) == 0) {
+      float so[16], go[16];
+      ld_global_v8(srcout + e, so); ld_global_v8(srcout + e + 8, so + 8);
+      if (accumulate) { ld_global_v8(gout + e, go); ld_global_v8(gout + e + 8, go + 8); }
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      r[j] = 0.f;
-      if (n0 + j < N) {
-        float gq = v[j] * act_grad_from_out(act, srcout[e + j]);
-        r[j] = accumulate ? gout[e + j] + gq : gq;
+      for (int j = 0; j < 16; j++) {
+        float gq = v[j] * act_grad_from_out(act, so[j]);
+        r[j] = accumulate ? go[j] + gq : gq;
       }
-    }
-    if (n0 + 15 < N) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(gout + e + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      store_f32x16(gout + e, r);
       store_planes16(hi, lo_off, e, r);
     } else {
-      for (int j = 0; j < 16; j++) if (n0 + j < N) { gout[e + j] = r[j]; store_plane1(hi, lo_off, e + j, r[j]); }
+      for (int j = 0; j < 16; j++) if (n0 + j < N) {
+        float gq = v[j] * act_grad_from_out(act, srcout[e + j]);
+        float rr = accumulate ? gout[e + j] + gq : gq;
+        gout[e + j] = rr; store_plane1(hi, lo_off, e + j, rr);
+      }
     }
   }
 };
@@ -303,15 +340,18 @@ struct TcEpiAtomic {
 };
 
 // ------------------------------------------------------------------------------------------
-// The kernel.
+// The kernel: persistent, warp-specialised.
+//   warps 0-3  producers   (cp.async gathers into the stage ring)
+//   warp  4    MMA issuer  (tcgen05.mma into one of two TMEM accumulator buffers)
+//   warps 5-8  epilogue    (tcgen05.ld of the other buffer -> global) -- overlaps the next tile's main loop
+// Each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  of the (m-tile, n-tile, k-split) space.
 //   A_MN / B_MN : operand is MN-major (its tile rows are the K entity) instead of K-major.
-//   KT          : reduction elements per pipeline stage (multiple of 16)
-//   NT          : N tile (16..256, multiple of 16) = UMMA N
+//   KT          : reduction elements per pipeline stage;  NT : N tile = UMMA N (16..256, multiple of 16)
 //   A_SPLIT / B_SPLIT : operand carries a bf16 residual plane (bf16x3); false = exact in bf16
-// grid = (ceil(Mext/128), ceil(Next/NT), ksplit);  block = 160 threads
 // ------------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 160;
 constexpr int TC_PRODUCERS = 128;
+constexpr int TC_THREADS = 288;
+constexpr int TC_MAXCOLS = 128;   // cached column groups per operand (K-major conv operands: K/8 <= 128)
 
 template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT>
 struct TcCfg {
@@ -322,62 +362,71 @@ struct TcCfg {
   static constexpr int A_BYTES = A_ROWS * A_CHUNKS * 16;
   static constexpr int B_BYTES = B_ROWS * B_CHUNKS * 16;
   static constexpr int STAGE_BYTES = A_BYTES * (A_SPLIT ? 2 : 1) + B_BYTES * (B_SPLIT ? 2 : 1);
-  static constexpr int STAGES = (STAGE_BYTES * 4 <= 100 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 100 * 1024) ? 3 : 2);
+  static constexpr int STAGES = (STAGE_BYTES * 4 <= 108 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 108 * 1024) ? 3 : 2);
   static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + 1024;
-  static constexpr int TMEM_COLS = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));
+  static constexpr int TMEM_COLS = NT <= 16 ? 32 : (NT <= 32 ? 64 : (NT <= 64 ? 128 : (NT <= 128 ? 256 : 512)));  // two buffers
+  static constexpr int CTAS_PER_SM = (2 * SMEM_BYTES + 8192 <= 227 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
 
+// per-operand producer state: rows are re-initialised when they change (K-major: once per tile; MN-major: per stage)
 template <int ROWS, int CHUNKS, bool MN, bool SPLIT, class SRC>
-__device__ __forceinline__ void produce_tile(const SRC& src, uint32_t hi_smem, uint32_t lo_smem, int mn0, int k0,
-                                             int mn_ext, int k_end, int tid) {
-  // slot s -> (row = s % ROWS, chunk = s / ROWS); K-major: row is an MN entity (mn0+row), chunk along K
-  // (k0+8*chunk); MN-major: row is a K entity (k0+row), chunk along MN (mn0+8*chunk).
-  constexpr int SLOTS = ROWS * CHUNKS;
+struct Producer {
+  static constexpr int SLOTS = ROWS * CHUNKS;
   static_assert(SLOTS % TC_PRODUCERS == 0, "tile slots must tile the producer threads");
-  constexpr int PER = SLOTS / TC_PRODUCERS;
-  const int row_lim = MN ? k_end : mn_ext;
-  const int col_lim = MN ? mn_ext : k_end;
-  typename SRC::Row row;
-  int cur_row = -1;
-  const bf16* dummy = src.any();
+  static constexpr int PER = SLOTS / TC_PRODUCERS;
+  static constexpr int NROW = (ROWS >= TC_PRODUCERS) ? ROWS / TC_PRODUCERS : 1;   // distinct rows per thread
+  typename SRC::Row rows[NROW];
+
+  __device__ __forceinline__ void init_rows(const SRC& src, int row0, int row_lim, int tid) {
 #pragma unroll
-  for (int i = 0; i < PER; i++) {
-    int s = tid + i * TC_PRODUCERS;
-    int r = s % ROWS, c = s / ROWS;
-    int grow = MN ? k0 + r : mn0 + r;
-    int gcol = MN ? mn0 + 8 * c : k0 + 8 * c;
-    if (r != cur_row) {
-      src.init_row(grow, row);
-      if (grow >= row_lim) row.valid = 0;
-      cur_row = r;
+    for (int q = 0; q < NROW; q++) {
+      int r = (tid + q * TC_PRODUCERS) % ROWS;
+      src.init_row(row0 + r, rows[q]);
+      if (row0 + r >= row_lim) rows[q].valid = 0;
     }
-    const bf16* p = (gcol < col_lim) ? src.chunk(row, gcol) : nullptr;
-    uint32_t off = (uint32_t)c * ROWS * 16 + (uint32_t)r * 16;
-    cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
-    if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
   }
-}
+  // col_base: first column of the cached table; cols: table (unused when !SRC::TABLE)
+  __device__ __forceinline__ void produce(const SRC& src, const Col* cols, int col_base, uint32_t hi_smem, uint32_t lo_smem,
+                                          int col0, int col_lim, int tid) {
+    const bf16* dummy = src.any();
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      int s = tid + i * TC_PRODUCERS;
+      int r = s % ROWS, c = s / ROWS;
+      int gcol = col0 + 8 * c;
+      const typename SRC::Row& row = rows[(ROWS >= TC_PRODUCERS) ? (i % NROW) : 0];
+      const bf16* p = nullptr;
+      if (gcol < col_lim) {
+        Col ci = SRC::TABLE ? cols[(gcol - col_base) >> 3] : src.col_info(gcol);
+        p = src.chunk(row, ci);
+      }
+      uint32_t off = (uint32_t)c * ROWS * 16 + (uint32_t)r * 16;
+      cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
+      if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
+    }
+  }
+};
+
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT, class ASRC, class BSRC, class EPI>
 __global__ void __launch_bounds__(TC_THREADS)
-tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, int k_chunk) {
+tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, int k_chunk, int m_tiles, int n_tiles,
+               int total_tiles) {
   using Cfg = TcCfg<NT, KT, A_MN, B_MN, A_SPLIT, B_SPLIT>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_slot;
+  __shared__ Col col_tab[2][2][TC_MAXCOLS];     // [tile parity][operand][column group]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * NT;
-  const int kbeg = blockIdx.z * k_chunk;
-  const int kend = min(k_ext, kbeg + k_chunk);
-  const int n_tiles = (kend - kbeg + KT - 1) / KT;
-
-  uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum = smem_u32(&bars[2 * STAGES]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, TC_PRODUCERS); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(accum, 1);
+    for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
@@ -386,68 +435,114 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const uint32_t smem_base = smem_u32(smem);
+  const int mn_tiles = m_tiles * n_tiles;
 
   if (warp < 4) {
-    // ================= producers: asynchronous 16-byte copies, completion signalled on the stage barrier ====
-    int stage = 0; uint32_t phase = 0;
-    for (int t = 0; t < n_tiles; t++) {
-      mbar_wait(empty0 + 8 * stage, phase ^ 1);
-      uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-      uint32_t sa_lo = sa + Cfg::A_BYTES;
-      uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
-      uint32_t sb_lo = sb + Cfg::B_BYTES;
-      int k0 = kbeg + t * KT;
-      produce_tile<Cfg::A_ROWS, Cfg::A_CHUNKS, A_MN, A_SPLIT>(asrc, sa, sa_lo, m0, k0, m_ext, kend, tid);
-      produce_tile<Cfg::B_ROWS, Cfg::B_CHUNKS, B_MN, B_SPLIT>(bsrc, sb, sb_lo, n0, k0, n_ext, kend, tid);
-      cp_async_mbar_arrive_noinc(full0 + 8 * stage);
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    // ================= producers =================
+    Producer<Cfg::A_ROWS, Cfg::A_CHUNKS, A_MN, A_SPLIT, ASRC> pa;
+    Producer<Cfg::B_ROWS, Cfg::B_CHUNKS, B_MN, B_SPLIT, BSRC> pb;
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const int z = tile / mn_tiles, rem = tile - z * mn_tiles;
+      const int nt_i = rem / m_tiles, mt_i = rem - nt_i * m_tiles;
+      const int m0 = mt_i * 128, n0 = nt_i * NT;
+      const int kbeg = z * k_chunk, kend = min(k_ext, kbeg + k_chunk);
+      const int n_kt = (kend - kbeg + KT - 1) / KT;
+      Col* ta = col_tab[it & 1][0];
+      Col* tb = col_tab[it & 1][1];
+      // column-group tables: K-major operands cache the K range of this tile, MN-major ones their MN range
+      if (ASRC::TABLE) {
+        int base = A_MN ? m0 : kbeg, lim = A_MN ? min(m_ext, m0 + 128) : kend;
+        for (int j = tid; base + 8 * j < lim && j < TC_MAXCOLS; j += TC_PRODUCERS) ta[j] = asrc.col_info(base + 8 * j);
+      }
+      if (BSRC::TABLE) {
+        int base = B_MN ? n0 : kbeg, lim = B_MN ? min(n_ext, n0 + NT) : kend;
+        for (int j = tid; base + 8 * j < lim && j < TC_MAXCOLS; j += TC_PRODUCERS) tb[j] = bsrc.col_info(base + 8 * j);
+      }
+      if (ASRC::TABLE || BSRC::TABLE) producer_bar_sync();
+      if (!A_MN) pa.init_rows(asrc, m0, m_ext, tid);
+      if (!B_MN) pb.init_rows(bsrc, n0, n_ext, tid);
+      for (int t = 0; t < n_kt; t++) {
+        const int k0 = kbeg + t * KT;
+        if (A_MN) pa.init_rows(asrc, k0, kend, tid);
+        if (B_MN) pb.init_rows(bsrc, k0, kend, tid);
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+        uint32_t sa_lo = sa + Cfg::A_BYTES;
+        uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
+        uint32_t sb_lo = sb + Cfg::B_BYTES;
+        pa.produce(asrc, ta, A_MN ? m0 : kbeg, sa, sa_lo, A_MN ? m0 : k0, A_MN ? m_ext : kend, tid);
+        pb.produce(bsrc, tb, B_MN ? n0 : kbeg, sb, sb_lo, B_MN ? n0 : k0, B_MN ? n_ext : kend, tid);
+        cp_async_mbar_arrive_noinc(full0 + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
     }
-    // ================= epilogue =================
-    mbar_wait(accum, 0);
-    tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-    for (int c = 0; c < NT; c += 16) {
-      float v[16];
-      tmem_ld16(lane_addr + c, v);
-      if (n_tiles > 0) epi.store16(row, n0 + c, v);
-    }
-    tc_fence_before();
-  } else {
+  } else if (warp == 4) {
     // ================= MMA issuer =================
     constexpr uint32_t IDESC = make_idesc(NT, A_MN, B_MN);
     constexpr uint32_t A_LBO = A_MN ? 128 : Cfg::A_ROWS * 16, A_SBO = A_MN ? Cfg::A_ROWS * 16 : 128;
     constexpr uint32_t B_LBO = B_MN ? 128 : Cfg::B_ROWS * 16, B_SBO = B_MN ? Cfg::B_ROWS * 16 : 128;
     constexpr uint32_t A_KSTEP = A_MN ? 256 : 2 * Cfg::A_ROWS * 16;   // advance of one K=16 step
     constexpr uint32_t B_KSTEP = B_MN ? 256 : 2 * Cfg::B_ROWS * 16;
-    int stage = 0; uint32_t phase = 0;
-    for (int t = 0; t < n_tiles; t++) {
-      mbar_wait(full0 + 8 * stage, phase);
-      if (lane == 0) {
-        fence_proxy_async();      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
-        tc_fence_after();
-        uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-        uint32_t sa_lo = sa + Cfg::A_BYTES;
-        uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
-        uint32_t sb_lo = sb + Cfg::B_BYTES;
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const int z = tile / mn_tiles;
+      const int kbeg = z * k_chunk, kend = min(k_ext, kbeg + k_chunk);
+      const int n_kt = (kend - kbeg + KT - 1) / KT;
+      const int buf = it & 1;
+      const uint32_t acc = tmem_base + buf * NT;
+      mbar_wait(tempty0 + 8 * buf, ((it >> 1) & 1) ^ 1);      // the epilogue drained this accumulator
+      tc_fence_after();
+      for (int t = 0; t < n_kt; t++) {
+        mbar_wait(full0 + 8 * stage, phase);
+        if (lane == 0) {
+          fence_proxy_async();      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+          tc_fence_after();
+          uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          uint32_t sa_lo = sa + Cfg::A_BYTES;
+          uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
+          uint32_t sb_lo = sb + Cfg::B_BYTES;
 #pragma unroll
-        for (int j = 0; j < KT / 16; j++) {
-          uint64_t ah = make_desc(sa + j * A_KSTEP, A_LBO, A_SBO);
-          uint64_t bh = make_desc(sb + j * B_KSTEP, B_LBO, B_SBO);
-          umma_bf16(tmem_base, ah, bh, IDESC, (t > 0 || j > 0) ? 1u : 0u);
-          if (B_SPLIT) umma_bf16(tmem_base, ah, make_desc(sb_lo + j * B_KSTEP, B_LBO, B_SBO), IDESC, 1u);
-          if (A_SPLIT) umma_bf16(tmem_base, make_desc(sa_lo + j * A_KSTEP, A_LBO, A_SBO), bh, IDESC, 1u);
+          for (int j = 0; j < KT / 16; j++) {
+            uint64_t ah = make_desc(sa + j * A_KSTEP, A_LBO, A_SBO);
+            uint64_t bh = make_desc(sb + j * B_KSTEP, B_LBO, B_SBO);
+            umma_bf16(acc, ah, bh, IDESC, (t > 0 || j > 0) ? 1u : 0u);
+            if (B_SPLIT) umma_bf16(acc, ah, make_desc(sb_lo + j * B_KSTEP, B_LBO, B_SBO), IDESC, 1u);
+            if (A_SPLIT) umma_bf16(acc, make_desc(sa_lo + j * A_KSTEP, A_LBO, A_SBO), bh, IDESC, 1u);
+          }
+          umma_commit(empty0 + 8 * stage);            // frees the smem stage when these MMAs retire
+          if (t == n_kt - 1) umma_commit(tfull0 + 8 * buf);   // accumulator complete
         }
-        umma_commit(empty0 + 8 * stage);          // frees the smem stage when these MMAs retire
-        if (t == n_tiles - 1) umma_commit(accum); // accumulator complete
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if (n_kt == 0 && lane == 0) mbar_arrive(tfull0 + 8 * buf);
     }
-    if (n_tiles == 0 && lane == 0) mbar_arrive(accum);
-    tc_fence_before();
+  } else {
+    // ================= epilogue (warps 5..8 own TMEM lane quarters 1,2,3,0) =================
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const int z = tile / mn_tiles, rem = tile - z * mn_tiles;
+      const int nt_i = rem / m_tiles, mt_i = rem - nt_i * m_tiles;
+      const int m0 = mt_i * 128, n0 = nt_i * NT;
+      const int kbeg = z * k_chunk, kend = min(k_ext, kbeg + k_chunk);
+      const int buf = it & 1;
+      mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT;
+#pragma unroll 1
+      for (int c = 0; c < NT; c += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + c, v);
+        if (kend > kbeg) epi.store16(row, n0 + c, v);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * buf);
+    }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();

@@ -1,5 +1,6 @@
 // tc_dispatch.cuh -- host-side selection of tcgen05 kernel instantiations per layer operation.
 #pragma once
+#include <algorithm>
 #include "gemm_tc.cuh"
 
 namespace xtb {
@@ -19,8 +20,14 @@ static cudaError_t launch_tc(const AS& a, const BS& b, const EP& e, int m_ext, i
   if (ksplit < 1) ksplit = 1;
   int kc = (k_ext + ksplit - 1) / ksplit;
   kc = (kc + KT - 1) / KT * KT;
-  dim3 grid((m_ext + 127) / 128, (n_ext + NT - 1) / NT, (k_ext + kc - 1) / kc);
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a, b, e, m_ext, n_ext, k_ext, kc);
+  // K-major conv operands cache the column groups of one tile's K range in shared memory
+  if ((AS::TABLE && !A_MN) || (BS::TABLE && !B_MN)) {
+    while (kc / 8 > TC_MAXCOLS) { ksplit++; kc = ((k_ext + ksplit - 1) / ksplit + KT - 1) / KT * KT; }
+  }
+  int m_tiles = (m_ext + 127) / 128, n_tiles = (n_ext + NT - 1) / NT, k_tiles = (k_ext + kc - 1) / kc;
+  long long total = (long long)m_tiles * n_tiles * k_tiles;
+  int grid = (int)std::min<long long>(total, 148LL * Cfg::CTAS_PER_SM);
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a, b, e, m_ext, n_ext, k_ext, kc, m_tiles, n_tiles, (int)total);
   return cudaPeekAtLastError();
 }
 
