@@ -221,17 +221,30 @@ def run_b200(args):
     act_t = torch.empty(T, E, dtype=torch.int32, device=dev); logp_t = torch.empty(T, E, device=dev); val_t = torch.empty(T + 1, E, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
-    def device_iteration():
+    seg = {"infer": [], "gae": [], "train": []}
+
+    def device_iteration(record=False):
         # (1) batched inference over the E stacked observations, once per env step
+        if record:
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
         model.rollout_infer_device(store.obs, step_idx, E, T, act_t, logp_t, val_t)
         val_t[T].copy_(val_t[T - 1])            # bootstrap value (synthetic rollout: no next observation)
         store.action[:n].copy_(act_t.t().reshape(-1)); store.old_logp[:n].copy_(logp_t.t().reshape(-1))
         value_d.copy_(val_t.t())
+        if record:
+            e1.record()
         # (2) GAE on [E,T]
         capi.check(lib.xtb_gae(_ptr(value_d), _ptr(reward_d), _ptr(done_d), E, T, 0.99, 0.95, 1,
                                _ptr(store.adv), _ptr(store.old_v), _ptr(store.target_v), stream_ptr()))
+        if record:
+            e2.record()
         # (3) minibatch SGD
-        return model.train_device(n)
+        loss = model.train_device(n)
+        if record:
+            e3.record(); torch.cuda.synchronize()
+            seg["infer"].append(e0.elapsed_time(e1)); seg["gae"].append(e1.elapsed_time(e2)); seg["train"].append(e2.elapsed_time(e3))
+        return loss
 
     def barrier():
         if world > 1:
@@ -257,6 +270,9 @@ def run_b200(args):
     barrier()
     ms_local = sum(a.elapsed_time(b) for a, b in ev)
     launches = lib.xtb_launch_count() - launches0
+    for _ in range(2):
+        device_iteration(record=True)
+    breakdown = {k: float(np.mean(v)) for k, v in seg.items()}
     # ---- e2e through the plugin API with host buffers ----------------------------------------------
     host_obs = [np.ascontiguousarray(ro["obs"][np.arange(E) * T + t]) for t in range(T)]
     traj = []
@@ -333,7 +349,7 @@ def run_b200(args):
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": world * n / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
-           "roofline": roofline, "whole_step": whole, "cpu_baseline": cpu}
+           "roofline": roofline, "whole_step": whole, "breakdown_ms": breakdown, "cpu_baseline": cpu}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
