@@ -176,6 +176,8 @@ void xtb_adam_destroy(xtb_adam* opt);
 /* grad_scale multiplies the gradient before clipping (1 normally). After the call
  * *xtb_adam_grad_norm() holds the pre-clip global norm (device float). */
 int xtb_adam_step(xtb_adam* opt, float* params, const float* grads, float grad_scale, void* stream);
+/* Same step on a bound network's parameters/gradients; the kernel also refreshes the weights' bf16 planes. */
+int xtb_adam_step_net(xtb_adam* opt, xtb_net* net, float grad_scale, void* stream);
 const float* xtb_adam_grad_norm(const xtb_adam* opt);
 int xtb_adam_set_lr(xtb_adam* opt, float lr);
 

@@ -68,6 +68,7 @@ _SIGS = {
                                   C.c_float, C.POINTER(C.c_longlong), C.c_int, _P, _P, C.POINTER(_P)]),
     "xtb_adam_destroy": (None, [_P]),
     "xtb_adam_step": (C.c_int, [_P, _P, _P, C.c_float, _P]),
+    "xtb_adam_step_net": (C.c_int, [_P, _P, C.c_float, _P]),
     "xtb_adam_grad_norm": (_P, [_P]),
     "xtb_adam_set_lr": (C.c_int, [_P, C.c_float]),
     "xtb_ppo_train": (C.c_int, [_P, _P, C.POINTER(PpoRollout), C.c_int, C.c_int, C.c_int, _P,

@@ -293,13 +293,45 @@ struct TcEpiBiasAct {
     }
   }
 };
+// `db` (optional): bias gradient of the layer that produced the source tensor = column sums of this
+// gradient; rows of a warp are reduced with shuffles, one atomic per column per warp (ld == C: column = n).
 struct TcEpiDgrad {
-  float* gout; const float* srcout; int act; int ld; int accumulate; int M, N; bf16* hi; long long lo_off;
+  float* gout; const float* srcout; int act; int ld; int accumulate; int M, N; bf16* hi; long long lo_off; float* db;
   __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
+    const bool fast = n0 + 15 < N && (ld & 15) == 0;
+    if (db && fast) {   // warp-uniform path: every lane participates in the shuffles, rows past M contribute 0
+      float r[16], q[16];
+      long long e = (long long)m * ld + n0;
+      if (m < M) {
+        float so[16], go[16];
+        ld_global_v8(srcout + e, so); ld_global_v8(srcout + e + 8, so + 8);
+        if (accumulate) { ld_global_v8(gout + e, go); ld_global_v8(gout + e + 8, go + 8); }
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          q[j] = v[j] * act_grad_from_out(act, so[j]);
+          r[j] = accumulate ? go[j] + q[j] : q[j];
+        }
+        store_f32x16(gout + e, r);
+        store_planes16(hi, lo_off, e, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) q[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) atomicAdd(db + n0 + j, q[j]);
+      }
+      return;
+    }
     if (m >= M || n0 >= N) return;
     long long e = (long long)m * ld + n0;
     float r[16];
-    if (n0 + 15 < N && (ld & 15) == 0) {
+    if (fast) {
       float so[16], go[16];
       ld_global_v8(srcout + e, so); ld_global_v8(srcout + e + 8, so + 8);
       if (accumulate) { ld_global_v8(gout + e, go); ld_global_v8(gout + e + 8, go + 8); }

@@ -5,6 +5,7 @@
 // Three launches per step: sqnorm (per-segment sum of squares, one atomic per block), prep
 // (1 thread: clip scales, lr_t, beta powers, re-zero accumulators), adam (elementwise update).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -69,7 +70,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             float* __restrict__ v, const int* __restrict__ blk_seg,
             const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
             const float* __restrict__ seg_scale, const AdamState* __restrict__ st, float beta1,
-            float beta2, float eps) {
+            float beta2, float eps, __nv_bfloat16* __restrict__ w_hi, long long w_lo_off) {
   long long beg = blk_beg[blockIdx.x];
   int n = blk_len[blockIdx.x];
   float sc = seg_scale[blk_seg[blockIdx.x]];
@@ -80,7 +81,13 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     float mm = beta1 * m[j] + (1.f - beta1) * gg;
     float vv = beta2 * v[j] + (1.f - beta2) * gg * gg;
     m[j] = mm; v[j] = vv;
-    p[j] -= lr_t * mm / (sqrtf(vv) + eps);
+    float pn = p[j] - lr_t * mm / (sqrtf(vv) + eps);
+    p[j] = pn;
+    if (w_hi) {   // keep the bf16 hi/lo planes of the weights current (tensor-core operands)
+      __nv_bfloat16 h = __float2bfloat16_rn(pn);
+      w_hi[j] = h;
+      w_hi[w_lo_off + j] = __float2bfloat16_rn(pn - __bfloat162float(h));
+    }
   }
 }
 

@@ -399,6 +399,7 @@ struct PpoHeadsArgs {
   __nv_bfloat16* gp_hi; long long gp_lo; __nv_bfloat16* gv_hi; long long gv_lo;   // their bf16 planes
   const float* w_pi; const float* b_pi; const float* w_v; const float* b_v;
   float* dw_pi; float* db_pi; float* dw_v; float* db_v;
+  float* dbh_pi; float* dbh_v;             // bias gradients of the layers that produced h_pi / h_v (column sums of g)
   const int32_t* idx; const int32_t* action; const float* old_logp; const float* adv; const float* old_v; const float* target_v;
   float* logits_out; float* v_out; float* loss_out;
   int B, K, A, act_pi, act_v, shared;
@@ -428,6 +429,9 @@ __global__ void __launch_bounds__(256) ppo_heads_kernel(PpoHeadsArgs a) {
     }
   }
   float dbp[HEAD_AMAX]; float dbv = 0.f, lsum = 0.f;
+  float bh_pi[HEAD_KPL], bh_v[HEAD_KPL];
+#pragma unroll
+  for (int j = 0; j < HEAD_KPL; j++) { bh_pi[j] = 0.f; bh_v[j] = 0.f; }
 #pragma unroll
   for (int i = 0; i < HEAD_AMAX; i++) dbp[i] = 0.f;
   for (int b = blockIdx.x * nwarp + warp; b < a.B; b += gridDim.x * nwarp) {
@@ -510,10 +514,12 @@ __global__ void __launch_bounds__(256) ppo_heads_kernel(PpoHeadsArgs a) {
         if (a.shared) {
           float r = (gp + gv) * act_grad_from_out(a.act_pi, hp_[j]);
           a.g_pi[eo] = r; f32_store_plane(a.gp_hi, a.gp_lo, eo, r);
+          bh_pi[j] += r;
         } else {
           float r1 = gp * act_grad_from_out(a.act_pi, hp_[j]), r2 = gv * act_grad_from_out(a.act_v, hv_[j]);
           a.g_pi[eo] = r1; f32_store_plane(a.gp_hi, a.gp_lo, eo, r1);
           a.g_v[eo] = r2; f32_store_plane(a.gv_hi, a.gv_lo, eo, r2);
+          bh_pi[j] += r1; bh_v[j] += r2;
         }
       }
     }
@@ -543,7 +549,85 @@ __global__ void __launch_bounds__(256) ppo_heads_kernel(PpoHeadsArgs a) {
     float g = sh_dw[K * (A + 1) + threadIdx.x];
     if ((int)threadIdx.x < A) atomicAdd(a.db_pi + threadIdx.x, g); else atomicAdd(a.db_v, g);
   }
+  // bias gradients of the hidden layer(s): column sums of g, reduced over the block through shared memory
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) sh_dw[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < HEAD_KPL; j++) {
+    if (j < kpl) {
+      int k = lane + 32 * j;
+      atomicAdd(&sh_dw[k], bh_pi[j]);
+      if (!a.shared) atomicAdd(&sh_dw[K + k], bh_v[j]);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    if (a.dbh_pi) atomicAdd(a.dbh_pi + k, sh_dw[k]);
+    if (!a.shared && a.dbh_v) atomicAdd(a.dbh_v + k, sh_dw[K + k]);
+  }
   block_atomic_add(lsum, a.loss_out);
+}
+
+// Inference heads: logits / value of both dense heads + Gumbel-max sampling in one kernel (one warp per sample).
+// Philox offset = *offset_dev + t_add (device-resident counter, see sample_rollout_kernel).
+template <int HEAD_KPL, int HEAD_AMAX>
+__global__ void __launch_bounds__(256)
+ppo_infer_heads_kernel(const float* __restrict__ h_pi, const float* __restrict__ h_v, const float* __restrict__ w_pi,
+                       const float* __restrict__ b_pi, const float* __restrict__ w_v, const float* __restrict__ b_v,
+                       int B, int K, int A, uint64_t seed, const unsigned long long* __restrict__ offset_dev, int t_add,
+                       int32_t* __restrict__ action, float* __restrict__ logp, float* __restrict__ v_out,
+                       float* __restrict__ logits_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int kpl = K / 32;
+  const uint64_t offset = (uint64_t)(*offset_dev) + (uint64_t)t_add;
+  for (int b = blockIdx.x * nwarp + warp; b < B; b += gridDim.x * nwarp) {
+    float acc[HEAD_AMAX + 1];
+#pragma unroll
+    for (int i = 0; i <= HEAD_AMAX; i++) acc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < HEAD_KPL; j++) {
+      if (j < kpl) {
+        int k = lane + 32 * j;
+        float hp = h_pi[(long long)b * K + k], hv = h_v[(long long)b * K + k];
+#pragma unroll
+        for (int i = 0; i < HEAD_AMAX; i++) if (i < A) acc[i] = fmaf(hp, w_pi[k * A + i], acc[i]);
+        acc[HEAD_AMAX] = fmaf(hv, w_v[k], acc[HEAD_AMAX]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i <= HEAD_AMAX; i++) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+      float lg[HEAD_AMAX]; float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < HEAD_AMAX; i++) { lg[i] = (i < A) ? acc[i] + b_pi[i] : -INFINITY; mx = fmaxf(mx, lg[i]); }
+      float z = 0.f;
+#pragma unroll
+      for (int i = 0; i < HEAD_AMAX; i++) if (i < A) z += expf(lg[i] - mx);
+      float lz = logf(z), best = -INFINITY; int bi = 0;
+      uint32_t c[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int i = 0; i < HEAD_AMAX; i++) {
+        if (i < A) {
+          if ((i & 3) == 0) {
+            c[0] = (uint32_t)b; c[1] = (uint32_t)(i >> 2);
+            c[2] = (uint32_t)(offset & 0xffffffffu); c[3] = (uint32_t)(offset >> 32);
+            philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+          }
+          float u = (float)(c[i & 3] >> 8) * 5.9604644775390625e-08f + 2.98023223876953125e-08f;
+          float sc = lg[i] - logf(-logf(u));
+          if (sc > best) { best = sc; bi = i; }
+          if (logits_out) logits_out[(long long)b * A + i] = lg[i];
+        }
+      }
+      float la = 0.f;
+#pragma unroll
+      for (int i = 0; i < HEAD_AMAX; i++) if (i == bi) la = lg[i];
+      action[b] = bi;
+      logp[b] = la - mx - lz;
+      v_out[b] = acc[HEAD_AMAX] + b_v[0];
+    }
+  }
 }
 
 // Keras train_on_batch(states, y) with loss='mse': mean over B*A of (q-y)^2

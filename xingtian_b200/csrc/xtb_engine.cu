@@ -409,21 +409,23 @@ static cudaError_t tc_dense_wgrad(const LayerPlan& lp, Planes x, Planes dy, floa
 }
 
 static cudaError_t tc_conv_dgrad(const LayerPlan& lp, Planes dy, Planes w, float* gsrc, const float* xsrc, Planes pg, int acc,
-                                 int B, cudaStream_t st) {
+                                 float* db_src, int B, cudaStream_t st) {
   int M = B * lp.g.H * lp.g.W;
   tc::SrcDgrad a{dy.hi, dy.lo_off, lp.g, lp.oshift, lp.sshift, M};
   tc::SrcWDgrad bs{w.hi + lp.w_off, w.lo_off, lp.g.C, lp.N, lp.oshift, lp.g.C};
-  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc, M, lp.g.C, pg.hi, pg.lo_off};
+  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc, M, lp.g.C, pg.hi, pg.lo_off, db_src};
   if (lp.g.C <= 16) return tc::launch_tc<16, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
   if (lp.g.C <= 32) return tc::launch_tc<32, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
   return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
 }
 
 static cudaError_t tc_dense_dgrad(const LayerPlan& lp, Planes dy, Planes w, float* gsrc, const float* xsrc, Planes pg, int acc,
-                                  int B, cudaStream_t st) {
+                                  float* db_src, int B, cudaStream_t st) {
   tc::SrcDense a{dy.hi, dy.lo_off, nullptr, lp.N, B};
   tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K};          // rows = kw (N' entity), cols = n (K')
-  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc, B, lp.K, pg.hi, pg.lo_off};
+  // the source of a dense layer may be a conv map [B, H*W*C]: its bias gradient is per channel, not per flattened
+  // unit, so the column-sum fusion only applies when the source layer is dense itself (db_src != NULL then)
+  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc, B, lp.K, pg.hi, pg.lo_off, db_src};
   return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, B, lp.K, lp.N, 1, st);
 }
 
@@ -587,7 +589,7 @@ static int op_decode(xtb_net* net, const void* obs, const int32_t* idx, int B, c
   return XTB_OK;
 }
 
-static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, int B, cudaStream_t st) {
+static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, int B, cudaStream_t st, bool bias_done = false) {
   const LayerPlan& lp = net->L[i];
   int t = i + 1;
   const float* dy = (const float*)(net->ws + net->gout_off[t]);
@@ -627,7 +629,7 @@ static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, in
   }
   if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 wgrad launch (layer %d): %s", i, cudaGetErrorString(te));
   LAUNCH_CHECK();
-  if (need_colsum) {   // bias gradient = column sums of dY
+  if (need_colsum && !bias_done) {   // bias gradient = column sums of dY
     int Mb = lp.d.kind == XTB_CONV ? B * lp.g.P : B;
     dim3 gridb((lp.N + 31) / 32, (Mb + 1023) / 1024);
     colsum_kernel<<<gridb, 256, 0, st>>>(dy, Mb, lp.N, db);
@@ -637,7 +639,8 @@ static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, in
 }
 
 // data gradient of layer i into its source tensor (gradient wrt the source's pre-activation)
-static int op_dgrad(xtb_net* net, int i, int acc, int B, cudaStream_t st) {
+// db_src: bias gradient of the layer producing the source tensor, accumulated by the epilogue when non-NULL
+static int op_dgrad(xtb_net* net, int i, int acc, int B, cudaStream_t st, float* db_src = nullptr) {
   const LayerPlan& lp = net->L[i];
   int t = i + 1, s = lp.d.src;
   const float* dy = (const float*)(net->ws + net->gout_off[t]);
@@ -648,7 +651,7 @@ static int op_dgrad(xtb_net* net, int i, int acc, int B, cudaStream_t st) {
   const float* w = net->params + lp.w_off;
   cudaError_t te = cudaSuccess;
   if (lp.d.kind == XTB_CONV) {
-    if (tc_conv_dgrad_ok(lp)) te = tc_conv_dgrad(lp, pdy, w_planes(net), gsrc, x, pg, acc, B, st);
+    if (tc_conv_dgrad_ok(lp)) te = tc_conv_dgrad(lp, pdy, w_planes(net), gsrc, x, pg, acc, db_src, B, st);
     else {
       ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
       BConvDgrad bl{w, lp.wk, lp.N};
@@ -656,7 +659,7 @@ static int op_dgrad(xtb_net* net, int i, int acc, int B, cudaStream_t st) {
       launch_gemm(al, bl, ep, B * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
     }
   } else {
-    if (tc_dense_ok(lp)) te = tc_dense_dgrad(lp, pdy, w_planes(net), gsrc, x, pg, acc, B, st);
+    if (tc_dense_ok(lp)) te = tc_dense_dgrad(lp, pdy, w_planes(net), gsrc, x, pg, acc, db_src, B, st);
     else {
       ADense<float> al{dy, nullptr, lp.N};
       BTransposed bl{w, lp.N};
@@ -696,14 +699,16 @@ static int net_forward_impl(xtb_net* net, const float* params, const void* obs, 
 }
 
 static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
-                             const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads);
+                             const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads,
+                             unsigned bias_done_tensors = 0u);
 extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
                                 const int32_t* head_tensors, int n_heads, void* stream) {
   return net_backward_impl(net, obs, gather_idx, batch, head_tensors, n_heads, stream, 0u, true);
 }
 // head_tensors: tensors whose gradient buffers (fp32 AND planes) were filled by the caller / by a fp32 kernel
 static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
-                             const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads) {
+                             const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads,
+                             unsigned bias_done_tensors) {
   if (!net || !net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_net_backward: net not bound (grads required)");
   if (batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "batch out of range");
   cudaStream_t st = S(stream);
@@ -725,16 +730,36 @@ static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gathe
     }
   }
   if (zero_grads) CUDA_TRY(cudaMemsetAsync(net->grads, 0, net->n_params * sizeof(float), st));
+  // bias-gradient fusion: the bias gradient of the layer producing tensor s is the column sum of gout(s); when
+  // every consumer of s writes its contribution through a tensor-core data-gradient epilogue, those epilogues
+  // accumulate the column sums and the separate colsum launch of that layer is dropped
+  std::vector<char> fuse_bias(nl + 1, 0);
+  for (int s = 1; s <= nl; s++) {
+    if (bias_done_tensors & (1u << s)) { fuse_bias[s] = 2; continue; }
+    const LayerPlan& ps = net->L[s - 1];
+    bool all = true, any = false;
+    for (int j = 0; j < nl; j++) {
+      if (net->L[j].d.src != s) continue;
+      any = true;
+      const LayerPlan& c = net->L[j];
+      bool ok = !(skip_mask & (1u << j)) &&
+                ((c.d.kind == XTB_CONV && tc_conv_dgrad_ok(c) && ps.d.kind == XTB_CONV && c.g.C % 16 == 0) ||
+                 (c.d.kind == XTB_DENSE && tc_dense_ok(c) && ps.d.kind == XTB_DENSE && c.K % 16 == 0));
+      if (!ok) all = false;
+    }
+    fuse_bias[s] = (any && all) ? 1 : 0;
+  }
   for (int i = nl - 1; i >= 0; i--) {
     if (skip_mask & (1u << i)) continue;
     const LayerPlan& lp = net->L[i];
     int t = i + 1;
     if (!has_grad[t]) continue;   // tensor does not influence the loss
-    int rc = op_wgrad(net, i, obs, gather_idx, batch, st);
+    int rc = op_wgrad(net, i, obs, gather_idx, batch, st, fuse_bias[t] != 0);
     if (rc) return rc;
     if (lp.d.src != 0) {
       int s = lp.d.src;
-      rc = op_dgrad(net, i, written[s] ? 1 : 0, batch, st);
+      float* db_src = fuse_bias[s] == 1 ? net->grads + net->L[s - 1].b_off : nullptr;
+      rc = op_dgrad(net, i, written[s] ? 1 : 0, batch, st, db_src);
       if (rc) return rc;
       written[s] = 1; has_grad[s] = 1;
     }
@@ -907,7 +932,18 @@ extern "C" void xtb_adam_destroy(xtb_adam* o) {
   delete o;
 }
 
+static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream, tc::bf16* w_hi, long long w_lo);
 extern "C" int xtb_adam_step(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream) {
+  return adam_step_impl(o, params, grads, grad_scale, stream, nullptr, 0);
+}
+// optimiser step on a network's bound parameters; the weights' bf16 planes are refreshed by the same kernel
+extern "C" int xtb_adam_step_net(xtb_adam* o, xtb_net* net, float grad_scale, void* stream) {
+  if (!net || !net->ws || !net->params || !net->grads) return fail(XTB_ERR_STATE, "xtb_adam_step_net: net not bound");
+  if (!o || o->count != net->n_params) return fail(XTB_ERR_ARG, "xtb_adam_step_net: optimiser/net size mismatch");
+  Planes w = w_planes(net);
+  return adam_step_impl(o, net->params, net->grads, grad_scale, stream, w.hi, w.lo_off);
+}
+static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream, tc::bf16* w_hi, long long w_lo) {
   if (!o || !params || !grads) return fail(XTB_ERR_ARG, "xtb_adam_step: null pointer");
   cudaStream_t st = S(stream);
   sqnorm_kernel<<<o->n_blk, OPT_THREADS, 0, st>>>(grads, o->blk_seg, o->blk_beg, o->blk_len, o->norm_sq);
@@ -916,7 +952,7 @@ extern "C" int xtb_adam_step(xtb_adam* o, float* params, const float* grads, flo
                                      o->lr, o->beta1, o->beta2);
   LAUNCH_CHECK();
   adam_kernel<<<o->n_blk, OPT_THREADS, 0, st>>>(params, grads, o->m, o->v, o->blk_seg, o->blk_beg, o->blk_len,
-                                                o->seg_scale, o->st, o->beta1, o->beta2, o->eps);
+                                                o->seg_scale, o->st, o->beta1, o->beta2, o->eps, w_hi, w_lo);
   LAUNCH_CHECK();
   return XTB_OK;
 }
@@ -980,6 +1016,13 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         a.gv_hi = gout_planes(net, lv.d.src).hi; a.gv_lo = gout_planes(net, lv.d.src).lo_off;
         a.w_pi = net->params + lpi.w_off; a.b_pi = net->params + lpi.b_off; a.w_v = net->params + lv.w_off; a.b_v = net->params + lv.b_off;
         a.dw_pi = net->grads + lpi.w_off; a.db_pi = net->grads + lpi.b_off; a.dw_v = net->grads + lv.w_off; a.db_v = net->grads + lv.b_off;
+        // the hidden layers' bias gradients (column sums of g) when they are dense and only feed the heads
+        auto only_feeds_heads = [&](int tsr) { for (int j = 0; j < (int)net->L.size(); j++) if (net->L[j].d.src == tsr && !(skip & (1u << j))) return false; return true; };
+        bool bh_pi_ok = net->L[lpi.d.src - 1].d.kind == XTB_DENSE && only_feeds_heads(lpi.d.src);
+        bool bh_v_ok = net->L[lv.d.src - 1].d.kind == XTB_DENSE && only_feeds_heads(lv.d.src);
+        a.dbh_pi = bh_pi_ok ? net->grads + net->L[lpi.d.src - 1].b_off : nullptr;
+        a.dbh_v = bh_v_ok ? net->grads + net->L[lv.d.src - 1].b_off : nullptr;
+        unsigned bias_done = (bh_pi_ok ? (1u << lpi.d.src) : 0u) | ((lpi.d.src != lv.d.src && bh_v_ok) ? (1u << lv.d.src) : 0u);
         a.idx = idx; a.action = ro->action; a.old_logp = ro->old_logp; a.adv = ro->adv; a.old_v = ro->old_v; a.target_v = ro->target_v;
         a.logits_out = xtb_net_tensor(net, pi_t); a.v_out = xtb_net_tensor(net, v_t); a.loss_out = loss_per_step + step;
         a.B = mb; a.K = lpi.K; a.A = adim; a.act_pi = lpi.src_act; a.act_v = lv.src_act; a.shared = lpi.d.src == lv.d.src ? 1 : 0;
@@ -992,7 +1035,7 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         LAUNCH_CHECK();
         int srcs[2] = {lpi.d.src, lv.d.src};
         net->gout_planes_fresh = true;    // the fused kernel wrote fp32 and planes
-        rc = net_backward_impl(net, ro->obs, idx, mb, srcs, a.shared ? 1 : 2, stream, skip, false);
+        rc = net_backward_impl(net, ro->obs, idx, mb, srcs, a.shared ? 1 : 2, stream, skip, false, bias_done);
         net->gout_planes_fresh = false;
         if (rc) return rc;
       } else {
@@ -1007,9 +1050,7 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         rc = g_grad_hook(g_grad_hook_user, net->grads, net->n_params, stream);
         if (rc) return fail(XTB_ERR_STATE, "gradient hook failed with %d", rc);
       }
-      rc = xtb_adam_step(opt, net->params, net->grads, 1.f, stream);
-      if (rc) return rc;
-      rc = xtb_net_sync_weights(net, stream);
+      rc = xtb_adam_step_net(opt, net, 1.f, stream);
       if (rc) return rc;
     }
   }
@@ -1089,12 +1130,28 @@ static int rollout_infer_launch(xtb_net* net, const void* obs, const int32_t* st
                                 uint64_t seed, unsigned long long* offset_dev, int32_t* action, float* logp, float* value,
                                 void* stream) {
   int adim = net->tsize[pi_t];
+  const LayerPlan& lpi = net->L[pi_t - 1];
+  const LayerPlan& lv = net->L[v_t - 1];
+  int kpl = lpi.K / 32;
+  bool fuse = g_fuse_heads && lpi.d.kind == XTB_DENSE && lv.d.kind == XTB_DENSE && lpi.d.act == 0 && lv.d.act == 0 &&
+              lpi.d.src != 0 && lv.d.src != 0 && lpi.K == lv.K && lpi.K % 32 == 0 && adim <= 8 && kpl <= 16;
+  unsigned skip = fuse ? ((1u << (pi_t - 1)) | (1u << (v_t - 1))) : 0u;
   for (int t = 0; t < T; t++) {
-    int rc = xtb_net_forward(net, nullptr, obs, step_idx ? step_idx + (long long)t * E : nullptr, E, stream);
+    int rc = net_forward_impl(net, nullptr, obs, step_idx ? step_idx + (long long)t * E : nullptr, E, stream, skip);
     if (rc) return rc;
-    sample_rollout_kernel<<<(E + 127) / 128, 128, 0, S(stream)>>>(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), E, adim, seed,
-                                                                 offset_dev, t, action + (long long)t * E, logp + (long long)t * E,
-                                                                 value + (long long)t * E);
+    int32_t* a_t = action + (long long)t * E; float* lp_t = logp + (long long)t * E; float* v_o = value + (long long)t * E;
+    if (fuse) {
+      const float* hp = (const float*)(net->ws + net->out_off[lpi.d.src]);
+      const float* hv = (const float*)(net->ws + net->out_off[lv.d.src]);
+      const float *wp = net->params + lpi.w_off, *bp = net->params + lpi.b_off, *wv = net->params + lv.w_off, *bv = net->params + lv.b_off;
+      int blocks = std::max(1, std::min(148, (E + 7) / 8));
+      if (kpl <= 2) ppo_infer_heads_kernel<2, 8><<<blocks, 256, 0, S(stream)>>>(hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
+      else if (kpl <= 8) ppo_infer_heads_kernel<8, 8><<<blocks, 256, 0, S(stream)>>>(hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
+      else ppo_infer_heads_kernel<16, 8><<<blocks, 256, 0, S(stream)>>>(hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
+    } else {
+      sample_rollout_kernel<<<(E + 127) / 128, 128, 0, S(stream)>>>(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), E, adim, seed,
+                                                                   offset_dev, t, a_t, lp_t, v_o);
+    }
     LAUNCH_CHECK();
   }
   bump_counter_kernel<<<1, 1, 0, S(stream)>>>(offset_dev, T);

@@ -211,9 +211,7 @@ class Adam(object):
             pass
 
     def step(self, grad_scale=1.0):
-        check(self.lib.xtb_adam_step(self.handle, _ptr(self.net.params), _ptr(self.net.grads),
-                                     float(grad_scale), stream_ptr()))
-        self.net.params_changed()
+        check(self.lib.xtb_adam_step_net(self.handle, self.net.handle, float(grad_scale), stream_ptr()))
 
     def grad_norm(self):
         p = self.lib.xtb_adam_grad_norm(self.handle)
