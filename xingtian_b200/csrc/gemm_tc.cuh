@@ -277,9 +277,13 @@ struct SrcWDgrad {
 // bf16 hi/lo planes of the result current (hi == NULL when nothing on the tensor-core path reads it).
 // Rows are written as 32-byte full-sector stores (ld % 16 == 0 on the fast path).
 // ------------------------------------------------------------------------------------------
+struct EpiNoState {};
 struct TcEpiBiasAct {
+  typedef EpiNoState State;
   float* out; const float* bias; float alpha; int act; int ld; int M, N; bf16* hi; long long lo_off;
-  __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
+  __device__ __forceinline__ void init(State&) const {}
+  __device__ __forceinline__ void finish(State&, float*, int) const {}
+  __device__ __forceinline__ void store16(State&, int, int m, int n0, const float v[16]) const {
     if (m >= M || n0 >= N) return;
     long long e = (long long)m * ld + n0;
     float r[16];
@@ -293,45 +297,23 @@ struct TcEpiBiasAct {
     }
   }
 };
-// `db` (optional): bias gradient of the layer that produced the source tensor = column sums of this
-// gradient; rows of a warp are reduced with shuffles, one atomic per column per warp (ld == C: column = n).
+// `db` (optional): bias gradient of the layer that produced the source tensor = column sums of this gradient.
+// Each epilogue thread keeps per-column partial sums in registers across all tiles of its persistent CTA; they
+// are reduced once (warp shuffles -> shared memory -> one atomic per column per CTA).  Requires a single N tile.
 struct TcEpiDgrad {
+  struct State { float acc[64]; };
   float* gout; const float* srcout; int act; int ld; int accumulate; int M, N; bf16* hi; long long lo_off; float* db;
-  __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
-    const bool fast = n0 + 15 < N && (ld & 15) == 0;
-    if (db && fast) {   // warp-uniform path: every lane participates in the shuffles, rows past M contribute 0
-      float r[16], q[16];
-      long long e = (long long)m * ld + n0;
-      if (m < M) {
-        float so[16], go[16];
-        ld_global_v8(srcout + e, so); ld_global_v8(srcout + e + 8, so + 8);
-        if (accumulate) { ld_global_v8(gout + e, go); ld_global_v8(gout + e + 8, go + 8); }
+  __device__ __forceinline__ void init(State& st) const {
+    if (db) {
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          q[j] = v[j] * act_grad_from_out(act, so[j]);
-          r[j] = accumulate ? go[j] + q[j] : q[j];
-        }
-        store_f32x16(gout + e, r);
-        store_planes16(hi, lo_off, e, r);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; j++) q[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; j++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
-      }
-      if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int j = 0; j < 16; j++) atomicAdd(db + n0 + j, q[j]);
-      }
-      return;
+      for (int j = 0; j < 64; j++) st.acc[j] = 0.f;
     }
+  }
+  __device__ __forceinline__ void store16(State& st, int c, int m, int n0, const float v[16]) const {
     if (m >= M || n0 >= N) return;
     long long e = (long long)m * ld + n0;
     float r[16];
-    if (fast) {
+    if (n0 + 15 < N && (ld & 15) == 0) {
       float so[16], go[16];
       ld_global_v8(srcout + e, so); ld_global_v8(srcout + e + 8, so + 8);
       if (accumulate) { ld_global_v8(gout + e, go); ld_global_v8(gout + e + 8, go + 8); }
@@ -339,6 +321,10 @@ struct TcEpiDgrad {
       for (int j = 0; j < 16; j++) {
         float gq = v[j] * act_grad_from_out(act, so[j]);
         r[j] = accumulate ? go[j] + gq : gq;
+        if (db) {   // c is a compile-time multiple of 16 after unrolling of the caller's column loop
+#pragma unroll
+          for (int q = 0; q < 4; q++) if (c == 16 * q) st.acc[16 * q + j] += gq;
+        }
       }
       store_f32x16(gout + e, r);
       store_planes16(hi, lo_off, e, r);
@@ -350,10 +336,29 @@ struct TcEpiDgrad {
       }
     }
   }
+  // sh: zero-initialised shared floats [>= N]; called once by all 128 epilogue threads
+  __device__ __forceinline__ void finish(State& st, float* sh, int nt) const {
+    if (!db) return;
+#pragma unroll
+    for (int j = 0; j < 64; j++) {
+      if (j < nt) {
+        float q = st.acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(sh + j, q);
+      }
+    }
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    int t = (threadIdx.x - 160);
+    if (t >= 0 && t < nt && t < N) atomicAdd(db + t, sh[t]);
+  }
 };
 struct TcEpiStore {     // plain row-major store (self-test)
+  typedef EpiNoState State;
   float* out; int ld; int M, N;
-  __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
+  __device__ __forceinline__ void init(State&) const {}
+  __device__ __forceinline__ void finish(State&, float*, int) const {}
+  __device__ __forceinline__ void store16(State&, int, int m, int n0, const float v[16]) const {
     if (m >= M) return;
 #pragma unroll
     for (int j = 0; j < 16; j++)
@@ -361,8 +366,11 @@ struct TcEpiStore {     // plain row-major store (self-test)
   }
 };
 struct TcEpiAtomic {
+  typedef EpiNoState State;
   float* out; float alpha; int ld; int M, N;
-  __device__ __forceinline__ void store16(int m, int n0, const float v[16]) const {
+  __device__ __forceinline__ void init(State&) const {}
+  __device__ __forceinline__ void finish(State&, float*, int) const {}
+  __device__ __forceinline__ void store16(State&, int, int m, int n0, const float v[16]) const {
     if (m >= M) return;
     float* o = out + (long long)m * ld + n0;
 #pragma unroll
@@ -452,6 +460,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ Col col_tab[2][2][TC_MAXCOLS];     // [tile parity][operand][column group]
+  __shared__ float epi_sh[64];                  // epilogue reductions (bias gradients)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
@@ -462,6 +471,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  if (tid < 64) epi_sh[tid] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -553,6 +563,8 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   } else {
     // ================= epilogue (warps 5..8 own TMEM lane quarters 1,2,3,0) =================
     const int quarter = warp & 3;
+    typename EPI::State est;
+    epi.init(est);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int z = tile / mn_tiles, rem = tile - z * mn_tiles;
@@ -564,15 +576,16 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < NT; c += 16) {
         float v[16];
         tmem_ld16(lane_addr + c, v);
-        if (kend > kbeg) epi.store16(row, n0 + c, v);
+        if (kend > kbeg) epi.store16(est, c, row, n0 + c, v);
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * buf);
     }
+    epi.finish(est, epi_sh, NT);
   }
   tc_fence_before();
   __syncthreads();

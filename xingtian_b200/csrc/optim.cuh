@@ -75,7 +75,36 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   int n = blk_len[blockIdx.x];
   float sc = seg_scale[blk_seg[blockIdx.x]];
   float lr_t = st->lr_t;
-  for (int i = threadIdx.x; i < n; i += OPT_THREADS) {
+  const bool vec = ((beg & 3) == 0);      // 16-byte aligned chunk: 4 parameters per thread per iteration
+  int nv = vec ? (n & ~3) : 0;
+  for (int i = threadIdx.x * 4; i < nv; i += OPT_THREADS * 4) {
+    long long j = beg + i;
+    float4 g4 = *reinterpret_cast<const float4*>(g + j);
+    float4 m4 = *reinterpret_cast<const float4*>(m + j);
+    float4 v4 = *reinterpret_cast<const float4*>(v + j);
+    float4 p4 = *reinterpret_cast<const float4*>(p + j);
+    float gg[4] = {g4.x * sc, g4.y * sc, g4.z * sc, g4.w * sc};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      mm[q] = beta1 * mm[q] + (1.f - beta1) * gg[q];
+      vv[q] = beta2 * vv[q] + (1.f - beta2) * gg[q] * gg[q];
+      pp[q] -= lr_t * mm[q] / (sqrtf(vv[q]) + eps);
+    }
+    *reinterpret_cast<float4*>(m + j) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + j) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    *reinterpret_cast<float4*>(p + j) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    if (w_hi) {   // keep the bf16 hi/lo planes of the weights current (tensor-core operands)
+      __nv_bfloat162 h01 = __floats2bfloat162_rn(pp[0], pp[1]), h23 = __floats2bfloat162_rn(pp[2], pp[3]);
+      __nv_bfloat162 l01 = __floats2bfloat162_rn(pp[0] - __low2float(h01), pp[1] - __high2float(h01));
+      __nv_bfloat162 l23 = __floats2bfloat162_rn(pp[2] - __low2float(h23), pp[3] - __high2float(h23));
+      uint2 hu = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+      uint2 lu = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+      *reinterpret_cast<uint2*>(w_hi + j) = hu;
+      *reinterpret_cast<uint2*>(w_hi + w_lo_off + j) = lu;
+    }
+  }
+  for (int i = nv + threadIdx.x; i < n; i += OPT_THREADS) {
     long long j = beg + i;
     float gg = g[j] * sc;
     float mm = beta1 * m[j] + (1.f - beta1) * gg;
@@ -83,7 +112,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     m[j] = mm; v[j] = vv;
     float pn = p[j] - lr_t * mm / (sqrtf(vv) + eps);
     p[j] = pn;
-    if (w_hi) {   // keep the bf16 hi/lo planes of the weights current (tensor-core operands)
+    if (w_hi) {
       __nv_bfloat16 h = __float2bfloat16_rn(pn);
       w_hi[j] = h;
       w_hi[w_lo_off + j] = __float2bfloat16_rn(pn - __bfloat162float(h));

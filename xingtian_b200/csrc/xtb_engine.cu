@@ -499,22 +499,23 @@ static void dense_fwd(const LayerPlan& lp, const T* x, const int32_t* idx, const
 }
 template <typename T>
 static void conv_wgrad(const LayerPlan& lp, const T* x, const int32_t* idx, const float* dy, float alpha,
-                       float* dw, int B, cudaStream_t st) {
+                       float* dw, int B, cudaStream_t st, bool bias_row = true) {
   int Mr = B * lp.g.P;
   BRowMajor bl{dy, lp.N};
   EpiAtomic ep{dw, alpha, lp.N};
   // rows 0..K-1 scaled by alpha (input decode scale); the bias row (K) must not be scaled:
   // it rides in the same GEMM only when alpha == 1, else colsum_kernel computes it.
-  if (lp.pad) { AIm2colT<T, true> al{x, idx, lp.g, lp.koff, lp.kyx, Mr}; launch_gemm(al, bl, ep, lp.K + (alpha == 1.f ? 1 : 0), lp.N, Mr, true, st); }
-  else { AIm2colT<T, false> al{x, idx, lp.g, lp.koff, lp.kyx, Mr}; launch_gemm(al, bl, ep, lp.K + (alpha == 1.f ? 1 : 0), lp.N, Mr, true, st); }
+  int rows = lp.K + ((alpha == 1.f && bias_row) ? 1 : 0);
+  if (lp.pad) { AIm2colT<T, true> al{x, idx, lp.g, lp.koff, lp.kyx, Mr}; launch_gemm(al, bl, ep, rows, lp.N, Mr, true, st); }
+  else { AIm2colT<T, false> al{x, idx, lp.g, lp.koff, lp.kyx, Mr}; launch_gemm(al, bl, ep, rows, lp.N, Mr, true, st); }
 }
 template <typename T>
 static void dense_wgrad(const LayerPlan& lp, const T* x, const int32_t* idx, const float* dy, float alpha,
-                        float* dw, int B, cudaStream_t st) {
+                        float* dw, int B, cudaStream_t st, bool bias_row = true) {
   ADenseT<T> al{x, idx, lp.K, lp.K};
   BRowMajor bl{dy, lp.N};
   EpiAtomic ep{dw, alpha, lp.N};
-  launch_gemm(al, bl, ep, lp.K + (alpha == 1.f ? 1 : 0), lp.N, B, true, st);
+  launch_gemm(al, bl, ep, lp.K + ((alpha == 1.f && bias_row) ? 1 : 0), lp.N, B, true, st);
 }
 
 // bias gradient: db[n] = sum_m dy[m,n]
@@ -606,11 +607,11 @@ static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, in
       need_colsum = true;
     } else {
       if (net->desc.input_u8) {
-        if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st);
-        else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st);
+        if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st, !bias_done);
+        else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st, !bias_done);
       } else {
-        if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st);
-        else dense_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st);
+        if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st, !bias_done);
+        else dense_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st, !bias_done);
       }
       need_colsum = alpha != 1.f;
     }
@@ -621,10 +622,10 @@ static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, in
       if (tc_conv_ok(net, lp)) {
         te = lp.pad ? tc_conv_wgrad_t<true>(lp, px, true, pdy, 1.f, dw, B, st) : tc_conv_wgrad_t<false>(lp, px, true, pdy, 1.f, dw, B, st);
         need_colsum = true;
-      } else conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st);
+      } else conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st, !bias_done);
     } else {
       if (tc_dense_ok(lp)) { te = tc_dense_wgrad(lp, px, pdy, dw, B, st); need_colsum = true; }
-      else dense_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st);
+      else dense_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st, !bias_done);
     }
   }
   if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 wgrad launch (layer %d): %s", i, cudaGetErrorString(te));
@@ -744,7 +745,7 @@ static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gathe
       const LayerPlan& c = net->L[j];
       bool ok = !(skip_mask & (1u << j)) &&
                 ((c.d.kind == XTB_CONV && tc_conv_dgrad_ok(c) && ps.d.kind == XTB_CONV && c.g.C % 16 == 0) ||
-                 (c.d.kind == XTB_DENSE && tc_dense_ok(c) && ps.d.kind == XTB_DENSE && c.K % 16 == 0));
+                 (c.d.kind == XTB_DENSE && tc_dense_ok(c) && ps.d.kind == XTB_DENSE && c.K % 16 == 0 && c.K <= 64));
       if (!ok) all = false;
     }
     fuse_bias[s] = (any && all) ? 1 : 0;
