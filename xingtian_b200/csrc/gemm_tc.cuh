@@ -187,6 +187,7 @@ struct Col { int a, b; };
 // plain rows: X[row(m)*ld + col], optional row gather.  ld % 8 == 0.
 struct SrcDense {
   static constexpr bool TABLE = false;
+  __device__ __forceinline__ void set_class(int) {}
   const bf16* x; long long lo_off; const int32_t* idx; int ld; int n_rows;
   struct Row { long long base; int valid; };
   __device__ __forceinline__ const bf16* any() const { return x; }
@@ -204,6 +205,7 @@ struct SrcDense {
 template <bool PAD>
 struct SrcIm2col {
   static constexpr bool TABLE = true;
+  __device__ __forceinline__ void set_class(int) {}
   const bf16* x; long long lo_off; ConvGeom g; int cshift; int n_rows;
   struct Row { long long base; int iy0, ix0, valid; };
   __device__ __forceinline__ const bf16* any() const { return x; }
@@ -233,6 +235,7 @@ struct SrcIm2col {
 // with oy=(iy+padT-ky)/S when divisible and in range.  Cout is a power of two >= 8 (oshift = log2 Cout).
 struct SrcDgrad {
   static constexpr bool TABLE = true;
+  __device__ __forceinline__ void set_class(int) {}
   const bf16* dy; long long lo_off; ConvGeom g; int oshift; int sshift; int n_rows;
   struct Row { long long base; int iy0, ix0, valid; };
   __device__ __forceinline__ const bf16* any() const { return dy; }
@@ -261,6 +264,7 @@ struct SrcDgrad {
 // conv weights for the data gradient: row = ci, col = (ky,kx,co) -> W[ky,kx,ci,co]
 struct SrcWDgrad {
   static constexpr bool TABLE = false;
+  __device__ __forceinline__ void set_class(int) {}
   const bf16* w; long long lo_off; int Cin, Cout, oshift; int n_rows;
   struct Row { int ci, valid; };
   __device__ __forceinline__ const bf16* any() const { return w; }
@@ -269,6 +273,73 @@ struct SrcWDgrad {
   __device__ __forceinline__ const bf16* chunk(const Row& r, const Col& c) const {
     if (!r.valid) return nullptr;
     return w + ((long long)(c.a * Cin + r.ci) << oshift) + c.b;
+  }
+};
+
+// Stride-S transposed-conv gather decomposed by parity class (py,px) of (iy+padT, ix+padL): only the taps with
+// ky = py (mod S), kx = px (mod S) reach an input position of that class, so each class is a dense GEMM with
+// K/S^2 columns over 1/S^2 of the rows instead of a GEMM whose operand tile is (S^2-1)/S^2 zeros.
+// Rows of class z are enumerated (b, jy, jx): uy = uy0 + S*jy, ux = ux0 + S*jx;  cols = (ty, tx, co) with
+// ky = py + S*ty, kx = px + S*tx.  KH % S == 0, KW % S == 0.
+struct DgradClass {
+  int S, sshift, padT, padL, H, W, nY, nX;      // nY = ceil(H/S), nX = ceil(W/S)
+  int py, px, uy0, ux0;
+  __device__ __forceinline__ void set(int z) {
+    py = z >> sshift; px = z & (S - 1);
+    uy0 = padT + ((py - padT) & (S - 1));
+    ux0 = padL + ((px - padL) & (S - 1));
+  }
+  // class row m -> (b, iy, ix); returns false when the position falls outside the image (ragged classes)
+  __device__ __forceinline__ bool decode(int m, int& b, int& iy, int& ix, int& qy, int& qx) const {
+    int per = nY * nX;
+    b = m / per; int p = m - b * per; int jy = p / nX, jx = p - jy * nX;
+    int uy = uy0 + S * jy, ux = ux0 + S * jx;
+    iy = uy - padT; ix = ux - padL;
+    qy = (uy - py) >> sshift; qx = (ux - px) >> sshift;
+    return iy < H && ix < W;
+  }
+};
+struct SrcDgradS {
+  static constexpr bool TABLE = true;
+  const bf16* dy; long long lo_off; ConvGeom g; int oshift; int n_rows; DgradClass k; int KWs;
+  struct Row { long long base; int qy, qx, valid; };
+  __device__ __forceinline__ const bf16* any() const { return dy; }
+  __device__ __forceinline__ void set_class(int z) { k.set(z); }
+  __device__ __forceinline__ void init_row(int m, Row& r) const {
+    r.valid = m < n_rows; r.base = 0; r.qy = r.qx = 0;
+    if (!r.valid) return;
+    int b, iy, ix;
+    r.valid = k.decode(m, b, iy, ix, r.qy, r.qx);
+    r.base = (long long)b * g.P * g.Cout;
+  }
+  __device__ __forceinline__ Col col_info(int col) const {
+    int tap = col >> oshift, co = col & (g.Cout - 1);
+    int ty = tap / KWs, tx = tap - ty * KWs;
+    return Col{co, (ty << 16) | tx};
+  }
+  __device__ __forceinline__ const bf16* chunk(const Row& r, const Col& c) const {
+    if (!r.valid) return nullptr;
+    int oy = r.qy - (c.b >> 16), ox = r.qx - (c.b & 0xffff);
+    if ((unsigned)oy >= (unsigned)g.OH || (unsigned)ox >= (unsigned)g.OW) return nullptr;
+    return dy + r.base + (((long long)(oy * g.OW + ox)) << oshift) + c.a;
+  }
+};
+struct SrcWDgradS {
+  static constexpr bool TABLE = true;
+  const bf16* w; long long lo_off; int Cin, Cout, oshift; int n_rows; int KW, KWs; DgradClass k;
+  struct Row { int ci, valid; };
+  __device__ __forceinline__ const bf16* any() const { return w; }
+  __device__ __forceinline__ void set_class(int z) { k.set(z); }
+  __device__ __forceinline__ void init_row(int m, Row& r) const { r.valid = m < n_rows; r.ci = m; }
+  __device__ __forceinline__ Col col_info(int col) const {
+    int tap = col >> oshift, co = col & (Cout - 1);
+    int ty = tap / KWs, tx = tap - ty * KWs;
+    int ky = k.py + k.S * ty, kx = k.px + k.S * tx;
+    return Col{(ky * KW + kx) * Cin, co};
+  }
+  __device__ __forceinline__ const bf16* chunk(const Row& r, const Col& c) const {
+    if (!r.valid) return nullptr;
+    return w + ((long long)(c.a + r.ci) << oshift) + c.b;
   }
 };
 
@@ -281,6 +352,7 @@ struct EpiNoState {};
 struct TcEpiBiasAct {
   typedef EpiNoState State;
   float* out; const float* bias; float alpha; int act; int ld; int M, N; bf16* hi; long long lo_off;
+  __device__ __forceinline__ void set_class(int) {}
   __device__ __forceinline__ void init(State&) const {}
   __device__ __forceinline__ void finish(State&, float*, int) const {}
   __device__ __forceinline__ void store16(State&, int, int m, int n0, const float v[16]) const {
@@ -303,6 +375,8 @@ struct TcEpiBiasAct {
 struct TcEpiDgrad {
   struct State { float acc[64]; };
   float* gout; const float* srcout; int act; int ld; int accumulate; int M, N; bf16* hi; long long lo_off; float* db;
+  int use_class; DgradClass k;     // use_class: rows are parity-class rows (b,jy,jx) of a strided transposed conv
+  __device__ __forceinline__ void set_class(int z) { if (use_class) k.set(z); }
   __device__ __forceinline__ void init(State& st) const {
     if (db) {
 #pragma unroll
@@ -312,6 +386,11 @@ struct TcEpiDgrad {
   __device__ __forceinline__ void store16(State& st, int c, int m, int n0, const float v[16]) const {
     if (m >= M || n0 >= N) return;
     long long e = (long long)m * ld + n0;
+    if (use_class) {
+      int b, iy, ix, qy, qx;
+      if (!k.decode(m, b, iy, ix, qy, qx)) return;
+      e = (((long long)b * k.H + iy) * k.W + ix) * ld + n0;
+    }
     float r[16];
     if (n0 + 15 < N && (ld & 15) == 0) {
       float so[16], go[16];
@@ -356,6 +435,7 @@ struct TcEpiDgrad {
 struct TcEpiStore {     // plain row-major store (self-test)
   typedef EpiNoState State;
   float* out; int ld; int M, N;
+  __device__ __forceinline__ void set_class(int) {}
   __device__ __forceinline__ void init(State&) const {}
   __device__ __forceinline__ void finish(State&, float*, int) const {}
   __device__ __forceinline__ void store16(State&, int, int m, int n0, const float v[16]) const {
@@ -368,6 +448,7 @@ struct TcEpiStore {     // plain row-major store (self-test)
 struct TcEpiAtomic {
   typedef EpiNoState State;
   float* out; float alpha; int ld; int M, N;
+  __device__ __forceinline__ void set_class(int) {}
   __device__ __forceinline__ void init(State&) const {}
   __device__ __forceinline__ void finish(State&, float*, int) const {}
   __device__ __forceinline__ void store16(State&, int, int m, int n0, const float v[16]) const {
@@ -449,7 +530,8 @@ struct Producer {
 
 __device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT, class ASRC, class BSRC, class EPI>
+// CLASSES: the third tile coordinate selects a parity class (set_class) instead of a K split
+template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT, bool CLASSES, class ASRC, class BSRC, class EPI>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, int k_chunk, int m_tiles, int n_tiles,
                int total_tiles) {
@@ -488,8 +570,9 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       const int z = tile / mn_tiles, rem = tile - z * mn_tiles;
       const int nt_i = rem / m_tiles, mt_i = rem - nt_i * m_tiles;
       const int m0 = mt_i * 128, n0 = nt_i * NT;
-      const int kbeg = z * k_chunk, kend = min(k_ext, kbeg + k_chunk);
+      const int kbeg = CLASSES ? 0 : z * k_chunk, kend = CLASSES ? k_ext : min(k_ext, kbeg + k_chunk);
       const int n_kt = (kend - kbeg + KT - 1) / KT;
+      if (CLASSES) { asrc.set_class(z); bsrc.set_class(z); }
       Col* ta = col_tab[it & 1][0];
       Col* tb = col_tab[it & 1][1];
       // column-group tables: K-major operands cache the K range of this tile, MN-major ones their MN range
@@ -529,7 +612,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
     int stage = 0; uint32_t phase = 0; int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int z = tile / mn_tiles;
-      const int kbeg = z * k_chunk, kend = min(k_ext, kbeg + k_chunk);
+      const int kbeg = CLASSES ? 0 : z * k_chunk, kend = CLASSES ? k_ext : min(k_ext, kbeg + k_chunk);
       const int n_kt = (kend - kbeg + KT - 1) / KT;
       const int buf = it & 1;
       const uint32_t acc = tmem_base + buf * NT;
@@ -570,8 +653,9 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       const int z = tile / mn_tiles, rem = tile - z * mn_tiles;
       const int nt_i = rem / m_tiles, mt_i = rem - nt_i * m_tiles;
       const int m0 = mt_i * 128, n0 = nt_i * NT;
-      const int kbeg = z * k_chunk, kend = min(k_ext, kbeg + k_chunk);
+      const int kbeg = CLASSES ? 0 : z * k_chunk, kend = CLASSES ? k_ext : min(k_ext, kbeg + k_chunk);
       const int buf = it & 1;
+      if (CLASSES) epi.set_class(z);
       mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;

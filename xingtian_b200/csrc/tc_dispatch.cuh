@@ -6,11 +6,13 @@
 namespace xtb {
 namespace tc {
 
-template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT, class AS, class BS, class EP>
+// classes > 0: the kernel runs `classes` independent GEMMs over the full K range (parity classes of a strided
+// transposed conv, see SrcDgradS) instead of a K split
+template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT, class AS, class BS, class EP, bool CLASSES = false>
 static cudaError_t launch_tc(const AS& a, const BS& b, const EP& e, int m_ext, int n_ext, int k_ext, int ksplit,
-                             cudaStream_t st) {
+                             cudaStream_t st, int classes = 0) {
   using Cfg = TcCfg<NT, KT, A_MN, B_MN, A_SPLIT, B_SPLIT>;
-  auto kern = tc_gemm_kernel<NT, KT, A_MN, B_MN, A_SPLIT, B_SPLIT, AS, BS, EP>;
+  auto kern = tc_gemm_kernel<NT, KT, A_MN, B_MN, A_SPLIT, B_SPLIT, CLASSES, AS, BS, EP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -25,6 +27,7 @@ static cudaError_t launch_tc(const AS& a, const BS& b, const EP& e, int m_ext, i
     while (kc / 8 > TC_MAXCOLS) { ksplit++; kc = ((k_ext + ksplit - 1) / ksplit + KT - 1) / KT * KT; }
   }
   int m_tiles = (m_ext + 127) / 128, n_tiles = (n_ext + NT - 1) / NT, k_tiles = (k_ext + kc - 1) / kc;
+  if (CLASSES) { if (kc < k_ext || k_ext / 8 > TC_MAXCOLS) return cudaErrorInvalidValue; k_tiles = classes; }
   long long total = (long long)m_tiles * n_tiles * k_tiles;
   int grid = (int)std::min<long long>(total, 148LL * Cfg::CTAS_PER_SM);
   kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a, b, e, m_ext, n_ext, k_ext, kc, m_tiles, n_tiles, (int)total);

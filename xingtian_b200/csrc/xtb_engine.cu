@@ -410,13 +410,27 @@ static cudaError_t tc_dense_wgrad(const LayerPlan& lp, Planes x, Planes dy, floa
 
 static cudaError_t tc_conv_dgrad(const LayerPlan& lp, Planes dy, Planes w, float* gsrc, const float* xsrc, Planes pg, int acc,
                                  float* db_src, int B, cudaStream_t st) {
-  int M = B * lp.g.H * lp.g.W;
-  tc::SrcDgrad a{dy.hi, dy.lo_off, lp.g, lp.oshift, lp.sshift, M};
-  tc::SrcWDgrad bs{w.hi + lp.w_off, w.lo_off, lp.g.C, lp.N, lp.oshift, lp.g.C};
-  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.g.C, acc, M, lp.g.C, pg.hi, pg.lo_off, db_src};
-  if (lp.g.C <= 16) return tc::launch_tc<16, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
-  if (lp.g.C <= 32) return tc::launch_tc<32, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
-  return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, M, lp.g.C, lp.Kd, 1, st);
+  const ConvGeom& g = lp.g;
+  if (g.S > 1 && g.KH % g.S == 0 && g.KW % g.S == 0 && (lp.Kd / (g.S * g.S)) / 8 <= tc::TC_MAXCOLS) {
+    // strided transposed conv: one dense GEMM per parity class of the input position
+    tc::DgradClass k{g.S, lp.sshift, g.padT, g.padL, g.H, g.W, (g.H + g.S - 1) / g.S, (g.W + g.S - 1) / g.S, 0, 0, 0, 0};
+    int M = B * k.nY * k.nX;
+    int Kc = lp.Kd / (g.S * g.S);
+    tc::SrcDgradS a{dy.hi, dy.lo_off, g, lp.oshift, M, k, g.KW / g.S};
+    tc::SrcWDgradS bs{w.hi + lp.w_off, w.lo_off, g.C, lp.N, lp.oshift, g.C, g.KW, g.KW / g.S, k};
+    tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, g.C, acc, M, g.C, pg.hi, pg.lo_off, db_src, 1, k};
+    int cls = g.S * g.S;
+    if (g.C <= 16) return tc::launch_tc<16, 64, false, false, true, true, tc::SrcDgradS, tc::SrcWDgradS, tc::TcEpiDgrad, true>(a, bs, ep, M, g.C, Kc, 1, st, cls);
+    if (g.C <= 32) return tc::launch_tc<32, 64, false, false, true, true, tc::SrcDgradS, tc::SrcWDgradS, tc::TcEpiDgrad, true>(a, bs, ep, M, g.C, Kc, 1, st, cls);
+    return tc::launch_tc<64, 64, false, false, true, true, tc::SrcDgradS, tc::SrcWDgradS, tc::TcEpiDgrad, true>(a, bs, ep, M, g.C, Kc, 1, st, cls);
+  }
+  int M = B * g.H * g.W;
+  tc::SrcDgrad a{dy.hi, dy.lo_off, g, lp.oshift, lp.sshift, M};
+  tc::SrcWDgrad bs{w.hi + lp.w_off, w.lo_off, g.C, lp.N, lp.oshift, g.C};
+  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, g.C, acc, M, g.C, pg.hi, pg.lo_off, db_src, 0, tc::DgradClass{}};
+  if (g.C <= 16) return tc::launch_tc<16, 64, false, false, true, true>(a, bs, ep, M, g.C, lp.Kd, 1, st);
+  if (g.C <= 32) return tc::launch_tc<32, 64, false, false, true, true>(a, bs, ep, M, g.C, lp.Kd, 1, st);
+  return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, M, g.C, lp.Kd, 1, st);
 }
 
 static cudaError_t tc_dense_dgrad(const LayerPlan& lp, Planes dy, Planes w, float* gsrc, const float* xsrc, Planes pg, int acc,
@@ -425,7 +439,7 @@ static cudaError_t tc_dense_dgrad(const LayerPlan& lp, Planes dy, Planes w, floa
   tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K};          // rows = kw (N' entity), cols = n (K')
   // the source of a dense layer may be a conv map [B, H*W*C]: its bias gradient is per channel, not per flattened
   // unit, so the column-sum fusion only applies when the source layer is dense itself (db_src != NULL then)
-  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc, B, lp.K, pg.hi, pg.lo_off, db_src};
+  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc, B, lp.K, pg.hi, pg.lo_off, db_src, 0, tc::DgradClass{}};
   return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, B, lp.K, lp.N, 1, st);
 }
 
