@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "launch.cuh"
+
 namespace xtb {
 
 // keep the bf16 hi/lo planes of a tensor current (hi == NULL: tensor has no tensor-core consumer)
@@ -236,6 +238,7 @@ struct EpiAtomic {     // dW += alpha*acc  (split-K)
 template <int BM, int BN, int BK, int TM, int TN, class AL, class BL, class EP>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_f32_kernel(AL al, BL bl, EP ep, int M, int N, int K, int k_chunk) {
+  pdl_wait(); pdl_trigger();
   constexpr int NT = (BM / TM) * (BN / TN);
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];

@@ -557,6 +557,10 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // prologue done (barriers, TMEM, no global memory touched): wait for the producer grid, then let the next
+  // kernel start its own prologue underneath this one
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_slot;
   const uint32_t smem_base = smem_u32(smem);
   const int mn_tiles = m_tiles * n_tiles;
@@ -684,6 +688,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
 // ------------------------------------------------------------------------------------------
 // fp32 -> bf16 hi / lo planes (weights after an optimiser step or set_weights; any fp32 tensor)
 __global__ void split_planes_kernel(const float* __restrict__ src, bf16* __restrict__ hi, long long lo_off, long long n) {
+  pdl_wait(); pdl_trigger();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 v = *reinterpret_cast<const float4*>(src + i);
@@ -698,6 +703,7 @@ __global__ void split_planes_kernel(const float* __restrict__ src, bf16* __restr
 // uint8 frame decode with the minibatch gather folded in: dst[b, :] = bf16(obs[idx[b], :])   (exact)
 __global__ void decode_u8_kernel(const uint8_t* __restrict__ obs, const int32_t* __restrict__ idx, int per_sample,
                                  bf16* __restrict__ dst) {
+  pdl_wait(); pdl_trigger();
   int b = blockIdx.y;
   long long srow = idx ? idx[b] : b;
   const uint8_t* s = obs + srow * per_sample;

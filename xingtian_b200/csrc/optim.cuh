@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "launch.cuh"
+
 namespace xtb {
 
 constexpr int OPT_CHUNK = 4096;   // elements per block
@@ -22,6 +24,7 @@ __global__ void __launch_bounds__(OPT_THREADS)
 sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ blk_seg,
               const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
               double* __restrict__ norm_sq) {
+  pdl_wait(); pdl_trigger();
   const float* p = g + blk_beg[blockIdx.x];
   int n = blk_len[blockIdx.x];
   float s = 0.f;
@@ -42,6 +45,7 @@ sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ blk_seg,
 __global__ void adam_prep_kernel(AdamState* st, double* norm_sq, float* seg_scale, int n_seg,
                                  int clip_mode, float clip, float grad_scale, float lr, float beta1,
                                  float beta2) {
+  pdl_wait(); pdl_trigger();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double tot = 0.0;
   for (int s = 0; s < n_seg; s++) tot += norm_sq[s];
@@ -71,6 +75,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
             const float* __restrict__ seg_scale, const AdamState* __restrict__ st, float beta1,
             float beta2, float eps, __nv_bfloat16* __restrict__ w_hi, long long w_lo_off) {
+  pdl_wait(); pdl_trigger();
   long long beg = blk_beg[blockIdx.x];
   int n = blk_len[blockIdx.x];
   float sc = seg_scale[blk_seg[blockIdx.x]];

@@ -44,6 +44,7 @@ __global__ void gae_kernel(const float* __restrict__ value, const float* __restr
                            const uint8_t* __restrict__ done, int n_env, int T, float gamma, float lam,
                            int sign_clip, float* __restrict__ adv, float* __restrict__ old_v,
                            float* __restrict__ target_v) {
+  pdl_wait(); pdl_trigger();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= n_env) return;
@@ -114,6 +115,7 @@ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 __global__ void sample_kernel(const float* __restrict__ logits, int B, int A,
                               const float* __restrict__ uniforms, uint64_t seed, uint64_t offset,
                               int32_t* __restrict__ action, float* __restrict__ logp) {
+  pdl_wait(); pdl_trigger();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* l = logits + (long long)b * A;
@@ -149,6 +151,7 @@ __global__ void sample_kernel(const float* __restrict__ logits, int B, int A,
 __global__ void sample_rollout_kernel(const float* __restrict__ logits, const float* __restrict__ v_in, int B, int A,
                                       uint64_t seed, const unsigned long long* __restrict__ offset_dev, int t_add,
                                       int32_t* __restrict__ action, float* __restrict__ logp, float* __restrict__ v_out) {
+  pdl_wait(); pdl_trigger();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   uint64_t offset = (uint64_t)(*offset_dev) + (uint64_t)t_add;
@@ -174,9 +177,11 @@ __global__ void sample_rollout_kernel(const float* __restrict__ logits, const fl
   logp[b] = l[bi] - mx - lz;
   v_out[b] = v_in[b];
 }
-__global__ void bump_counter_kernel(unsigned long long* ctr, int add) { *ctr += (unsigned long long)add; }
+__global__ void bump_counter_kernel(unsigned long long* ctr, int add) {
+  pdl_wait(); pdl_trigger(); *ctr += (unsigned long long)add; }
 
 __global__ void argmax_kernel(const float* __restrict__ q, int B, int A, int32_t* __restrict__ action) {
+  pdl_wait(); pdl_trigger();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* l = q + (long long)b * A;
@@ -197,6 +202,7 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, const float* _
                                 int B, int A, PpoHyperDev hp, float inv_count,
                                 float* __restrict__ dlogits, float* __restrict__ dv,
                                 float* __restrict__ loss_out) {
+  pdl_wait(); pdl_trigger();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float lsum = 0.f;
   if (b < B) {
@@ -262,6 +268,7 @@ __global__ void vtrace_kernel(const float* __restrict__ tp_logits, const float* 
                               int n_traj, int S, int A, float gamma, float* __restrict__ dlogits,
                               float* __restrict__ dbaseline, float* __restrict__ vs_out,
                               float* __restrict__ pg_out, float* __restrict__ loss_out) {
+  pdl_wait(); pdl_trigger();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   float lsum = 0.f;
@@ -358,6 +365,7 @@ __global__ void dqn_loss_kernel(const float* __restrict__ q, const float* __rest
                                 const float* __restrict__ reward, const uint8_t* __restrict__ done,
                                 int B, int A, float gamma, float inv_count, float* __restrict__ dq,
                                 float* __restrict__ y_out, float* __restrict__ loss_out) {
+  pdl_wait(); pdl_trigger();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float lsum = 0.f;
   if (b < B) {
@@ -408,6 +416,7 @@ struct PpoHeadsArgs {
 
 template <int HEAD_KPL, int HEAD_AMAX>
 __global__ void __launch_bounds__(256) ppo_heads_kernel(PpoHeadsArgs a) {
+  pdl_wait(); pdl_trigger();
   extern __shared__ float sh_dw[];          // [K*(A+1) + (A+1)] block-level weight/bias gradient accumulators
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int K = a.K, A = a.A, kpl = K / 32;
@@ -578,6 +587,7 @@ ppo_infer_heads_kernel(const float* __restrict__ h_pi, const float* __restrict__
                        int B, int K, int A, uint64_t seed, const unsigned long long* __restrict__ offset_dev, int t_add,
                        int32_t* __restrict__ action, float* __restrict__ logp, float* __restrict__ v_out,
                        float* __restrict__ logits_out) {
+  pdl_wait(); pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int kpl = K / 32;
   const uint64_t offset = (uint64_t)(*offset_dev) + (uint64_t)t_add;
@@ -633,6 +643,7 @@ ppo_infer_heads_kernel(const float* __restrict__ h_pi, const float* __restrict__
 // Keras train_on_batch(states, y) with loss='mse': mean over B*A of (q-y)^2
 __global__ void mse_loss_kernel(const float* __restrict__ q, const float* __restrict__ y, long long n,
                                 float inv_count, float* __restrict__ dq, float* __restrict__ loss_out) {
+  pdl_wait(); pdl_trigger();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float lsum = 0.f;
   if (i < n) {

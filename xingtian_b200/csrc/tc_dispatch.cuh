@@ -30,7 +30,7 @@ static cudaError_t launch_tc(const AS& a, const BS& b, const EP& e, int m_ext, i
   if (CLASSES) { if (kc < k_ext || k_ext / 8 > TC_MAXCOLS) return cudaErrorInvalidValue; k_tiles = classes; }
   long long total = (long long)m_tiles * n_tiles * k_tiles;
   int grid = (int)std::min<long long>(total, 148LL * Cfg::CTAS_PER_SM);
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a, b, e, m_ext, n_ext, k_ext, kc, m_tiles, n_tiles, (int)total);
+  XLAUNCH(kern, grid, TC_THREADS, Cfg::SMEM_BYTES, st, a, b, e, m_ext, n_ext, k_ext, kc, m_tiles, n_tiles, (int)total);
   return cudaPeekAtLastError();
 }
 

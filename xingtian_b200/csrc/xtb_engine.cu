@@ -273,7 +273,7 @@ static void launch_cfg(const AL& al, const BL& bl, const EP& ep, int M, int N, i
   kc = (kc + BK - 1) / BK * BK;
   int ks = (K + kc - 1) / kc;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, ks);
-  gemm_f32_kernel<BM, BN, BK, TM, TN, AL, BL, EP><<<grid, (BM / TM) * (BN / TN), 0, st>>>(al, bl, ep, M, N, K, kc);
+  XLAUNCH((gemm_f32_kernel<BM, BN, BK, TM, TN, AL, BL, EP>), grid, (BM / TM) * (BN / TN), 0, st, al, bl, ep, M, N, K, kc);
 }
 
 // split_ok: epilogue is atomic-accumulating so K may be partitioned over gridDim.z
@@ -318,6 +318,7 @@ static inline Planes w_planes(const xtb_net* n) { return Planes{(tc::bf16*)(n->w
 // bias + activation after a split-K forward (fp32 sums are already in `out`), planes kept current
 __global__ void bias_act_kernel(float* __restrict__ out, const float* __restrict__ bias, long long total, int N,
                                 float alpha, int act, tc::bf16* hi, long long lo_off) {
+  pdl_wait(); pdl_trigger();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) {
     float r = act_apply(act, alpha * out[i] + bias[i % N]);
@@ -372,7 +373,7 @@ static cudaError_t tc_dense_fwd(const LayerPlan& lp, Planes x, Planes w, const f
     e = tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, ks, st);
     if (e != cudaSuccess) return e;
     long long total = (long long)B * lp.N;
-    bias_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, b, total, lp.N, 1.f, lp.d.act, po.hi, po.lo_off);
+    XLAUNCH(bias_act_kernel, (unsigned)((total + 255) / 256), 256, 0, st, out, b, total, lp.N, 1.f, lp.d.act, po.hi, po.lo_off);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaPeekAtLastError();
   }
@@ -448,7 +449,7 @@ extern "C" int xtb_net_sync_weights(xtb_net* net, void* stream) {
   if (!net || !net->ws || !net->params) return fail(XTB_ERR_STATE, "xtb_net_sync_weights: net not bound");
   Planes w = w_planes(net);
   long long n = net->n_params;
-  tc::split_planes_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, S(stream)>>>(net->params, w.hi, w.lo_off, n);
+  XLAUNCH(tc::split_planes_kernel, (unsigned)((n / 4 + 255) / 256 + 1), 256, 0, S(stream), net->params, w.hi, w.lo_off, n);
   LAUNCH_CHECK();
   return XTB_OK;
 }
@@ -466,8 +467,8 @@ extern "C" int xtb_tc_gemm_test(int mode, const float* a, const float* b, float*
   tc::bf16 *pa = nullptr, *pb = nullptr;
   CUDA_TRY(cudaMalloc(&pa, 2 * na * sizeof(tc::bf16)));
   CUDA_TRY(cudaMalloc(&pb, 2 * nb * sizeof(tc::bf16)));
-  tc::split_planes_kernel<<<(unsigned)((na / 4 + 255) / 256 + 1), 256, 0, st>>>(a, pa, na, na);
-  tc::split_planes_kernel<<<(unsigned)((nb / 4 + 255) / 256 + 1), 256, 0, st>>>(b, pb, nb, nb);
+  XLAUNCH(tc::split_planes_kernel, (unsigned)((na / 4 + 255) / 256 + 1), 256, 0, st, a, pa, na, na);
+  XLAUNCH(tc::split_planes_kernel, (unsigned)((nb / 4 + 255) / 256 + 1), 256, 0, st, b, pb, nb, nb);
   cudaError_t e;
   tc::SrcDense as{pa, na, nullptr, mode == 2 ? M : K, mode == 2 ? K : M};
   tc::SrcDense bs{pb, nb, nullptr, mode == 1 ? K : N, mode == 1 ? N : K};
@@ -534,6 +535,7 @@ static void dense_wgrad(const LayerPlan& lp, const T* x, const int32_t* idx, con
 
 // bias gradient: db[n] = sum_m dy[m,n]
 __global__ void colsum_kernel(const float* __restrict__ dy, int M, int N, float* __restrict__ db) {
+  pdl_wait(); pdl_trigger();
   int n = blockIdx.x * 32 + (threadIdx.x & 31);
   int r0 = blockIdx.y * 1024 + (threadIdx.x >> 5);
   float s = 0.f;
@@ -599,7 +601,7 @@ static int op_decode(xtb_net* net, const void* obs, const int32_t* idx, int B, c
   if (!need) return XTB_OK;
   int per = net->tsize[0];
   dim3 grid((per / 16 + 255) / 256, B);
-  tc::decode_u8_kernel<<<grid, 256, 0, st>>>((const uint8_t*)obs, idx, per, obs_planes(net).hi);
+  XLAUNCH(tc::decode_u8_kernel, grid, 256, 0, st, (const uint8_t*)obs, idx, per, obs_planes(net).hi);
   LAUNCH_CHECK();
   return XTB_OK;
 }
@@ -647,7 +649,7 @@ static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, in
   if (need_colsum && !bias_done) {   // bias gradient = column sums of dY
     int Mb = lp.d.kind == XTB_CONV ? B * lp.g.P : B;
     dim3 gridb((lp.N + 31) / 32, (Mb + 1023) / 1024);
-    colsum_kernel<<<gridb, 256, 0, st>>>(dy, Mb, lp.N, db);
+    XLAUNCH(colsum_kernel, gridb, 256, 0, st, dy, Mb, lp.N, db);
     LAUNCH_CHECK();
   }
   return XTB_OK;
@@ -740,7 +742,7 @@ static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gathe
         !net->gout_planes_fresh) {
       Planes pg = gout_planes(net, t);
       long long n = (long long)batch * net->tsize[t];
-      tc::split_planes_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st>>>((const float*)(net->ws + net->gout_off[t]), pg.hi, pg.lo_off, n);
+      XLAUNCH(tc::split_planes_kernel, (unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st, (const float*)(net->ws + net->gout_off[t]), pg.hi, pg.lo_off, n);
       LAUNCH_CHECK();
     }
   }
@@ -805,14 +807,14 @@ extern "C" int xtb_net_bench_layer(xtb_net* net, int layer, int which, const voi
 extern "C" int xtb_categorical_sample(const float* logits, int batch, int adim, const float* uniforms,
                                       uint64_t seed, uint64_t offset, int32_t* action, float* logp, void* stream) {
   if (!logits || !action || !logp || batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_categorical_sample: bad argument");
-  sample_kernel<<<(batch + 127) / 128, 128, 0, S(stream)>>>(logits, batch, adim, uniforms, seed, offset, action, logp);
+  XLAUNCH(sample_kernel, (batch + 127) / 128, 128, 0, S(stream), logits, batch, adim, uniforms, seed, offset, action, logp);
   LAUNCH_CHECK();
   return XTB_OK;
 }
 
 extern "C" int xtb_argmax(const float* q, int batch, int adim, int32_t* action, void* stream) {
   if (!q || !action || batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_argmax: bad argument");
-  argmax_kernel<<<(batch + 127) / 128, 128, 0, S(stream)>>>(q, batch, adim, action);
+  XLAUNCH(argmax_kernel, (batch + 127) / 128, 128, 0, S(stream), q, batch, adim, action);
   LAUNCH_CHECK();
   return XTB_OK;
 }
@@ -825,7 +827,7 @@ extern "C" int xtb_gae(const float* value, const float* reward, const uint8_t* d
   if (n_env < 0 || n_step < 0) return fail(XTB_ERR_ARG, "xtb_gae: negative size");
   int threads = 128;  // 4 envs per block
   int blocks = (n_env * 32 + threads - 1) / threads;
-  gae_kernel<<<blocks, threads, 0, S(stream)>>>(value, reward, done, n_env, n_step, gamma, lam, sign_clip, adv,
+  XLAUNCH(gae_kernel, blocks, threads, 0, S(stream), value, reward, done, n_env, n_step, gamma, lam, sign_clip, adv,
                                                 old_value, target_value);
   LAUNCH_CHECK();
   return XTB_OK;
@@ -840,7 +842,7 @@ extern "C" int xtb_ppo_loss_grad(const float* logits, const float* v, const int3
     return fail(XTB_ERR_ARG, "xtb_ppo_loss_grad: null pointer");
   if (batch <= 0 || adim <= 0 || adim > MAX_ADIM) return fail(XTB_ERR_ARG, "xtb_ppo_loss_grad: batch/adim out of range");
   PpoHyperDev h{hp->clip_ratio, hp->ent_coef, hp->vf_clip, hp->critic_coef};
-  ppo_loss_kernel<<<(batch + 127) / 128, 128, 0, S(stream)>>>(logits, v, gather_idx, action, old_logp, adv, old_v,
+  XLAUNCH(ppo_loss_kernel, (batch + 127) / 128, 128, 0, S(stream), logits, v, gather_idx, action, old_logp, adv, old_v,
                                                               target_v, batch, adim, h, inv_count, dlogits, dv, loss_out);
   LAUNCH_CHECK();
   return XTB_OK;
@@ -856,7 +858,7 @@ extern "C" int xtb_vtrace_loss_grad(const float* tp_logits, const float* baselin
   if (n_traj <= 0 || step_len < 2 || adim <= 0 || adim > MAX_ADIM) return fail(XTB_ERR_ARG, "xtb_vtrace_loss_grad: bad sizes");
   int threads = 128;
   int blocks = (n_traj * 32 + threads - 1) / threads;
-  vtrace_kernel<<<blocks, threads, 0, S(stream)>>>(tp_logits, baseline, bp_logits, action, done, reward, n_traj,
+  XLAUNCH(vtrace_kernel, blocks, threads, 0, S(stream), tp_logits, baseline, bp_logits, action, done, reward, n_traj,
                                                    step_len, adim, gamma, dlogits, dbaseline, vs_out, pg_adv_out, loss_out);
   LAUNCH_CHECK();
   return XTB_OK;
@@ -868,7 +870,7 @@ extern "C" int xtb_dqn_loss_grad(const float* q, const float* q_next_target, con
                                  float* loss_out, void* stream) {
   if (!q || !q_next_target || !action || !reward || !done || !dq || !loss_out) return fail(XTB_ERR_ARG, "xtb_dqn_loss_grad: null pointer");
   if (batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_dqn_loss_grad: bad sizes");
-  dqn_loss_kernel<<<(batch + 127) / 128, 128, 0, S(stream)>>>(q, q_next_target, q_next_online, action, reward, done,
+  XLAUNCH(dqn_loss_kernel, (batch + 127) / 128, 128, 0, S(stream), q, q_next_target, q_next_online, action, reward, done,
                                                               batch, adim, gamma, inv_count, dq, y_out, loss_out);
   LAUNCH_CHECK();
   return XTB_OK;
@@ -878,7 +880,7 @@ extern "C" int xtb_mse_loss_grad(const float* q, const float* y, int batch, int 
                                  float* loss_out, void* stream) {
   if (!q || !y || !dq || !loss_out || batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_mse_loss_grad: bad argument");
   long long n = (long long)batch * adim;
-  mse_loss_kernel<<<(unsigned)((n + 127) / 128), 128, 0, S(stream)>>>(q, y, n, inv_count, dq, loss_out);
+  XLAUNCH(mse_loss_kernel, (unsigned)((n + 127) / 128), 128, 0, S(stream), q, y, n, inv_count, dq, loss_out);
   LAUNCH_CHECK();
   return XTB_OK;
 }
@@ -961,12 +963,12 @@ extern "C" int xtb_adam_step_net(xtb_adam* o, xtb_net* net, float grad_scale, vo
 static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream, tc::bf16* w_hi, long long w_lo) {
   if (!o || !params || !grads) return fail(XTB_ERR_ARG, "xtb_adam_step: null pointer");
   cudaStream_t st = S(stream);
-  sqnorm_kernel<<<o->n_blk, OPT_THREADS, 0, st>>>(grads, o->blk_seg, o->blk_beg, o->blk_len, o->norm_sq);
+  XLAUNCH(sqnorm_kernel, o->n_blk, OPT_THREADS, 0, st, grads, o->blk_seg, o->blk_beg, o->blk_len, o->norm_sq);
   LAUNCH_CHECK();
-  adam_prep_kernel<<<1, 32, 0, st>>>(o->st, o->norm_sq, o->seg_scale, o->n_seg, o->clip_mode, o->clip, grad_scale,
+  XLAUNCH(adam_prep_kernel, 1, 32, 0, st, o->st, o->norm_sq, o->seg_scale, o->n_seg, o->clip_mode, o->clip, grad_scale,
                                      o->lr, o->beta1, o->beta2);
   LAUNCH_CHECK();
-  adam_kernel<<<o->n_blk, OPT_THREADS, 0, st>>>(params, grads, o->m, o->v, o->blk_seg, o->blk_beg, o->blk_len,
+  XLAUNCH(adam_kernel, o->n_blk, OPT_THREADS, 0, st, params, grads, o->m, o->v, o->blk_seg, o->blk_beg, o->blk_len,
                                                 o->seg_scale, o->st, o->beta1, o->beta2, o->eps, w_hi, w_lo);
   LAUNCH_CHECK();
   return XTB_OK;
@@ -1044,9 +1046,9 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         a.hp = PpoHyperDev{hp->clip_ratio, hp->ent_coef, hp->vf_clip, hp->critic_coef}; a.inv_count = inv_world / mb;
         int blocks = std::max(1, std::min(148, (mb + 15) / 16));
         size_t shb = (size_t)(lpi.K * (adim + 1) + adim + 1) * sizeof(float);
-        if (kpl <= 2) ppo_heads_kernel<2, 8><<<blocks, 256, shb, S(stream)>>>(a);
-        else if (kpl <= 8) ppo_heads_kernel<8, 8><<<blocks, 256, shb, S(stream)>>>(a);
-        else ppo_heads_kernel<16, 4><<<blocks, 256, shb, S(stream)>>>(a);
+        if (kpl <= 2) XLAUNCH((ppo_heads_kernel<2, 8>), blocks, 256, shb, S(stream), a);
+        else if (kpl <= 8) XLAUNCH((ppo_heads_kernel<8, 8>), blocks, 256, shb, S(stream), a);
+        else XLAUNCH((ppo_heads_kernel<16, 4>), blocks, 256, shb, S(stream), a);
         LAUNCH_CHECK();
         int srcs[2] = {lpi.d.src, lv.d.src};
         net->gout_planes_fresh = true;    // the fused kernel wrote fp32 and planes
@@ -1160,16 +1162,16 @@ static int rollout_infer_launch(xtb_net* net, const void* obs, const int32_t* st
       const float* hv = (const float*)(net->ws + net->out_off[lv.d.src]);
       const float *wp = net->params + lpi.w_off, *bp = net->params + lpi.b_off, *wv = net->params + lv.w_off, *bv = net->params + lv.b_off;
       int blocks = std::max(1, std::min(148, (E + 7) / 8));
-      if (kpl <= 2) ppo_infer_heads_kernel<2, 8><<<blocks, 256, 0, S(stream)>>>(hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
-      else if (kpl <= 8) ppo_infer_heads_kernel<8, 8><<<blocks, 256, 0, S(stream)>>>(hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
-      else ppo_infer_heads_kernel<16, 8><<<blocks, 256, 0, S(stream)>>>(hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
+      if (kpl <= 2) XLAUNCH((ppo_infer_heads_kernel<2, 8>), blocks, 256, 0, S(stream), hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
+      else if (kpl <= 8) XLAUNCH((ppo_infer_heads_kernel<8, 8>), blocks, 256, 0, S(stream), hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
+      else XLAUNCH((ppo_infer_heads_kernel<16, 8>), blocks, 256, 0, S(stream), hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
     } else {
-      sample_rollout_kernel<<<(E + 127) / 128, 128, 0, S(stream)>>>(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), E, adim, seed,
+      XLAUNCH(sample_rollout_kernel, (E + 127) / 128, 128, 0, S(stream), xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), E, adim, seed,
                                                                    offset_dev, t, a_t, lp_t, v_o);
     }
     LAUNCH_CHECK();
   }
-  bump_counter_kernel<<<1, 1, 0, S(stream)>>>(offset_dev, T);
+  XLAUNCH(bump_counter_kernel, 1, 1, 0, S(stream), offset_dev, T);
   LAUNCH_CHECK();
   return XTB_OK;
 }
