@@ -39,10 +39,27 @@ class PPO(Algorithm):
 
     # -- data path ---------------------------------------------------------------------------
     def _stage(self, dst, arr, np_dtype):
-        """Copy one host array into device tensor `dst` through a pinned bounce buffer."""
+        """Copy one host array into device tensor `dst`; large arrays go through a persistent pair of pinned
+        bounce buffers (async H2D overlapping the next host memcpy) instead of a pageable, synchronous copy."""
         a = np.ascontiguousarray(arr, dtype=np_dtype).reshape(dst.shape)
         t = torch.from_numpy(a)
-        dst.copy_(t.pin_memory() if a.nbytes >= (1 << 20) else t, non_blocking=True)
+        if a.nbytes < (1 << 20):
+            dst.copy_(t, non_blocking=True)
+            return
+        ring = getattr(self, "_pin_ring", None)
+        if ring is None or ring[0][0].numel() < a.nbytes:
+            ring = [[torch.empty(a.nbytes, dtype=torch.uint8).pin_memory(), None] for _ in range(2)]
+            self._pin_ring, self._pin_next = ring, 0
+        buf, ev = ring[self._pin_next]
+        if ev is not None:
+            ev.synchronize()               # the previous H2D out of this buffer has finished
+        view = buf[:a.nbytes].view(t.dtype).view(t.shape)
+        view.copy_(t)
+        dst.copy_(view, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ring[self._pin_next][1] = ev
+        self._pin_next ^= 1
 
     def prepare_data(self, train_data, **kwargs):
         ro = self.actor.rollout

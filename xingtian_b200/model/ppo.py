@@ -172,17 +172,41 @@ class PPO(XTModel):
                                                  self.pi_t, self.v_t, C.c_uint64(self._sample_seed), _ptr(self._offset_dev),
                                                  _ptr(action), _ptr(logp), _ptr(value), 1 if self.use_graph else 0, stream_ptr()))
 
+    def _predict_io(self, batch):
+        """Persistent staging for the host-facing predict(): pinned input, device input, one packed
+        device/pinned output block [action | logp | value] so a call is 1 H2D + 1 graph launch + 1 D2H."""
+        io = self._pred_bufs.get(("io", batch))
+        if io is None:
+            dev = self.device
+            shape = (batch,) + tuple(self.state_dim)
+            out_dev = torch.empty(3, batch, dtype=torch.float32, device=dev)
+            io = dict(pin_in=torch.empty(shape, dtype=self._obs_dt).pin_memory(),
+                      obs=torch.empty(shape, dtype=self._obs_dt, device=dev), out_dev=out_dev,
+                      act=out_dev[0].view(torch.int32), logp=out_dev[1], val=out_dev[2],
+                      pin_out=torch.empty(3, batch, dtype=torch.float32).pin_memory())
+            self._pred_bufs[("io", batch)] = io
+        return io
+
     def predict(self, state, uniforms=None):
         """xt/model/ppo/ppo.py:104-109: (action [B] int32, logp [B,1], v [B,1])."""
         state = np.ascontiguousarray(state, dtype=np.uint8 if self.input_dtype == "uint8" else np.float32)
         batch = state.shape[0]
-        bufs = self._pred_buffers(batch)
-        bufs["obs"].copy_(torch.from_numpy(state), non_blocking=True)
-        u = None
-        if uniforms is not None:
-            u = torch.from_numpy(np.ascontiguousarray(uniforms, np.float32)).to(self.device)
-        action, logp, v = self.predict_device(bufs["obs"], batch, u)
-        return (action.cpu().numpy(), logp.cpu().numpy().reshape(batch, 1), v.cpu().numpy().reshape(batch, 1))
+        if uniforms is not None or batch > self.net.max_batch:
+            bufs = self._pred_buffers(batch)
+            bufs["obs"].copy_(torch.from_numpy(state), non_blocking=True)
+            u = None
+            if uniforms is not None:
+                u = torch.from_numpy(np.ascontiguousarray(uniforms, np.float32)).to(self.device)
+            action, logp, v = self.predict_device(bufs["obs"], batch, u)
+            return (action.cpu().numpy(), logp.cpu().numpy().reshape(batch, 1), v.cpu().numpy().reshape(batch, 1))
+        io = self._predict_io(batch)
+        io["pin_in"].copy_(torch.from_numpy(state))
+        io["obs"].copy_(io["pin_in"], non_blocking=True)
+        self.rollout_infer_device(io["obs"], None, batch, 1, io["act"], io["logp"], io["val"])
+        io["pin_out"].copy_(io["out_dev"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = io["pin_out"].numpy()
+        return (out[0].view(np.int32).copy(), out[1].reshape(batch, 1).copy(), out[2].reshape(batch, 1).copy())
 
     # -- training ----------------------------------------------------------------------------
     def make_perm(self, nbatch):
