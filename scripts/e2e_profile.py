@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Host-side time of the plugin entry points (predict / prepare_data / train) at C2 shapes."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import xingtian_b200 as xb
+from oracle import xt_oracle as orc
+E, T = 32, 128
+info = {"actor": {"model_name": "PpoCnn", "state_dim": [84, 84, 4], "action_dim": 4, "input_dtype": "uint8",
+                  "model_config": {"BATCH_SIZE": 320, "ENTROPY_LOSS": 0.003, "LOSS_CLIPPING": 0.1, "LR": 0.00025, "NUM_SGD_ITER": 4,
+                                   "hidden_sizes": [256], "action_type": "Categorical", "init_seed": 0}, "max_predict_batch": 320}}
+alg = xb.alg_builder("PPO", info, {"instance_num": E, "agent_num": 1})
+ro = orc.synth_ppo_rollout(0, E, T)
+host_obs = [np.ascontiguousarray(ro["obs"][np.arange(E) * T + t]) for t in range(T)]
+traj = [dict(cur_state=ro["obs"][e * T:(e + 1) * T], action=ro["action"][e * T:(e + 1) * T], logp=ro["logp"][e * T:(e + 1) * T],
+             value=ro["value"][e], reward=ro["reward"][e * T:(e + 1) * T], done=ro["done"][e * T:(e + 1) * T]) for e in range(E)]
+for rep in range(3):
+    t0 = time.perf_counter()
+    for t in range(T):
+        alg.actor.predict(host_obs[t])
+    t1 = time.perf_counter()
+    for e in range(E):
+        alg.prepare_data(traj[e])
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    alg.train()
+    t3 = time.perf_counter()
+    print("predict x128 %.1f ms | prepare_data x32 %.1f ms | train %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))

@@ -54,7 +54,7 @@ class PPO(Algorithm):
         if ev is not None:
             ev.synchronize()               # the previous H2D out of this buffer has finished
         view = buf[:a.nbytes].view(t.dtype).view(t.shape)
-        view.copy_(t)
+        np.copyto(view.numpy(), a)         # plain memcpy into pinned memory (no torch thread pool)
         dst.copy_(view, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()

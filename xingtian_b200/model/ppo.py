@@ -184,6 +184,7 @@ class PPO(XTModel):
                       obs=torch.empty(shape, dtype=self._obs_dt, device=dev), out_dev=out_dev,
                       act=out_dev[0].view(torch.int32), logp=out_dev[1], val=out_dev[2],
                       pin_out=torch.empty(3, batch, dtype=torch.float32).pin_memory())
+            io["pin_in_np"] = io["pin_in"].numpy()     # plain memcpy into pinned memory (no torch thread pool)
             self._pred_bufs[("io", batch)] = io
         return io
 
@@ -200,7 +201,7 @@ class PPO(XTModel):
             action, logp, v = self.predict_device(bufs["obs"], batch, u)
             return (action.cpu().numpy(), logp.cpu().numpy().reshape(batch, 1), v.cpu().numpy().reshape(batch, 1))
         io = self._predict_io(batch)
-        io["pin_in"].copy_(torch.from_numpy(state))
+        np.copyto(io["pin_in_np"], state)
         io["obs"].copy_(io["pin_in"], non_blocking=True)
         self.rollout_infer_device(io["obs"], None, batch, 1, io["act"], io["logp"], io["val"])
         io["pin_out"].copy_(io["out_dev"], non_blocking=True)
