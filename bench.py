@@ -323,14 +323,14 @@ def run_b200(args):
         if kind == "conv":
             oh, ow = (ish[0] - sp["k"]) // sp["s"] + 1, (ish[1] - sp["k"]) // sp["s"] + 1
             shapes[name] = (oh, ow, sp["cout"])
-            m, n, k = BATCH * oh * ow, sp["cout"], sp["k"] * sp["k"] * ish[2]
+            gm, gn, gk = BATCH * oh * ow, sp["cout"], sp["k"] * sp["k"] * ish[2]
         else:
             shapes[name] = (sp["n"],)
-            m, n, k = BATCH, sp["n"], int(np.prod(ish))
+            gm, gn, gk = BATCH, sp["n"], int(np.prod(ish))
         for which, tag in ((0, "forward"), (1, "weight-gradient"), (2, "data-gradient")):
             if which == 2 and src == "obs":
                 continue
-            ops.append((li, which, "%s %s (M=%d N=%d K=%d)" % (name, tag, m, n, k), 2.0 * m * n * k))
+            ops.append((li, which, "%s %s (M=%d N=%d K=%d)" % (name, tag, gm, gn, gk), 2.0 * gm * gn * gk))
     reps = 10
     best = None
     for li, which, label, flop in ops:
