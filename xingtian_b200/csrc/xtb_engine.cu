@@ -329,7 +329,8 @@ __global__ void bias_act_kernel(float* __restrict__ out, const float* __restrict
 
 // first-layer convs read the decoded uint8 frames: 2 taps per 16-byte chunk need even geometry
 static bool tc_conv_ok(const xtb_net* net, const LayerPlan& lp) {
-  if (!g_tc_mode || lp.d.kind != XTB_CONV || lp.N % 8 || lp.N > 64 || lp.K % 8) return false;
+  // K/8 column groups of a tile are cached in shared memory (TC_MAXCOLS); forward epilogues cannot split K
+  if (!g_tc_mode || lp.d.kind != XTB_CONV || lp.N % 8 || lp.N > 64 || lp.K % 8 || lp.K / 8 > tc::TC_MAXCOLS) return false;
   if (lp.d.src == 0) {
     if (!net->desc.input_u8 || lp.cshift != 2) return false;
     return lp.g.KW % 2 == 0 && lp.g.padL % 2 == 0 && lp.g.S % 2 == 0 && lp.g.W % 2 == 0;
@@ -340,7 +341,9 @@ static bool tc_dense_ok(const LayerPlan& lp) {
   return g_tc_mode && lp.d.kind == XTB_DENSE && lp.d.src != 0 && lp.K % 8 == 0 && lp.N % 8 == 0 && lp.K >= 64 && lp.N >= 16;
 }
 static bool tc_conv_dgrad_ok(const LayerPlan& lp) {
-  return g_tc_mode && lp.d.kind == XTB_CONV && lp.d.src != 0 && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.oshift >= 3;
+  if (!(g_tc_mode && lp.d.kind == XTB_CONV && lp.d.src != 0 && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.oshift >= 3)) return false;
+  const bool cls = lp.g.S > 1 && lp.g.KH % lp.g.S == 0 && lp.g.KW % lp.g.S == 0;
+  return (cls ? lp.Kd / (lp.g.S * lp.g.S) : lp.Kd) / 8 <= tc::TC_MAXCOLS;
 }
 
 template <bool PAD>
@@ -412,7 +415,7 @@ static cudaError_t tc_dense_wgrad(const LayerPlan& lp, Planes x, Planes dy, floa
 static cudaError_t tc_conv_dgrad(const LayerPlan& lp, Planes dy, Planes w, float* gsrc, const float* xsrc, Planes pg, int acc,
                                  float* db_src, int B, cudaStream_t st) {
   const ConvGeom& g = lp.g;
-  if (g.S > 1 && g.KH % g.S == 0 && g.KW % g.S == 0 && (lp.Kd / (g.S * g.S)) / 8 <= tc::TC_MAXCOLS) {
+  if (g.S > 1 && g.KH % g.S == 0 && g.KW % g.S == 0) {
     // strided transposed conv: one dense GEMM per parity class of the input position
     tc::DgradClass k{g.S, lp.sshift, g.padT, g.padL, g.H, g.W, (g.H + g.S - 1) / g.S, (g.W + g.S - 1) / g.S, 0, 0, 0, 0};
     int M = B * k.nY * k.nX;
