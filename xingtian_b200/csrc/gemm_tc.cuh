@@ -19,13 +19,16 @@
 //   warps 0-3 : epilogue after the K loop: tcgen05.ld (32 lanes x 16 columns per instruction),
 //               bias+activation / activation-gradient mask / split-K atomic accumulation.
 //
-// Shared-memory tile layout (both majors): addr(row, chunk) = chunk*ROWS*16 + row*16.
-//   K-major operand  (rows = M/N entity, chunks along K):  core matrix = 8 rows x 16 B contiguous,
-//       SBO (8-row group stride) = 128 B, LBO (stride between the two K chunks of one MMA) = ROWS*16.
-//   MN-major operand (rows = K entity, chunks along M/N): core matrix = 8 K-rows x 16 B contiguous,
-//       LBO (stride between 8-row K groups) = 128 B, SBO (stride between 16-byte MN chunks) = ROWS*16.
-// The same row-gather therefore feeds the forward GEMM (K-major) and the weight-gradient GEMM
-// (MN-major) without any transpose.
+// Shared-memory tile layouts:
+//   K-major operand  (rows = M/N entity, 64 K elements per stage): SWIZZLE_128B canonical layout -- row r is 128 B at
+//       r*128, its 16-byte chunk c stored at position c ^ (r & 7); SBO (8-row group stride) = 1024 B; one K=16 step =
+//       +32 B on the descriptor start address.  Lanes of a producer warp walk the 8 chunks of a row, so a warp
+//       instruction reads 4 rows x 128 contiguous bytes and writes 4 conflict-free smem rows.
+//   MN-major operand (rows = K entity, chunks along M/N): no-swizzle canonical layout addr(row,chunk) =
+//       chunk*ROWS*16 + row*16; core matrix = 8 K-rows x 16 B contiguous, LBO (stride between 8-row K groups) = 128 B,
+//       SBO (stride between 16-byte MN chunks) = ROWS*16.
+// The im2col row gather therefore feeds the forward GEMM (K-major) and the weight-gradient GEMM (MN-major: the
+// transposed use of the same rows) without any transpose.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -117,6 +120,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version = 1 (Blackwell)
   return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+// K-major operand in the SWIZZLE_128B canonical layout: rows of 128 B (64 bf16) at 128-byte stride, the 16-byte
+// chunk index XORed with (row & 7); 8-row groups are 1024 B apart (SBO); the tile base is 1024-byte aligned and a
+// K=16 step advances the start address by 32 B inside the swizzle atom.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major)
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32; // SBO
+  d |= (uint64_t)1 << 46;                       // descriptor version = 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B
+  return d;
 }
 // instruction descriptor: bf16 x bf16 -> fp32, M=128
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
@@ -472,6 +487,22 @@ struct TcEpiAtomic {
 // ------------------------------------------------------------------------------------------
 constexpr int TC_PRODUCERS = 128;
 constexpr int TC_THREADS = 288;
+
+// Optional timeline trace (XTB_TC_TRACE builds only): %globaltimer stamps per CTA / role / tile event.
+#ifdef XTB_TC_TRACE
+__device__ unsigned long long* g_tc_trace = nullptr;     // [cta][slot] ; slot 0 = count
+constexpr int TC_TRACE_SLOTS = 256;
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void trace(int code) {
+  if (!g_tc_trace) return;
+  unsigned long long* b = g_tc_trace + (size_t)blockIdx.x * TC_TRACE_SLOTS;
+  unsigned long long i = atomicAdd(b, 1ULL) + 1;
+  if (i < TC_TRACE_SLOTS) b[i] = (gtimer() << 8) | (unsigned)code;
+}
+#define TC_TRACE(code) do { if ((threadIdx.x & 31) == 0) trace(code); } while (0)
+#else
+#define TC_TRACE(code) do {} while (0)
+#endif
 constexpr int TC_MAXCOLS = 128;   // cached column groups per operand (K-major conv operands: K/8 <= 128)
 
 template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT>
@@ -489,15 +520,22 @@ struct TcCfg {
   static constexpr int CTAS_PER_SM = (2 * SMEM_BYTES + 8192 <= 227 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
 
-// per-operand producer state: rows are re-initialised when they change (K-major: once per tile; MN-major: per stage)
+// Per-operand producer.
+//  MN-major operand (tile rows = K entity): no-swizzle layout addr(row,chunk) = chunk*ROWS*16 + row*16, lanes run
+//    along rows (consecutive K rows are adjacent in memory for weights / dY), row state in registers per stage.
+//  K-major operand (tile rows = M/N entity, KT = 64): SWIZZLE_128B layout, lanes run along the 8 chunks of a row so
+//    that a warp instruction reads 4 rows x 128 contiguous bytes (instead of 32 scattered 16-byte pieces, which made
+//    the gather L1-tag bound) and writes 4 conflict-free 128-byte rows; row state is cached per tile in shared memory.
 template <int ROWS, int CHUNKS, bool MN, bool SPLIT, class SRC>
 struct Producer {
   static constexpr int SLOTS = ROWS * CHUNKS;
   static_assert(SLOTS % TC_PRODUCERS == 0, "tile slots must tile the producer threads");
+  static_assert(MN || CHUNKS == 8, "K-major tiles are 64 elements (one 128-byte swizzle atom) wide");
   static constexpr int PER = SLOTS / TC_PRODUCERS;
-  static constexpr int NROW = (ROWS >= TC_PRODUCERS) ? ROWS / TC_PRODUCERS : 1;   // distinct rows per thread
+  static constexpr int NROW = (ROWS >= TC_PRODUCERS) ? ROWS / TC_PRODUCERS : 1;   // distinct rows per thread (MN-major)
   typename SRC::Row rows[NROW];
 
+  // ---- MN-major
   __device__ __forceinline__ void init_rows(const SRC& src, int row0, int row_lim, int tid) {
 #pragma unroll
     for (int q = 0; q < NROW; q++) {
@@ -506,7 +544,6 @@ struct Producer {
       if (row0 + r >= row_lim) rows[q].valid = 0;
     }
   }
-  // col_base: first column of the cached table; cols: table (unused when !SRC::TABLE)
   __device__ __forceinline__ void produce(const SRC& src, const Col* cols, int col_base, uint32_t hi_smem, uint32_t lo_smem,
                                           int col0, int col_lim, int tid) {
     const bf16* dummy = src.any();
@@ -522,6 +559,32 @@ struct Producer {
         p = src.chunk(row, ci);
       }
       uint32_t off = (uint32_t)c * ROWS * 16 + (uint32_t)r * 16;
+      cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
+      if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
+    }
+  }
+  // ---- K-major
+  static __device__ __forceinline__ void fill_rows(const SRC& src, typename SRC::Row* rows_sm, int row0, int row_lim, int tid) {
+    for (int r = tid; r < ROWS; r += TC_PRODUCERS) {
+      typename SRC::Row rw;
+      src.init_row(row0 + r, rw);
+      if (row0 + r >= row_lim) rw.valid = 0;
+      rows_sm[r] = rw;
+    }
+  }
+  static __device__ __forceinline__ void produce_k(const SRC& src, const typename SRC::Row* rows_sm, const Col* cols, int col_base,
+                                                   uint32_t hi_smem, uint32_t lo_smem, int k0, int k_end, int tid) {
+    const bf16* dummy = src.any();
+    const int c = tid & 7;
+    const int gcol = k0 + 8 * c;
+    Col ci = Col{0, 0};
+    const bool col_ok = gcol < k_end;
+    if (col_ok) ci = SRC::TABLE ? cols[(gcol - col_base) >> 3] : src.col_info(gcol);
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      int r = (tid >> 3) + i * (TC_PRODUCERS / 8);
+      const bf16* p = col_ok ? src.chunk(rows_sm[r], ci) : nullptr;
+      uint32_t off = (uint32_t)r * 128 + (uint32_t)((c ^ (r & 7)) << 4);
       cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
       if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
     }
@@ -543,6 +606,8 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   __shared__ uint32_t tmem_slot;
   __shared__ Col col_tab[2][2][TC_MAXCOLS];     // [tile parity][operand][column group]
   __shared__ float epi_sh[64];                  // epilogue reductions (bias gradients)
+  __shared__ typename ASRC::Row a_rows[2][A_MN ? 1 : 128];   // K-major operands: per-tile row state
+  __shared__ typename BSRC::Row b_rows[2][B_MN ? 1 : NT];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
@@ -559,8 +624,10 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   tc_fence_after();
   // prologue done (barriers, TMEM, no global memory touched): wait for the producer grid, then let the next
   // kernel start its own prologue underneath this one
+  TC_TRACE(1);      // prologue done
   pdl_wait();
   pdl_trigger();
+  TC_TRACE(2);      // dependency satisfied
   const uint32_t tmem_base = tmem_slot;
   const uint32_t smem_base = smem_u32(smem);
   const int mn_tiles = m_tiles * n_tiles;
@@ -588,9 +655,9 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
         int base = B_MN ? n0 : kbeg, lim = B_MN ? min(n_ext, n0 + NT) : kend;
         for (int j = tid; base + 8 * j < lim && j < TC_MAXCOLS; j += TC_PRODUCERS) tb[j] = bsrc.col_info(base + 8 * j);
       }
-      if (ASRC::TABLE || BSRC::TABLE) producer_bar_sync();
-      if (!A_MN) pa.init_rows(asrc, m0, m_ext, tid);
-      if (!B_MN) pb.init_rows(bsrc, n0, n_ext, tid);
+      if (!A_MN) pa.fill_rows(asrc, a_rows[it & 1], m0, m_ext, tid);
+      if (!B_MN) pb.fill_rows(bsrc, b_rows[it & 1], n0, n_ext, tid);
+      if (ASRC::TABLE || BSRC::TABLE || !A_MN || !B_MN) producer_bar_sync();
       for (int t = 0; t < n_kt; t++) {
         const int k0 = kbeg + t * KT;
         if (A_MN) pa.init_rows(asrc, k0, kend, tid);
@@ -600,9 +667,12 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
         uint32_t sa_lo = sa + Cfg::A_BYTES;
         uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
         uint32_t sb_lo = sb + Cfg::B_BYTES;
-        pa.produce(asrc, ta, A_MN ? m0 : kbeg, sa, sa_lo, A_MN ? m0 : k0, A_MN ? m_ext : kend, tid);
-        pb.produce(bsrc, tb, B_MN ? n0 : kbeg, sb, sb_lo, B_MN ? n0 : k0, B_MN ? n_ext : kend, tid);
+        if (A_MN) pa.produce(asrc, ta, m0, sa, sa_lo, m0, m_ext, tid);
+        else pa.produce_k(asrc, a_rows[it & 1], ta, kbeg, sa, sa_lo, k0, kend, tid);
+        if (B_MN) pb.produce(bsrc, tb, n0, sb, sb_lo, n0, n_ext, tid);
+        else pb.produce_k(bsrc, b_rows[it & 1], tb, kbeg, sb, sb_lo, k0, kend, tid);
         cp_async_mbar_arrive_noinc(full0 + 8 * stage);
+        if (warp == 0) TC_TRACE(10);   // stage issued
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -624,6 +694,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       tc_fence_after();
       for (int t = 0; t < n_kt; t++) {
         mbar_wait(full0 + 8 * stage, phase);
+        TC_TRACE(20);                  // stage data landed
         if (lane == 0) {
           fence_proxy_async();      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           tc_fence_after();
@@ -633,11 +704,12 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
           uint32_t sb_lo = sb + Cfg::B_BYTES;
 #pragma unroll
           for (int j = 0; j < KT / 16; j++) {
-            uint64_t ah = make_desc(sa + j * A_KSTEP, A_LBO, A_SBO);
-            uint64_t bh = make_desc(sb + j * B_KSTEP, B_LBO, B_SBO);
+            // MN-major: no-swizzle canonical tile, 16 K rows per step; K-major: 128B-swizzled tile, 32 B per step
+            uint64_t ah = A_MN ? make_desc(sa + j * A_KSTEP, A_LBO, A_SBO) : make_desc_sw128(sa + j * 32);
+            uint64_t bh = B_MN ? make_desc(sb + j * B_KSTEP, B_LBO, B_SBO) : make_desc_sw128(sb + j * 32);
             umma_bf16(acc, ah, bh, IDESC, (t > 0 || j > 0) ? 1u : 0u);
-            if (B_SPLIT) umma_bf16(acc, ah, make_desc(sb_lo + j * B_KSTEP, B_LBO, B_SBO), IDESC, 1u);
-            if (A_SPLIT) umma_bf16(acc, make_desc(sa_lo + j * A_KSTEP, A_LBO, A_SBO), bh, IDESC, 1u);
+            if (B_SPLIT) umma_bf16(acc, ah, B_MN ? make_desc(sb_lo + j * B_KSTEP, B_LBO, B_SBO) : make_desc_sw128(sb_lo + j * 32), IDESC, 1u);
+            if (A_SPLIT) umma_bf16(acc, A_MN ? make_desc(sa_lo + j * A_KSTEP, A_LBO, A_SBO) : make_desc_sw128(sa_lo + j * 32), bh, IDESC, 1u);
           }
           umma_commit(empty0 + 8 * stage);            // frees the smem stage when these MMAs retire
           if (t == n_kt - 1) umma_commit(tfull0 + 8 * buf);   // accumulator complete
@@ -661,6 +733,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       const int buf = it & 1;
       if (CLASSES) epi.set_class(z);
       mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
+      if (warp == 5) TC_TRACE(30);     // accumulator ready
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT;
@@ -672,6 +745,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * buf);
+      if (warp == 5) TC_TRACE(31);     // tile stored
     }
     epi.finish(est, epi_sh, NT);
   }
@@ -680,6 +754,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    TC_TRACE(3);
   }
 }
 

@@ -457,6 +457,13 @@ extern "C" int xtb_net_sync_weights(xtb_net* net, void* stream) {
   return XTB_OK;
 }
 
+#ifdef XTB_TC_TRACE
+extern "C" int xtb_tc_trace_set(unsigned long long* buf) {
+  CUDA_TRY(cudaMemcpyToSymbol(tc::g_tc_trace, &buf, sizeof buf));
+  return XTB_OK;
+}
+#endif
+
 // Self-test of the three operand-major combinations on plain matrices (see tests/test_gpu_tc.py):
 //   mode 0: C[M,N] = A[M,K]   * B[K,N]      (A K-major, B MN-major : forward)
 //   mode 1: C[M,N] = A[M,K]   * Bt[N,K]^T   (both K-major         : data gradient)
