@@ -133,6 +133,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B
   return d;
 }
+// MN-major operand, 128 MN elements x 64 K rows, SWIZZLE_128B: K row r of MN-half h is 128 B at h*8192 + r*128 with
+// its 16-byte chunk index XORed with (r & 7); LBO = 8192 (next 64 MN elements), SBO = 1024 (next 8 K rows); one
+// K=16 step = two 8-row groups = +2048 B.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((8192u >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // instruction descriptor: bf16 x bf16 -> fp32, M=128
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -563,6 +575,26 @@ struct Producer {
       if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
     }
   }
+  // ---- MN-major, 128 MN elements (the A operand of a weight gradient): swizzled, lanes along the 16 chunks of a row
+  static __device__ __forceinline__ void produce_mn16(const SRC& src, const typename SRC::Row* rows_sm, const Col* cols, int col_base,
+                                                      uint32_t hi_smem, uint32_t lo_smem, int mn0, int mn_ext, int tid) {
+    static_assert(!MN || CHUNKS != 16 || ROWS == 64, "swizzled MN-major tiles hold 64 K rows");
+    const bf16* dummy = src.any();
+    const int c = tid & 15;
+    const int gcol = mn0 + 8 * c;
+    Col ci = Col{0, 0};
+    const bool col_ok = gcol < mn_ext;
+    if (col_ok) ci = SRC::TABLE ? cols[(gcol - col_base) >> 3] : src.col_info(gcol);
+    const uint32_t half = (uint32_t)(c >> 3) * 8192u;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      int r = (tid >> 4) + i * (TC_PRODUCERS / 16);
+      const bf16* p = col_ok ? src.chunk(rows_sm[r], ci) : nullptr;
+      uint32_t off = half + (uint32_t)r * 128 + (uint32_t)(((c & 7) ^ (r & 7)) << 4);
+      cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
+      if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
+    }
+  }
   // ---- K-major
   static __device__ __forceinline__ void fill_rows(const SRC& src, typename SRC::Row* rows_sm, int row0, int row_lim, int tid) {
     for (int r = tid; r < ROWS; r += TC_PRODUCERS) {
@@ -606,7 +638,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   __shared__ uint32_t tmem_slot;
   __shared__ Col col_tab[2][2][TC_MAXCOLS];     // [tile parity][operand][column group]
   __shared__ float epi_sh[64];                  // epilogue reductions (bias gradients)
-  __shared__ typename ASRC::Row a_rows[2][A_MN ? 1 : 128];   // K-major operands: per-tile row state
+  __shared__ typename ASRC::Row a_rows[2][A_MN ? KT : 128];  // K-major: per-tile row state; MN-major A: per-stage rows
   __shared__ typename BSRC::Row b_rows[2][B_MN ? 1 : NT];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -660,14 +692,14 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       if (ASRC::TABLE || BSRC::TABLE || !A_MN || !B_MN) producer_bar_sync();
       for (int t = 0; t < n_kt; t++) {
         const int k0 = kbeg + t * KT;
-        if (A_MN) pa.init_rows(asrc, k0, kend, tid);
+        if (A_MN) { pa.fill_rows(asrc, a_rows[t & 1], k0, kend, tid); producer_bar_sync(); }
         if (B_MN) pb.init_rows(bsrc, k0, kend, tid);
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         uint32_t sa_lo = sa + Cfg::A_BYTES;
         uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
         uint32_t sb_lo = sb + Cfg::B_BYTES;
-        if (A_MN) pa.produce(asrc, ta, m0, sa, sa_lo, m0, m_ext, tid);
+        if (A_MN) pa.produce_mn16(asrc, a_rows[t & 1], ta, m0, sa, sa_lo, m0, m_ext, tid);
         else pa.produce_k(asrc, a_rows[it & 1], ta, kbeg, sa, sa_lo, k0, kend, tid);
         if (B_MN) pb.produce(bsrc, tb, n0, sb, sb_lo, n0, n_ext, tid);
         else pb.produce_k(bsrc, b_rows[it & 1], tb, kbeg, sb, sb_lo, k0, kend, tid);
@@ -705,11 +737,11 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
 #pragma unroll
           for (int j = 0; j < KT / 16; j++) {
             // MN-major: no-swizzle canonical tile, 16 K rows per step; K-major: 128B-swizzled tile, 32 B per step
-            uint64_t ah = A_MN ? make_desc(sa + j * A_KSTEP, A_LBO, A_SBO) : make_desc_sw128(sa + j * 32);
+            uint64_t ah = A_MN ? make_desc_mn_sw128(sa + j * 2048) : make_desc_sw128(sa + j * 32);
             uint64_t bh = B_MN ? make_desc(sb + j * B_KSTEP, B_LBO, B_SBO) : make_desc_sw128(sb + j * 32);
             umma_bf16(acc, ah, bh, IDESC, (t > 0 || j > 0) ? 1u : 0u);
             if (B_SPLIT) umma_bf16(acc, ah, B_MN ? make_desc(sb_lo + j * B_KSTEP, B_LBO, B_SBO) : make_desc_sw128(sb_lo + j * 32), IDESC, 1u);
-            if (A_SPLIT) umma_bf16(acc, A_MN ? make_desc(sa_lo + j * A_KSTEP, A_LBO, A_SBO) : make_desc_sw128(sa_lo + j * 32), bh, IDESC, 1u);
+            if (A_SPLIT) umma_bf16(acc, A_MN ? make_desc_mn_sw128(sa_lo + j * 2048) : make_desc_sw128(sa_lo + j * 32), bh, IDESC, 1u);
           }
           umma_commit(empty0 + 8 * stage);            // frees the smem stage when these MMAs retire
           if (t == n_kt - 1) umma_commit(tfull0 + 8 * buf);   // accumulator complete
