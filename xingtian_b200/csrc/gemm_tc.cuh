@@ -208,6 +208,10 @@ __device__ __forceinline__ void store_plane1(__nv_bfloat16* hi_plane, long long 
 //          the kernel caches it in shared memory once per tile when TABLE is set)
 //   chunk(row, col) -> hi-plane address of the 8 elements, or NULL = zeros;  lo plane = hi + lo_off
 // ------------------------------------------------------------------------------------------
+constexpr int TC_PRODUCERS = 256;                 // 8 producer warps: the gathers are issue-latency bound per warp
+constexpr int TC_MMA_WARP = TC_PRODUCERS / 32;    // warp 8
+constexpr int TC_THREADS = TC_PRODUCERS + 32 + 128;   // + MMA warp + 4 epilogue warps (TMEM lane quarters 1,2,3,0)
+
 typedef __nv_bfloat16 bf16;
 struct Col { int a, b; };
 
@@ -455,7 +459,7 @@ struct TcEpiDgrad {
       }
     }
     asm volatile("bar.sync 2, 128;" ::: "memory");
-    int t = (threadIdx.x - 160);
+    int t = (int)threadIdx.x - (TC_PRODUCERS + 32);
     if (t >= 0 && t < nt && t < N) atomicAdd(db + t, sh[t]);
   }
 };
@@ -489,16 +493,14 @@ struct TcEpiAtomic {
 
 // ------------------------------------------------------------------------------------------
 // The kernel: persistent, warp-specialised.
-//   warps 0-3  producers   (cp.async gathers into the stage ring)
-//   warp  4    MMA issuer  (tcgen05.mma into one of two TMEM accumulator buffers)
-//   warps 5-8  epilogue    (tcgen05.ld of the other buffer -> global) -- overlaps the next tile's main loop
+//   warps 0-7  producers   (cp.async gathers into the stage ring)
+//   warp  8    MMA issuer  (tcgen05.mma into one of two TMEM accumulator buffers)
+//   warps 9-12 epilogue    (tcgen05.ld of the other buffer -> global) -- overlaps the next tile's main loop
 // Each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  of the (m-tile, n-tile, k-split) space.
 //   A_MN / B_MN : operand is MN-major (its tile rows are the K entity) instead of K-major.
 //   KT          : reduction elements per pipeline stage;  NT : N tile = UMMA N (16..256, multiple of 16)
 //   A_SPLIT / B_SPLIT : operand carries a bf16 residual plane (bf16x3); false = exact in bf16
 // ------------------------------------------------------------------------------------------
-constexpr int TC_PRODUCERS = 128;
-constexpr int TC_THREADS = 288;
 
 // Optional timeline trace (XTB_TC_TRACE builds only): %globaltimer stamps per CTA / role / tile event.
 #ifdef XTB_TC_TRACE
@@ -541,13 +543,12 @@ struct TcCfg {
 template <int ROWS, int CHUNKS, bool MN, bool SPLIT, class SRC>
 struct Producer {
   static constexpr int SLOTS = ROWS * CHUNKS;
-  static_assert(SLOTS % TC_PRODUCERS == 0, "tile slots must tile the producer threads");
   static_assert(MN || CHUNKS == 8, "K-major tiles are 64 elements (one 128-byte swizzle atom) wide");
-  static constexpr int PER = SLOTS / TC_PRODUCERS;
+  static constexpr int PER = (SLOTS + TC_PRODUCERS - 1) / TC_PRODUCERS;
   static constexpr int NROW = (ROWS >= TC_PRODUCERS) ? ROWS / TC_PRODUCERS : 1;   // distinct rows per thread (MN-major)
   typename SRC::Row rows[NROW];
 
-  // ---- MN-major
+  // ---- MN-major, no swizzle (weights / dY rows: consecutive K rows are adjacent in memory)
   __device__ __forceinline__ void init_rows(const SRC& src, int row0, int row_lim, int tid) {
 #pragma unroll
     for (int q = 0; q < NROW; q++) {
@@ -562,6 +563,7 @@ struct Producer {
 #pragma unroll
     for (int i = 0; i < PER; i++) {
       int s = tid + i * TC_PRODUCERS;
+      if (SLOTS % TC_PRODUCERS != 0 && s >= SLOTS) break;
       int r = s % ROWS, c = s / ROWS;
       int gcol = col0 + 8 * c;
       const typename SRC::Row& row = rows[(ROWS >= TC_PRODUCERS) ? (i % NROW) : 0];
@@ -578,7 +580,6 @@ struct Producer {
   // ---- MN-major, 128 MN elements (the A operand of a weight gradient): swizzled, lanes along the 16 chunks of a row
   static __device__ __forceinline__ void produce_mn16(const SRC& src, const typename SRC::Row* rows_sm, const Col* cols, int col_base,
                                                       uint32_t hi_smem, uint32_t lo_smem, int mn0, int mn_ext, int tid) {
-    static_assert(!MN || CHUNKS != 16 || ROWS == 64, "swizzled MN-major tiles hold 64 K rows");
     const bf16* dummy = src.any();
     const int c = tid & 15;
     const int gcol = mn0 + 8 * c;
@@ -586,16 +587,18 @@ struct Producer {
     const bool col_ok = gcol < mn_ext;
     if (col_ok) ci = SRC::TABLE ? cols[(gcol - col_base) >> 3] : src.col_info(gcol);
     const uint32_t half = (uint32_t)(c >> 3) * 8192u;
+    constexpr int RPP = TC_PRODUCERS / 16;      // rows per pass
 #pragma unroll
-    for (int i = 0; i < PER; i++) {
-      int r = (tid >> 4) + i * (TC_PRODUCERS / 16);
+    for (int i = 0; i < (ROWS + RPP - 1) / RPP; i++) {
+      int r = (tid >> 4) + i * RPP;
+      if (ROWS % RPP != 0 && r >= ROWS) break;
       const bf16* p = col_ok ? src.chunk(rows_sm[r], ci) : nullptr;
       uint32_t off = half + (uint32_t)r * 128 + (uint32_t)(((c & 7) ^ (r & 7)) << 4);
       cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
       if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
     }
   }
-  // ---- K-major
+  // ---- K-major: swizzled, lanes along the 8 chunks of a row
   static __device__ __forceinline__ void fill_rows(const SRC& src, typename SRC::Row* rows_sm, int row0, int row_lim, int tid) {
     for (int r = tid; r < ROWS; r += TC_PRODUCERS) {
       typename SRC::Row rw;
@@ -612,9 +615,11 @@ struct Producer {
     Col ci = Col{0, 0};
     const bool col_ok = gcol < k_end;
     if (col_ok) ci = SRC::TABLE ? cols[(gcol - col_base) >> 3] : src.col_info(gcol);
+    constexpr int RPP = TC_PRODUCERS / 8;       // rows per pass
 #pragma unroll
-    for (int i = 0; i < PER; i++) {
-      int r = (tid >> 3) + i * (TC_PRODUCERS / 8);
+    for (int i = 0; i < (ROWS + RPP - 1) / RPP; i++) {
+      int r = (tid >> 3) + i * RPP;
+      if (ROWS % RPP != 0 && r >= ROWS) break;
       const bf16* p = col_ok ? src.chunk(rows_sm[r], ci) : nullptr;
       uint32_t off = (uint32_t)r * 128 + (uint32_t)((c ^ (r & 7)) << 4);
       cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
@@ -623,7 +628,7 @@ struct Producer {
   }
 };
 
-__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory"); }
 
 // CLASSES: the third tile coordinate selects a parity class (set_class) instead of a K split
 template <int NT, int KT, bool A_MN, bool B_MN, bool A_SPLIT, bool B_SPLIT, bool CLASSES, class ASRC, class BSRC, class EPI>
@@ -649,7 +654,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
     for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  if (warp == TC_MMA_WARP) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
   if (tid < 64) epi_sh[tid] = 0.f;
   tc_fence_before();
   __syncthreads();
@@ -664,7 +669,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   const uint32_t smem_base = smem_u32(smem);
   const int mn_tiles = m_tiles * n_tiles;
 
-  if (warp < 4) {
+  if (warp < TC_MMA_WARP) {
     // ================= producers =================
     Producer<Cfg::A_ROWS, Cfg::A_CHUNKS, A_MN, A_SPLIT, ASRC> pa;
     Producer<Cfg::B_ROWS, Cfg::B_CHUNKS, B_MN, B_SPLIT, BSRC> pb;
@@ -708,7 +713,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == TC_MMA_WARP) {
     // ================= MMA issuer =================
     constexpr uint32_t IDESC = make_idesc(NT, A_MN, B_MN);
     constexpr uint32_t A_LBO = A_MN ? 128 : Cfg::A_ROWS * 16, A_SBO = A_MN ? Cfg::A_ROWS * 16 : 128;
@@ -752,7 +757,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       if (n_kt == 0 && lane == 0) mbar_arrive(tfull0 + 8 * buf);
     }
   } else {
-    // ================= epilogue (warps 5..8 own TMEM lane quarters 1,2,3,0) =================
+    // ================= epilogue (the 4 warps after the MMA warp; warp & 3 = TMEM lane quarter) =================
     const int quarter = warp & 3;
     typename EPI::State est;
     epi.init(est);
@@ -765,7 +770,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       const int buf = it & 1;
       if (CLASSES) epi.set_class(z);
       mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
-      if (warp == 5) TC_TRACE(30);     // accumulator ready
+      if (warp == TC_MMA_WARP + 1) TC_TRACE(30);     // accumulator ready
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT;
@@ -777,13 +782,13 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * buf);
-      if (warp == 5) TC_TRACE(31);     // tile stored
+      if (warp == TC_MMA_WARP + 1) TC_TRACE(31);     // tile stored
     }
     epi.finish(est, epi_sh, NT);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     TC_TRACE(3);
