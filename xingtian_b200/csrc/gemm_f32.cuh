@@ -24,7 +24,15 @@ __device__ __forceinline__ void f32_store_plane(__nv_bfloat16* hi, long long lo_
   hi[lo_off + e] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
+// exact floor(m/d) for 0 <= m < 2^24, 1 <= d < 2^16:  (m * (floor(2^40/d)+1)) >> 40   (the error term m*e/(d*2^40),
+// e <= d, stays below 1/d while m*d < 2^40)
+__host__ __device__ inline unsigned long long fastdiv_magic(int d) { return ((1ULL << 40) / (unsigned long long)d) + 1ULL; }
+__device__ __forceinline__ int fastdiv(int m, unsigned long long magic) {
+  return (int)(((unsigned long long)(unsigned)m * magic) >> 40);
+}
+
 struct ConvGeom {
+  unsigned long long mP, mOW, mHW, mW;   // fastdiv magics of P, OW, H*W, W
   int H, W, C;        // input
   int OH, OW, Cout;   // output
   int KH, KW, S;      // kernel, stride

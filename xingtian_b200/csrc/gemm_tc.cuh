@@ -243,7 +243,7 @@ struct SrcIm2col {
   __device__ __forceinline__ void init_row(int m, Row& r) const {
     r.valid = m < n_rows;
     if (!r.valid) { r.base = 0; r.iy0 = r.ix0 = 0; return; }
-    int b = m / g.P; int p = m - b * g.P; int oy = p / g.OW; int ox = p - oy * g.OW;
+    int b = fastdiv(m, g.mP); int p = m - b * g.P; int oy = fastdiv(p, g.mOW); int ox = p - oy * g.OW;
     r.iy0 = oy * g.S - g.padT; r.ix0 = ox * g.S - g.padL;
     r.base = (((long long)b * g.H + r.iy0) * g.W + r.ix0) * g.C;
   }
@@ -273,7 +273,7 @@ struct SrcDgrad {
   __device__ __forceinline__ void init_row(int m, Row& r) const {
     r.valid = m < n_rows;
     if (!r.valid) { r.base = 0; r.iy0 = r.ix0 = 0; return; }
-    int HW = g.H * g.W; int b = m / HW; int p = m - b * HW; int iy = p / g.W; int ix = p - iy * g.W;
+    int HW = g.H * g.W; int b = fastdiv(m, g.mHW); int p = m - b * HW; int iy = fastdiv(p, g.mW); int ix = p - iy * g.W;
     r.base = (long long)b * g.P * g.Cout; r.iy0 = iy + g.padT; r.ix0 = ix + g.padL;
   }
   __device__ __forceinline__ Col col_info(int col) const {
@@ -313,6 +313,7 @@ struct SrcWDgrad {
 // Rows of class z are enumerated (b, jy, jx): uy = uy0 + S*jy, ux = ux0 + S*jx;  cols = (ty, tx, co) with
 // ky = py + S*ty, kx = px + S*tx.  KH % S == 0, KW % S == 0.
 struct DgradClass {
+  unsigned long long mPer, mNX;                 // fastdiv magics of nY*nX, nX
   int S, sshift, padT, padL, H, W, nY, nX;      // nY = ceil(H/S), nX = ceil(W/S)
   int py, px, uy0, ux0;
   __device__ __forceinline__ void set(int z) {
@@ -323,7 +324,7 @@ struct DgradClass {
   // class row m -> (b, iy, ix); returns false when the position falls outside the image (ragged classes)
   __device__ __forceinline__ bool decode(int m, int& b, int& iy, int& ix, int& qy, int& qx) const {
     int per = nY * nX;
-    b = m / per; int p = m - b * per; int jy = p / nX, jx = p - jy * nX;
+    b = fastdiv(m, mPer); int p = m - b * per; int jy = fastdiv(p, mNX), jx = p - jy * nX;
     int uy = uy0 + S * jy, ux = ux0 + S * jx;
     iy = uy - padT; ix = ux - padL;
     qy = (uy - py) >> sshift; qx = (ux - px) >> sshift;

@@ -141,6 +141,15 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
       }
       if (g.OH <= 0 || g.OW <= 0) { delete net; return fail(XTB_ERR_ARG, "layer %d: empty conv output", i); }
       g.K = d.k * d.k * g.C; g.P = g.OH * g.OW;
+      g.mP = fastdiv_magic(g.P); g.mOW = fastdiv_magic(g.OW); g.mHW = fastdiv_magic(g.H * g.W); g.mW = fastdiv_magic(g.W);
+      {
+        // exact range of the fast division used by the tensor-core gathers: numerator < 2^24, divisor < 2^16
+        long long rows = (long long)max_batch * std::max(g.P, d.src != 0 ? g.H * g.W : 0);
+        if (rows >= (1LL << 24) || g.P >= (1 << 16) || g.H * g.W >= (1 << 16)) {
+          delete net;
+          return fail(XTB_ERR_ARG, "layer %d: max_batch*positions (%lld) exceeds 2^24 -- lower max_batch", i, rows);
+        }
+      }
       lp.K = g.K; lp.N = d.cout; lp.Kd = d.k * d.k * d.cout;
       lp.sshift = d.stride == 1 ? 0 : (d.stride == 2 ? 1 : 2);
       for (int sft = 0; sft < 12; sft++) { if ((1 << sft) == g.C) lp.cshift = sft; if ((1 << sft) == d.cout) lp.oshift = sft; }
@@ -417,7 +426,8 @@ static cudaError_t tc_conv_dgrad(const LayerPlan& lp, Planes dy, Planes w, float
   const ConvGeom& g = lp.g;
   if (g.S > 1 && g.KH % g.S == 0 && g.KW % g.S == 0) {
     // strided transposed conv: one dense GEMM per parity class of the input position
-    tc::DgradClass k{g.S, lp.sshift, g.padT, g.padL, g.H, g.W, (g.H + g.S - 1) / g.S, (g.W + g.S - 1) / g.S, 0, 0, 0, 0};
+    int nY = (g.H + g.S - 1) / g.S, nX = (g.W + g.S - 1) / g.S;
+    tc::DgradClass k{fastdiv_magic(nY * nX), fastdiv_magic(nX), g.S, lp.sshift, g.padT, g.padL, g.H, g.W, nY, nX, 0, 0, 0, 0};
     int M = B * k.nY * k.nX;
     int Kc = lp.Kd / (g.S * g.S);
     tc::SrcDgradS a{dy.hi, dy.lo_off, g, lp.oshift, M, k, g.KW / g.S};
