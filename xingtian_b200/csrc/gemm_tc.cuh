@@ -51,22 +51,24 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~hint ns pass)
+// instead of burning issue slots -- the 5 consumer warps of a CTA would otherwise out-issue the producers
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(20000u)
       : "memory");
   return ok;
 }
-// bounded spin: a protocol bug traps (kernel error) instead of hanging the GPU
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 20)) __trap();
   }
 }
 // 16-byte async copy global -> shared, zero-filled when src_bytes == 0
@@ -699,14 +701,17 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       for (int t = 0; t < n_kt; t++) {
         const int k0 = kbeg + t * KT;
         if (A_MN) { pa.fill_rows(asrc, a_rows[t & 1], k0, kend, tid); producer_bar_sync(); }
+        if (warp == 0) TC_TRACE(11);
         if (B_MN) pb.init_rows(bsrc, k0, kend, tid);
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        if (warp == 0) TC_TRACE(12);
         uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         uint32_t sa_lo = sa + Cfg::A_BYTES;
         uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
         uint32_t sb_lo = sb + Cfg::B_BYTES;
         if (A_MN) pa.produce_mn16(asrc, a_rows[t & 1], ta, m0, sa, sa_lo, m0, m_ext, tid);
         else pa.produce_k(asrc, a_rows[it & 1], ta, kbeg, sa, sa_lo, k0, kend, tid);
+        if (warp == 0) TC_TRACE(13);
         if (B_MN) pb.produce(bsrc, tb, n0, sb, sb_lo, n0, n_ext, tid);
         else pb.produce_k(bsrc, b_rows[it & 1], tb, kbeg, sb, sb_lo, k0, kend, tid);
         cp_async_mbar_arrive_noinc(full0 + 8 * stage);
