@@ -52,4 +52,4 @@ for code, name in [(1, "prologue done"), (2, "dependency ok"), (10, "first stage
 for code, name in [(10, "last stage issued"), (20, "last stage landed"), (30, "last accumulator ready"), (31, "last tile stored"), (3, "dealloc")]:
     print("%-26s min/med/max us: %s" % (name, stat(code, False)))
 e = sorted(rows[0])
-print("CTA0 timeline (us, code):", [(round((x[0] - t0) / 1e3, 2), x[1]) for x in e][:60])
+print("CTA0 timeline (us, code):", [(round((x[0] - t0) / 1e3, 2), x[1]) for x in e if x[1] not in (1, 2)][:90])

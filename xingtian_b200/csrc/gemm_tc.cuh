@@ -709,8 +709,10 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
         uint32_t sa_lo = sa + Cfg::A_BYTES;
         uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
         uint32_t sb_lo = sb + Cfg::B_BYTES;
+#ifndef XTB_EXP_NO_A
         if (A_MN) pa.produce_mn16(asrc, a_rows[t & 1], ta, m0, sa, sa_lo, m0, m_ext, tid);
         else pa.produce_k(asrc, a_rows[it & 1], ta, kbeg, sa, sa_lo, k0, kend, tid);
+#endif
         if (warp == 0) TC_TRACE(13);
         if (B_MN) pb.produce(bsrc, tb, n0, sb, sb_lo, n0, n_ext, tid);
         else pb.produce_k(bsrc, b_rows[it & 1], tb, kbeg, sb, sb_lo, k0, kend, tid);
@@ -784,7 +786,11 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       for (int c = 0; c < NT; c += 16) {
         float v[16];
         tmem_ld16(lane_addr + c, v);
+        if (warp == TC_MMA_WARP + 1) TC_TRACE(32);
+#ifndef XTB_EXP_NO_EPI
         if (kend > kbeg) epi.store16(est, c, row, n0 + c, v);
+#endif
+        if (warp == TC_MMA_WARP + 1) TC_TRACE(33);
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * buf);

@@ -377,7 +377,7 @@ static cudaError_t tc_dense_fwd(const LayerPlan& lp, Planes x, Planes w, const f
   tc::SrcDense a{x.hi, x.lo_off, nullptr, lp.K, B};
   tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K};
   long long ctas = (long long)((B + 127) / 128) * ((lp.N + 63) / 64);
-  int ks = lp.K >= 1024 ? tc::pick_ksplit(ctas, lp.K, 64, 296) : 1;
+  int ks = lp.K >= 1024 ? tc::pick_ksplit(ctas, lp.K, 64, 148) : 1;
   if (ks > 1) {   // split-K: atomics into a zeroed buffer, then bias + activation (+ planes) in place
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * lp.N * sizeof(float), st);
     if (e != cudaSuccess) return e;
@@ -401,7 +401,7 @@ static cudaError_t tc_conv_wgrad_t(const LayerPlan& lp, Planes x, bool x_split, 
   tc::SrcDense bs{dy.hi, dy.lo_off, nullptr, lp.N, Mr};
   tc::TcEpiAtomic ep{dw, alpha, lp.N, lp.K, lp.N};
   long long ctas = (long long)((lp.K + 127) / 128);
-  int ks = tc::pick_ksplit(ctas, Mr, 64, 296);
+  int ks = tc::pick_ksplit(ctas, Mr, 64, 148);
   if (x_split) {
     if (lp.N <= 16) return tc::launch_tc<16, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
     if (lp.N <= 32) return tc::launch_tc<32, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
@@ -417,7 +417,7 @@ static cudaError_t tc_dense_wgrad(const LayerPlan& lp, Planes x, Planes dy, floa
   tc::SrcDense bs{dy.hi, dy.lo_off, nullptr, lp.N, B};
   tc::TcEpiAtomic ep{dw, 1.f, lp.N, lp.K, lp.N};
   long long ctas = (long long)((lp.K + 127) / 128) * ((lp.N + 63) / 64);
-  int ks = tc::pick_ksplit(ctas, B, 64, 296);
+  int ks = tc::pick_ksplit(ctas, B, 64, 148);
   return tc::launch_tc<64, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st);
 }
 
