@@ -208,6 +208,14 @@ int xtb_ppo_rollout_infer(xtb_net* net, const void* obs, const int32_t* step_idx
                           int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
                           int32_t* action, float* logp, float* value, int use_graph, void* stream);
 
+/* PPO.predict (xt/model/ppo/ppo.py:104-109) on host buffers in one call: staged H2D of `obs_host` (pageable,
+ * obs_bytes) into `obs_dev`, xtb_ppo_rollout_infer with n_step = 1 writing the packed block
+ * out_dev = [action int32 | logp f32 | value f32] x n_env, one D2H into `out_host` (pinned) and a stream
+ * synchronise: when it returns, out_host holds the step's results. */
+int xtb_ppo_predict_host(xtb_net* net, const void* obs_host, size_t obs_bytes, void* obs_dev, int n_env,
+                         int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
+                         float* out_dev, float* out_host, int use_graph, void* stream);
+
 /* Data-parallel hook: called between backward and the optimiser with the flat
  * gradient bucket; must SUM it over ranks on `stream` (e.g. ncclAllReduce).  Called once with
  * grads == NULL before the loop: must return the world size.  While a hook is installed the
@@ -237,6 +245,11 @@ int xtb_tc_gemm_test(int mode, const float* a, const float* b, float* c, int M, 
 void* xtb_pinned_alloc(size_t bytes);
 void xtb_pinned_free(void* p);
 int xtb_copy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+/* Pageable host memory -> device: worker threads memcpy 256 KiB chunks into a pinned ring while the caller
+ * enqueues one async copy per staged chunk on `stream`.  On return `src_host` has been consumed (it may be
+ * reused); the device side is ordered on `stream`.  Replaces the single-threaded feed_dict staging of
+ * sess.run (xt/model/ppo/ppo.py:104-132).  XTB_STAGE_THREADS (default 4) sizes the pool. */
+int xtb_copy_h2d_staged(void* dst_dev, const void* src_host, size_t bytes, void* stream);
 int xtb_copy_d2h(void* dst_host, const void* src_dev, size_t bytes, void* stream);
 int xtb_stream_sync(void* stream);
 

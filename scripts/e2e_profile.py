@@ -26,3 +26,31 @@ for rep in range(3):
     alg.train()
     t3 = time.perf_counter()
     print("predict x128 %.1f ms | prepare_data x32 %.1f ms | train %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
+
+# ---- split of one predict() call: staged H2D alone, device inference alone ------------------------------
+from xingtian_b200.engine import _ptr, stream_ptr
+from xingtian_b200.capi import check
+m = alg.actor
+io = m._predict_io(E)
+lib = m.net.lib
+for rep in range(2):
+    t0 = time.perf_counter()
+    for t in range(T):
+        check(lib.xtb_copy_h2d_staged(io["obs_ptr"], host_obs[t].ctypes.data, host_obs[t].nbytes, stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+    t1 = time.perf_counter()
+    for t in range(T):
+        m.rollout_infer_device(io["obs"], None, E, 1, io["act"], io["logp"], io["val"])
+        io["pin_out"].copy_(io["out_dev"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t2 = time.perf_counter()
+    pin = torch.empty(host_obs[0].shape, dtype=torch.uint8).pin_memory()
+    for t in range(T):
+        io["obs"].copy_(pin, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t3 = time.perf_counter()
+    for t in range(T):
+        np.copyto(pin.numpy(), host_obs[t])
+    t4 = time.perf_counter()
+    print("per call: staged h2d+sync %.1f us | infer+d2h+sync %.1f us | pinned h2d+sync %.1f us | np.copyto %.1f us" %
+          ((t1 - t0) / T * 1e6, (t2 - t1) / T * 1e6, (t3 - t2) / T * 1e6, (t4 - t3) / T * 1e6))

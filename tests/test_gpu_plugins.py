@@ -306,3 +306,31 @@ def test_fused_heads_equals_unfused():
         lib.xtb_set_fuse_heads(1)
     assert rel_err(outs[0][1], outs[1][1]) < 1e-4
     assert l2_rel(outs[0][2], outs[1][2]) < 1e-4
+
+
+def test_staged_h2d_copy_is_exact():
+    """xtb_copy_h2d_staged (threaded pinned-ring staging of pageable arrays) is a byte-exact copy for empty,
+    sub-chunk, chunk-boundary and larger-than-ring sizes, back to back on one stream and across two streams."""
+    from xingtian_b200 import capi
+    from xingtian_b200.engine import stream_ptr
+    lib = capi.lib()
+    rng = np.random.default_rng(5)
+    chunk, ring = 256 << 10, 48 * (256 << 10)
+    sizes = [0, 1, 4097, chunk - 1, chunk, chunk + 1, 3 * chunk + 17, 32 * 28224, ring - 5, ring + chunk + 3, 3 * ring + 11]
+    side = torch.cuda.Stream()
+    for rep in range(2):
+        srcs, dsts = [], []
+        for i, n in enumerate(sizes):
+            a = rng.integers(0, 256, size=n, dtype=np.uint8)
+            d = torch.zeros(max(n, 1) + 64, dtype=torch.uint8, device="cuda")
+            with torch.cuda.stream(side if (i & 1) else torch.cuda.current_stream()):
+                capi.check(lib.xtb_copy_h2d_staged(d.data_ptr() + 32, a.ctypes.data, n, stream_ptr()))
+            srcs.append(a.copy())
+            a[:] = 0                      # the source may be reused as soon as the call returns
+            dsts.append(d)
+        torch.cuda.synchronize()
+        for n, a, d in zip(sizes, srcs, dsts):
+            h = d.cpu().numpy()
+            assert not h[:32].any() and not h[32 + n:].any()
+            assert np.array_equal(h[32:32 + n], a)
+    assert lib.xtb_copy_h2d_staged(None, srcs[1].ctypes.data, 1, None) == -1

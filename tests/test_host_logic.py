@@ -132,3 +132,17 @@ def test_algorithm_base_cadence_and_policies():
     info = f.get_dist_info(5)
     assert sorted((d["broker_id"], sorted(d["explorer_id"])) for d in info) == [(0, [1, 3]), (1, [2])]
     assert f.get_dist_info(5) == []
+
+
+def test_stager_thread_pool_with_mock_dma(repo_root, tmp_path):
+    """The pinned-ring stager (csrc/stager.cuh) against a fake asynchronous CUDA runtime: 300 copies from 1 B to
+    4x the ring, with 0, 1 and 6 worker threads; every byte must arrive and the source is clobbered right after
+    each call returns."""
+    import subprocess
+    exe = tmp_path / "stager_mock"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I/usr/local/cuda/include",
+                    "-I" + os.path.join(repo_root, "xingtian_b200", "csrc"),
+                    os.path.join(repo_root, "tests", "stager_mock.cpp"), "-o", str(exe)], check=True, capture_output=True)
+    for threads in ("0", "1", "6"):
+        res = subprocess.run([str(exe)], env=dict(os.environ, XTB_STAGE_THREADS=threads), capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0 and "all ok" in res.stdout, res.stdout[-500:]

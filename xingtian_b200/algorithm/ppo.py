@@ -39,27 +39,13 @@ class PPO(Algorithm):
 
     # -- data path ---------------------------------------------------------------------------
     def _stage(self, dst, arr, np_dtype):
-        """Copy one host array into device tensor `dst`; large arrays go through a persistent pair of pinned
-        bounce buffers (async H2D overlapping the next host memcpy) instead of a pageable, synchronous copy."""
+        """Copy one host (pageable) array into device tensor `dst` through the library's staged copy: worker
+        threads memcpy chunks into a pinned ring while the DMA of earlier chunks is in flight
+        (`xtb_copy_h2d_staged`); the source may be reused as soon as the call returns."""
         a = np.ascontiguousarray(arr, dtype=np_dtype).reshape(dst.shape)
-        t = torch.from_numpy(a)
-        if a.nbytes < (1 << 20):
-            dst.copy_(t, non_blocking=True)
-            return
-        ring = getattr(self, "_pin_ring", None)
-        if ring is None or ring[0][0].numel() < a.nbytes:
-            ring = [[torch.empty(a.nbytes, dtype=torch.uint8).pin_memory(), None] for _ in range(2)]
-            self._pin_ring, self._pin_next = ring, 0
-        buf, ev = ring[self._pin_next]
-        if ev is not None:
-            ev.synchronize()               # the previous H2D out of this buffer has finished
-        view = buf[:a.nbytes].view(t.dtype).view(t.shape)
-        np.copyto(view.numpy(), a)         # plain memcpy into pinned memory (no torch thread pool)
-        dst.copy_(view, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        ring[self._pin_next][1] = ev
-        self._pin_next ^= 1
+        if not dst.is_contiguous():
+            raise ValueError("staging target must be contiguous")
+        check(self.actor.net.lib.xtb_copy_h2d_staged(_ptr(dst), a.ctypes.data, a.nbytes, stream_ptr()))
 
     def prepare_data(self, train_data, **kwargs):
         ro = self.actor.rollout
@@ -78,9 +64,13 @@ class PPO(Algorithm):
             self._stage(ro.target_v[sl], train_data["target_value"], np.float32)
         else:
             dev = ro.obs.device
-            val = torch.from_numpy(np.ascontiguousarray(train_data["value"], np.float32).reshape(-1)).to(dev)
-            rew = torch.from_numpy(np.ascontiguousarray(train_data["reward"], np.float32).reshape(-1)).to(dev)
-            don = torch.from_numpy(np.ascontiguousarray(train_data["done"], np.bool_).reshape(-1).view(np.uint8)).to(dev)
+            value = np.ascontiguousarray(train_data["value"], np.float32).reshape(-1)
+            val = torch.empty(value.size, dtype=torch.float32, device=dev)
+            rew = torch.empty(n, dtype=torch.float32, device=dev)
+            don = torch.empty(n, dtype=torch.uint8, device=dev)
+            self._stage(val, value, np.float32)        # staged (asynchronous) copies: no host sync per trajectory
+            self._stage(rew, np.asarray(train_data["reward"]).reshape(-1), np.float32)
+            self._stage(don, np.asarray(train_data["done"]).reshape(-1).astype(np.bool_, copy=False).view(np.uint8), np.uint8)
             if val.numel() != n + 1:
                 raise ValueError("raw trajectory needs value[T+1] (bootstrap appended), got %d for T=%d" % (val.numel(), n))
             self._raw_segments.append((self._count, n, val, rew, don))

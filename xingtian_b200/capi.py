@@ -74,6 +74,7 @@ _SIGS = {
     "xtb_ppo_train": (C.c_int, [_P, _P, C.POINTER(PpoRollout), C.c_int, C.c_int, C.c_int, _P,
                                 C.POINTER(PpoHyper), C.c_int, C.c_int, _P, C.c_int, _P]),
     "xtb_ppo_rollout_infer": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, _P, C.c_int, _P]),
+    "xtb_ppo_predict_host": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, C.c_int, _P]),
     "xtb_set_grad_hook": (C.c_int, [GRAD_HOOK, _P]),
     "xtb_net_bench_layer": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "xtb_set_fuse_heads": (C.c_int, [C.c_int]),
@@ -83,6 +84,7 @@ _SIGS = {
     "xtb_pinned_alloc": (_P, [C.c_size_t]),
     "xtb_pinned_free": (None, [_P]),
     "xtb_copy_h2d": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "xtb_copy_h2d_staged": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "xtb_copy_d2h": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "xtb_stream_sync": (C.c_int, [_P]),
 }

@@ -542,7 +542,7 @@ struct TcCfg {
 //    along rows (consecutive K rows are adjacent in memory for weights / dY), row state in registers per stage.
 //  K-major operand (tile rows = M/N entity, KT = 64): SWIZZLE_128B layout, lanes run along the 8 chunks of a row so
 //    that a warp instruction reads 4 rows x 128 contiguous bytes (instead of 32 scattered 16-byte pieces, which made
-//    the gather L1-tag bound) and writes 4 conflict-free 128-byte rows; row state is cached per tile in shared memory.
+//    the gather L1-tag bound) and writes 4 conflict-free 128-byte rows; row state is held in registers for the whole output tile.
 template <int ROWS, int CHUNKS, bool MN, bool SPLIT, class SRC>
 struct Producer {
   static constexpr int SLOTS = ROWS * CHUNKS;
@@ -601,7 +601,7 @@ struct Producer {
       if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
     }
   }
-  // ---- K-major: swizzled, lanes along the 8 chunks of a row
+  // ---- shared-memory row table (MN-major A of a weight gradient: the K rows change every stage)
   static __device__ __forceinline__ void fill_rows(const SRC& src, typename SRC::Row* rows_sm, int row0, int row_lim, int tid) {
     for (int r = tid; r < ROWS; r += TC_PRODUCERS) {
       typename SRC::Row rw;
@@ -610,20 +610,34 @@ struct Producer {
       rows_sm[r] = rw;
     }
   }
-  static __device__ __forceinline__ void produce_k(const SRC& src, const typename SRC::Row* rows_sm, const Col* cols, int col_base,
-                                                   uint32_t hi_smem, uint32_t lo_smem, int k0, int k_end, int tid) {
+  // ---- K-major: swizzled, lanes along the 8 chunks of a row.  A thread serves the same rows (tid/8 + i*RPPK) for
+  // every K tile of an output tile, so their state lives in registers for the whole tile: the per-stage work is
+  // one column lookup plus address arithmetic (row state in shared memory cost two dependent LDS round trips per
+  // 16-byte copy, which is what the producers stalled on).
+  static constexpr int RPPK = TC_PRODUCERS / 8;       // rows per pass
+  static constexpr int KROWS = MN ? 1 : (ROWS + RPPK - 1) / RPPK;
+  typename SRC::Row krows[KROWS];
+  __device__ __forceinline__ void load_rows_k(const SRC& src, int row0, int row_lim, int tid) {
+#pragma unroll
+    for (int i = 0; i < KROWS; i++) {
+      int r = (tid >> 3) + i * RPPK;
+      src.init_row(row0 + r, krows[i]);
+      if (row0 + r >= row_lim || r >= ROWS) krows[i].valid = 0;
+    }
+  }
+  __device__ __forceinline__ void produce_k(const SRC& src, const Col* cols, int col_base, uint32_t hi_smem, uint32_t lo_smem,
+                                            int k0, int k_end, int tid) const {
     const bf16* dummy = src.any();
     const int c = tid & 7;
     const int gcol = k0 + 8 * c;
     Col ci = Col{0, 0};
     const bool col_ok = gcol < k_end;
     if (col_ok) ci = SRC::TABLE ? cols[(gcol - col_base) >> 3] : src.col_info(gcol);
-    constexpr int RPP = TC_PRODUCERS / 8;       // rows per pass
 #pragma unroll
-    for (int i = 0; i < (ROWS + RPP - 1) / RPP; i++) {
-      int r = (tid >> 3) + i * RPP;
-      if (ROWS % RPP != 0 && r >= ROWS) break;
-      const bf16* p = col_ok ? src.chunk(rows_sm[r], ci) : nullptr;
+    for (int i = 0; i < KROWS; i++) {
+      int r = (tid >> 3) + i * RPPK;
+      if (ROWS % RPPK != 0 && r >= ROWS) break;
+      const bf16* p = col_ok ? src.chunk(krows[i], ci) : nullptr;
       uint32_t off = (uint32_t)r * 128 + (uint32_t)((c ^ (r & 7)) << 4);
       cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
       if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
@@ -646,8 +660,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   __shared__ uint32_t tmem_slot;
   __shared__ Col col_tab[2][2][TC_MAXCOLS];     // [tile parity][operand][column group]
   __shared__ float epi_sh[64];                  // epilogue reductions (bias gradients)
-  __shared__ typename ASRC::Row a_rows[2][A_MN ? KT : 128];  // K-major: per-tile row state; MN-major A: per-stage rows
-  __shared__ typename BSRC::Row b_rows[2][B_MN ? 1 : NT];
+  __shared__ typename ASRC::Row a_rows[2][A_MN ? KT : 1];   // MN-major A: per-stage row state (K-major rows live in registers)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
@@ -695,9 +708,9 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
         int base = B_MN ? n0 : kbeg, lim = B_MN ? min(n_ext, n0 + NT) : kend;
         for (int j = tid; base + 8 * j < lim && j < TC_MAXCOLS; j += TC_PRODUCERS) tb[j] = bsrc.col_info(base + 8 * j);
       }
-      if (!A_MN) pa.fill_rows(asrc, a_rows[it & 1], m0, m_ext, tid);
-      if (!B_MN) pb.fill_rows(bsrc, b_rows[it & 1], n0, n_ext, tid);
-      if (ASRC::TABLE || BSRC::TABLE || !A_MN || !B_MN) producer_bar_sync();
+      if (!A_MN) pa.load_rows_k(asrc, m0, m_ext, tid);
+      if (!B_MN) pb.load_rows_k(bsrc, n0, n_ext, tid);
+      if (ASRC::TABLE || BSRC::TABLE) producer_bar_sync();
       for (int t = 0; t < n_kt; t++) {
         const int k0 = kbeg + t * KT;
         if (A_MN) { pa.fill_rows(asrc, a_rows[t & 1], k0, kend, tid); producer_bar_sync(); }
@@ -711,11 +724,11 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
         uint32_t sb_lo = sb + Cfg::B_BYTES;
 #ifndef XTB_EXP_NO_A
         if (A_MN) pa.produce_mn16(asrc, a_rows[t & 1], ta, m0, sa, sa_lo, m0, m_ext, tid);
-        else pa.produce_k(asrc, a_rows[it & 1], ta, kbeg, sa, sa_lo, k0, kend, tid);
+        else pa.produce_k(asrc, ta, kbeg, sa, sa_lo, k0, kend, tid);
 #endif
         if (warp == 0) TC_TRACE(13);
         if (B_MN) pb.produce(bsrc, tb, n0, sb, sb_lo, n0, n_ext, tid);
-        else pb.produce_k(bsrc, b_rows[it & 1], tb, kbeg, sb, sb_lo, k0, kend, tid);
+        else pb.produce_k(bsrc, tb, kbeg, sb, sb_lo, k0, kend, tid);
         cp_async_mbar_arrive_noinc(full0 + 8 * stage);
         if (warp == 0) TC_TRACE(10);   // stage issued
         if (++stage == STAGES) { stage = 0; phase ^= 1; }

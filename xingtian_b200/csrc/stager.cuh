@@ -1,0 +1,201 @@
+// stager.cuh -- pageable host memory -> HBM through a pinned ring filled by a small thread pool.
+//
+// The reference feeds every sess.run() from pageable numpy arrays (feed_dict, xt/model/ppo/ppo.py:104-132,
+// xt/model/tf_compat usage in xt/model/model.py:47-65); TF stages them with one host thread.  Here the
+// calling thread splits the source into chunks, worker threads memcpy chunks into pinned slots in
+// parallel, and the caller issues one cudaMemcpyAsync per chunk as soon as it is staged, so the host
+// memcpy (the slow leg: ~10 GB/s per core) runs on several cores and overlaps the DMA.
+//
+// Semantics of stage_h2d(): on return the source buffer has been fully consumed (it may be reused or
+// freed) and every copy is enqueued on `stream`, i.e. the same contract as cudaMemcpy from pageable
+// memory, minus the stream synchronisation.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace xtb {
+
+class Stager {
+ public:
+  static constexpr size_t CHUNK = 256u << 10;   // bytes per pinned slot
+  static constexpr int SLOTS = 48;              // 12 MiB ring
+
+  static Stager& instance() {
+    static Stager* s = new Stager();            // leaked on purpose: workers may outlive static destructors
+    return *s;
+  }
+
+  // returns cudaSuccess or the first CUDA error
+  cudaError_t stage_h2d(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+    if (bytes == 0) return cudaSuccess;
+    std::lock_guard<std::mutex> call_lock(call_mu_);       // one staged copy at a time
+    cudaError_t err = init();
+    if (err != cudaSuccess) return err;
+    const size_t n = (bytes + CHUNK - 1) / CHUNK;
+    const char* s = static_cast<const char*>(src);
+    char* d = static_cast<char*>(dst);
+    if (n == 1 || workers_.empty()) {                        // small copy: stage on the calling thread
+      for (size_t c = 0; c < n; c++) {
+        int slot = (int)((seq_ + c) % SLOTS);
+        if ((err = wait_slot(slot)) != cudaSuccess) return err;
+        size_t off = c * CHUNK, len = bytes - off < CHUNK ? bytes - off : CHUNK;
+        memcpy(ring_ + (size_t)slot * CHUNK, s + off, len);
+        if ((err = issue(slot, d + off, len, stream)) != cudaSuccess) return err;
+      }
+      seq_ += n;
+      return cudaSuccess;
+    }
+    // publish the job, then open it by resetting `next_`
+    if (done_.size() < n) done_ = std::vector<std::atomic<int>>(n);
+    for (size_t c = 0; c < n; c++) done_[c].store(0, std::memory_order_relaxed);
+    const uint64_t g = gen_.load(std::memory_order_relaxed) + 1;
+    job_src_.store(s, std::memory_order_relaxed); job_bytes_.store(bytes, std::memory_order_relaxed);
+    job_chunks_.store(n, std::memory_order_relaxed); job_seq_.store(seq_, std::memory_order_relaxed);
+    size_t allowed = 0;
+    while (allowed < n && allowed < (size_t)SLOTS) {         // slots last used by earlier calls
+      if ((err = wait_slot((int)((seq_ + allowed) % SLOTS))) != cudaSuccess) return err;
+      allowed++;
+    }
+    allowed_.store(allowed, std::memory_order_release);
+    next_.store(g << 32, std::memory_order_release);      // claim counter = (generation << 32) | chunk index
+    gen_.store(g, std::memory_order_release);
+    if (sleepers_.load(std::memory_order_acquire) > 0) { std::lock_guard<std::mutex> lk(mu_); cv_.notify_all(); }
+
+    cudaError_t first = cudaSuccess;
+    for (size_t c = 0; c < n; c++) {
+      // the caller helps with the memcpy while it waits for chunk c
+      while (!done_[c].load(std::memory_order_acquire)) {
+        if (!work_one(g)) cpu_relax();
+        if (allowed < n && allowed < c + SLOTS) {            // hand out slots whose previous DMA (issued: chunk < c) finished
+          int slot = (int)((seq_ + allowed) % SLOTS);
+          if (cudaEventQuery(ev_[slot]) == cudaSuccess) allowed_.store(++allowed, std::memory_order_release);
+        }
+      }
+      int slot = (int)((seq_ + c) % SLOTS);
+      size_t off = c * CHUNK, len = bytes - off < CHUNK ? bytes - off : CHUNK;
+      if (first == cudaSuccess) first = issue(slot, d + off, len, stream);
+      if (allowed < n && allowed <= c + 1) {                 // nothing else staged: block on the oldest DMA
+        int s2 = (int)((seq_ + allowed) % SLOTS);
+        cudaError_t e2 = cudaEventSynchronize(ev_[s2]);
+        if (first == cudaSuccess) first = e2;
+        allowed_.store(++allowed, std::memory_order_release);
+      }
+    }
+    seq_ += n;
+    return first;
+  }
+
+  int threads() const { return (int)workers_.size(); }
+
+ private:
+  Stager() {}
+
+  static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+  }
+
+  cudaError_t init() {
+    if (ring_) return cudaSuccess;
+    cudaError_t e = cudaHostAlloc((void**)&ring_, CHUNK * SLOTS, cudaHostAllocDefault);
+    if (e != cudaSuccess) { ring_ = nullptr; return e; }
+    for (int i = 0; i < SLOTS; i++) {
+      e = cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+      used_[i] = false;
+    }
+    int nt = 4;
+    if (const char* env = getenv("XTB_STAGE_THREADS")) nt = atoi(env);
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw && nt > (int)hw - 1) nt = (int)hw - 1;
+    if (nt < 0) nt = 0;
+    for (int i = 0; i < nt; i++) workers_.emplace_back([this] { worker(); });
+    for (auto& t : workers_) t.detach();
+    return cudaSuccess;
+  }
+
+  cudaError_t wait_slot(int slot) {
+    if (!used_[slot]) return cudaSuccess;
+    return cudaEventSynchronize(ev_[slot]);
+  }
+
+  cudaError_t issue(int slot, void* dst, size_t len, cudaStream_t stream) {
+    cudaError_t e = cudaMemcpyAsync(dst, ring_ + (size_t)slot * CHUNK, len, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    used_[slot] = true;
+    return cudaEventRecord(ev_[slot], stream);
+  }
+
+  // claim and stage one chunk of the open job; false if none is claimable right now
+  // A successful CAS on (g, c) proves job g is still open (chunk c was unclaimed), so its fields are stable.
+  bool work_one(uint64_t g) {
+    uint64_t cur = next_.load(std::memory_order_acquire);
+    if ((cur >> 32) != g) return false;
+    size_t c = (size_t)(cur & 0xffffffffu);
+    if (c >= job_chunks_.load(std::memory_order_relaxed) || c >= allowed_.load(std::memory_order_acquire)) return false;
+    if (!next_.compare_exchange_strong(cur, cur + 1, std::memory_order_acq_rel)) return true;   // lost a race: retry
+    int slot = (int)((job_seq_.load(std::memory_order_relaxed) + c) % SLOTS);
+    size_t bytes = job_bytes_.load(std::memory_order_relaxed);
+    size_t off = c * CHUNK, len = bytes - off < CHUNK ? bytes - off : CHUNK;
+    memcpy(ring_ + (size_t)slot * CHUNK, job_src_.load(std::memory_order_relaxed) + off, len);
+    done_[c].store(1, std::memory_order_release);
+    return true;
+  }
+
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      // spin briefly for the next job (rollout loops call every ~100 us), then sleep
+      auto t0 = std::chrono::steady_clock::now();
+      int spins = 0;
+      while (gen_.load(std::memory_order_acquire) == seen) {
+        cpu_relax();
+        if ((++spins & 1023) == 0 &&
+            std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) {
+          std::unique_lock<std::mutex> lk(mu_);
+          sleepers_.fetch_add(1, std::memory_order_acq_rel);
+          cv_.wait_for(lk, std::chrono::milliseconds(200),
+                       [&] { return gen_.load(std::memory_order_acquire) != seen; });
+          sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+          t0 = std::chrono::steady_clock::now();
+        }
+      }
+      seen = gen_.load(std::memory_order_acquire);
+      // drain the job: chunks become claimable as the caller frees slots
+      for (;;) {
+        if (work_one(seen)) continue;
+        uint64_t cur = next_.load(std::memory_order_acquire);
+        if ((cur >> 32) != seen || (size_t)(cur & 0xffffffffu) >= job_chunks_.load(std::memory_order_relaxed)) break;
+        cpu_relax();
+      }
+    }
+  }
+
+  std::mutex call_mu_, mu_;
+  std::condition_variable cv_;
+  std::atomic<uint64_t> gen_{0};
+  std::atomic<int> sleepers_{0};
+  std::atomic<uint64_t> next_{0};
+  std::atomic<size_t> allowed_{0};
+  std::vector<std::atomic<int>> done_;
+  std::atomic<const char*> job_src_{nullptr};
+  std::atomic<size_t> job_bytes_{0}, job_chunks_{0}, job_seq_{0};
+  size_t seq_ = 0;
+  char* ring_ = nullptr;
+  cudaEvent_t ev_[SLOTS];
+  bool used_[SLOTS];
+  std::vector<std::thread> workers_;
+};
+
+}  // namespace xtb

@@ -16,6 +16,7 @@
 #include "gemm_f32.cuh"
 #include "optim.cuh"
 #include "rl_kernels.cuh"
+#include "stager.cuh"
 #include "tc_dispatch.cuh"
 #include <cstdlib>
 #include <type_traits>
@@ -1244,6 +1245,25 @@ extern "C" void* xtb_pinned_alloc(size_t bytes) {
 extern "C" void xtb_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" int xtb_copy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
   CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, S(stream)));
+  return XTB_OK;
+}
+extern "C" int xtb_copy_h2d_staged(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes && (!dst || !src)) return fail(XTB_ERR_ARG, "xtb_copy_h2d_staged: null pointer");
+  CUDA_TRY(xtb::Stager::instance().stage_h2d(dst, src, bytes, S(stream)));
+  return XTB_OK;
+}
+// PPO.predict with host buffers in one call (xt/model/ppo/ppo.py:104-109): staged H2D of the observations, the
+// (graphed) forward + sampling, one packed D2H of [action | logp | value] and a stream synchronise.
+extern "C" int xtb_ppo_predict_host(xtb_net* net, const void* obs_host, size_t obs_bytes, void* obs_dev, int n_env,
+                                    int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
+                                    float* out_dev, float* out_host, int use_graph, void* stream) {
+  if (!obs_host || !obs_dev || !out_dev || !out_host) return fail(XTB_ERR_ARG, "xtb_ppo_predict_host: null pointer");
+  CUDA_TRY(xtb::Stager::instance().stage_h2d(obs_dev, obs_host, obs_bytes, S(stream)));
+  int rc = xtb_ppo_rollout_infer(net, obs_dev, nullptr, n_env, 1, pi_tensor, v_tensor, seed, offset_dev,
+                                 reinterpret_cast<int32_t*>(out_dev), out_dev + n_env, out_dev + 2 * (size_t)n_env, use_graph, stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_host, out_dev, sizeof(float) * 3 * (size_t)n_env, cudaMemcpyDeviceToHost, S(stream)));
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));
   return XTB_OK;
 }
 extern "C" int xtb_copy_d2h(void* dst, const void* src, size_t bytes, void* stream) {

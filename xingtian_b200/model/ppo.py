@@ -180,11 +180,11 @@ class PPO(XTModel):
             dev = self.device
             shape = (batch,) + tuple(self.state_dim)
             out_dev = torch.empty(3, batch, dtype=torch.float32, device=dev)
-            io = dict(pin_in=torch.empty(shape, dtype=self._obs_dt).pin_memory(),
-                      obs=torch.empty(shape, dtype=self._obs_dt, device=dev), out_dev=out_dev,
+            io = dict(obs=torch.empty(shape, dtype=self._obs_dt, device=dev), out_dev=out_dev,
                       act=out_dev[0].view(torch.int32), logp=out_dev[1], val=out_dev[2],
                       pin_out=torch.empty(3, batch, dtype=torch.float32).pin_memory())
-            io["pin_in_np"] = io["pin_in"].numpy()     # plain memcpy into pinned memory (no torch thread pool)
+            io["obs_ptr"], io["out_dev_ptr"], io["pin_out_ptr"] = _ptr(io["obs"]), _ptr(out_dev), _ptr(io["pin_out"])
+            io["pin_out_np"] = io["pin_out"].numpy()
             self._pred_bufs[("io", batch)] = io
         return io
 
@@ -201,12 +201,14 @@ class PPO(XTModel):
             action, logp, v = self.predict_device(bufs["obs"], batch, u)
             return (action.cpu().numpy(), logp.cpu().numpy().reshape(batch, 1), v.cpu().numpy().reshape(batch, 1))
         io = self._predict_io(batch)
-        np.copyto(io["pin_in_np"], state)
-        io["obs"].copy_(io["pin_in"], non_blocking=True)
-        self.rollout_infer_device(io["obs"], None, batch, 1, io["act"], io["logp"], io["val"])
-        io["pin_out"].copy_(io["out_dev"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        out = io["pin_out"].numpy()
+        if getattr(self, "_offset_dev", None) is None:
+            self._offset_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.net.ensure_batch(batch)
+        # staged H2D -> graphed forward + sampling -> packed D2H -> stream sync, in one native call
+        check(self.net.lib.xtb_ppo_predict_host(self.net.handle, state.ctypes.data, state.nbytes, io["obs_ptr"], batch,
+                                                self.pi_t, self.v_t, C.c_uint64(self._sample_seed), _ptr(self._offset_dev),
+                                                io["out_dev_ptr"], io["pin_out_ptr"], 1 if self.use_graph else 0, stream_ptr()))
+        out = io["pin_out_np"]
         return (out[0].view(np.int32).copy(), out[1].reshape(batch, 1).copy(), out[2].reshape(batch, 1).copy())
 
     # -- training ----------------------------------------------------------------------------
