@@ -218,15 +218,24 @@ typedef __nv_bfloat16 bf16;
 struct Col { int a, b; };
 
 // plain rows: X[row(m)*ld + col], optional row gather.  ld % 8 == 0.
+// Row k' = ((ty*k4 + tx)*16 + dy*4 + dx)*4 + c of the weight matrix of the (k4 x k4, stride 1, 64 channel) conv over a
+// space-to-depth plane is row ((4ty+dy)*4k4 + 4tx+dx)*4 + c of the real (4k4 x 4k4, stride 4, 4 channel) conv.
+__device__ __forceinline__ int s2d_row(int m, int k4) {
+  int tap = m >> 6, ty = tap / k4, tx = tap - ty * k4;
+  int dy = (m >> 4) & 3, dx = (m >> 2) & 3, c = m & 3;
+  return (((4 * ty + dy) * 4 * k4 + 4 * tx + dx) << 2) + c;
+}
 struct SrcDense {
   static constexpr bool TABLE = false;
   __device__ __forceinline__ void set_class(int) {}
   const bf16* x; long long lo_off; const int32_t* idx; int ld; int n_rows;
+  int s2d_k4;     // > 0: row m is a space-to-depth weight row (see s2d_row), read the real row instead
   struct Row { long long base; int valid; };
   __device__ __forceinline__ const bf16* any() const { return x; }
   __device__ __forceinline__ void init_row(int m, Row& r) const {
     r.valid = m < n_rows;
-    r.base = r.valid ? (long long)(idx ? idx[m] : m) * ld : 0;
+    int src = s2d_k4 ? s2d_row(m, s2d_k4) : m;
+    r.base = r.valid ? (long long)(idx ? idx[src] : src) * ld : 0;
   }
   __device__ __forceinline__ Col col_info(int col) const { return Col{col, 0}; }
   __device__ __forceinline__ const bf16* chunk(const Row& r, const Col& c) const { return r.valid ? x + r.base + c.a : nullptr; }
@@ -482,12 +491,13 @@ struct TcEpiStore {     // plain row-major store (self-test)
 struct TcEpiAtomic {
   typedef EpiNoState State;
   float* out; float alpha; int ld; int M, N;
+  int s2d_k4;                  // > 0: GEMM row m accumulates into output row s2d_row(m) (space-to-depth weight order)
   __device__ __forceinline__ void set_class(int) {}
   __device__ __forceinline__ void init(State&) const {}
   __device__ __forceinline__ void finish(State&, float*, int) const {}
   __device__ __forceinline__ void store16(State&, int, int m, int n0, const float v[16]) const {
     if (m >= M) return;
-    float* o = out + (long long)m * ld + n0;
+    float* o = out + (long long)(s2d_k4 ? s2d_row(m, s2d_k4) : m) * ld + n0;
 #pragma unroll
     for (int j = 0; j < 16; j++)
       if (n0 + j < N) atomicAdd(o + j, alpha * v[j]);
@@ -506,10 +516,10 @@ struct TcEpiAtomic {
 // ------------------------------------------------------------------------------------------
 
 // Optional timeline trace (XTB_TC_TRACE builds only): %globaltimer stamps per CTA / role / tile event.
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #ifdef XTB_TC_TRACE
 __device__ unsigned long long* g_tc_trace = nullptr;     // [cta][slot] ; slot 0 = count
 constexpr int TC_TRACE_SLOTS = 256;
-__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void trace(int code) {
   if (!g_tc_trace) return;
   unsigned long long* b = g_tc_trace + (size_t)blockIdx.x * TC_TRACE_SLOTS;
@@ -519,6 +529,20 @@ __device__ __forceinline__ void trace(int code) {
 #define TC_TRACE(code) do { if ((threadIdx.x & 31) == 0) trace(code); } while (0)
 #else
 #define TC_TRACE(code) do {} while (0)
+#endif
+// Optional per-role cycle accounting (XTB_TC_PROF builds only): clock64 deltas accumulated in registers by the lead
+// warp of each role and written once at kernel exit ([cta][role*8 + slot]); no memory traffic inside the loops.
+#ifdef XTB_TC_PROF
+__device__ long long* g_tc_prof = nullptr;
+#define PROF_DECL long long pf_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pf_last = clock64();
+#define PROF(i) do { long long n_ = clock64(); pf_acc[i] += n_ - pf_last; pf_last = n_; } while (0)
+#define PROF_STAMP(slot) do { if (g_tc_prof && threadIdx.x == 0) g_tc_prof[(size_t)blockIdx.x * 32 + (slot)] = (long long)gtimer(); } while (0)
+#define PROF_FLUSH(role) do { if (g_tc_prof && (threadIdx.x & 31) == 0) { for (int q_ = 0; q_ < 8; q_++) g_tc_prof[(size_t)blockIdx.x * 32 + (role) * 8 + q_] = pf_acc[q_]; } } while (0)
+#else
+#define PROF_DECL
+#define PROF(i) do {} while (0)
+#define PROF_FLUSH(role) do {} while (0)
+#define PROF_STAMP(slot) do {} while (0)
 #endif
 constexpr int TC_MAXCOLS = 128;   // cached column groups per operand (K-major conv operands: K/8 <= 128)
 
@@ -533,7 +557,11 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES * (A_SPLIT ? 2 : 1) + B_BYTES * (B_SPLIT ? 2 : 1);
   static constexpr int STAGES = (STAGE_BYTES * 4 <= 108 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 108 * 1024) ? 3 : 2);
   static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + 1024;
-  static constexpr int TMEM_COLS = NT <= 16 ? 32 : (NT <= 32 ? 64 : (NT <= 64 ? 128 : (NT <= 128 ? 256 : 512)));  // two buffers
+  // B_SPLIT: one MMA of N = 2*NT multiplies A by [B_hi | B_lo] (the planes are adjacent N chunks in shared memory), so an
+  // accumulator buffer is 2*NT columns and the epilogue adds the halves; A tiles are read once instead of twice
+  static constexpr int ACC_COLS = B_SPLIT ? 2 * NT : NT;
+  static_assert(ACC_COLS <= 256, "accumulator tile too wide");
+  static constexpr int TMEM_COLS = ACC_COLS <= 16 ? 32 : (ACC_COLS <= 32 ? 64 : (ACC_COLS <= 64 ? 128 : (ACC_COLS <= 128 ? 256 : 512)));  // two buffers
   static constexpr int CTAS_PER_SM = (2 * SMEM_BYTES + 8192 <= 227 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
 
@@ -548,33 +576,36 @@ struct Producer {
   static constexpr int SLOTS = ROWS * CHUNKS;
   static_assert(MN || CHUNKS == 8, "K-major tiles are 64 elements (one 128-byte swizzle atom) wide");
   static constexpr int PER = (SLOTS + TC_PRODUCERS - 1) / TC_PRODUCERS;
-  static constexpr int NROW = (ROWS >= TC_PRODUCERS) ? ROWS / TC_PRODUCERS : 1;   // distinct rows per thread (MN-major)
+  static constexpr int NROW = MN ? PER : 1;          // distinct K rows per thread per stage (MN-major, no swizzle)
+  static constexpr int RPPM = TC_PRODUCERS / CHUNKS;   // rows per pass
+  static_assert(!MN || CHUNKS == 16 || TC_PRODUCERS % CHUNKS == 0, "a thread keeps one chunk column");
   typename SRC::Row rows[NROW];
 
-  // ---- MN-major, no swizzle (weights / dY rows: consecutive K rows are adjacent in memory)
+  // ---- MN-major, no swizzle (weights / dY rows).  Lanes run along the chunks of a K row first, so a warp reads
+  // whole 128-byte lines (every CTA of the grid reads the same weight tile at the same time: with lanes along the
+  // rows each instruction asked L2 for 32 separate sectors of 16 useful bytes and the shared lines became an L2
+  // hot spot that paced the whole pipeline).
   __device__ __forceinline__ void init_rows(const SRC& src, int row0, int row_lim, int tid) {
 #pragma unroll
     for (int q = 0; q < NROW; q++) {
-      int r = (tid + q * TC_PRODUCERS) % ROWS;
+      int r = tid / CHUNKS + q * RPPM;
       src.init_row(row0 + r, rows[q]);
-      if (row0 + r >= row_lim) rows[q].valid = 0;
+      if (row0 + r >= row_lim || r >= ROWS) rows[q].valid = 0;
     }
   }
   __device__ __forceinline__ void produce(const SRC& src, const Col* cols, int col_base, uint32_t hi_smem, uint32_t lo_smem,
                                           int col0, int col_lim, int tid) {
     const bf16* dummy = src.any();
+    const int c = tid % CHUNKS;
+    const int gcol = col0 + 8 * c;
+    const bool col_ok = gcol < col_lim;
+    Col ci = Col{0, 0};
+    if (col_ok) ci = SRC::TABLE ? cols[(gcol - col_base) >> 3] : src.col_info(gcol);
 #pragma unroll
-    for (int i = 0; i < PER; i++) {
-      int s = tid + i * TC_PRODUCERS;
-      if (SLOTS % TC_PRODUCERS != 0 && s >= SLOTS) break;
-      int r = s % ROWS, c = s / ROWS;
-      int gcol = col0 + 8 * c;
-      const typename SRC::Row& row = rows[(ROWS >= TC_PRODUCERS) ? (i % NROW) : 0];
-      const bf16* p = nullptr;
-      if (gcol < col_lim) {
-        Col ci = SRC::TABLE ? cols[(gcol - col_base) >> 3] : src.col_info(gcol);
-        p = src.chunk(row, ci);
-      }
+    for (int i = 0; i < NROW; i++) {
+      int r = tid / CHUNKS + i * RPPM;
+      if (ROWS % RPPM != 0 && r >= ROWS) break;
+      const bf16* p = col_ok ? src.chunk(rows[i], ci) : nullptr;
       uint32_t off = (uint32_t)c * ROWS * 16 + (uint32_t)r * 16;
       cp_async16(hi_smem + off, p ? p : dummy, p ? 16u : 0u);
       if (SPLIT) cp_async16(lo_smem + off, p ? p + src.lo_off : dummy, p ? 16u : 0u);
@@ -663,6 +694,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   __shared__ typename ASRC::Row a_rows[2][A_MN ? KT : 1];   // MN-major A: per-stage row state (K-major rows live in registers)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  PROF_STAMP(24);     // CTA entry
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
   const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
   if (tid == 0) {
@@ -678,8 +710,10 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
   // prologue done (barriers, TMEM, no global memory touched): wait for the producer grid, then let the next
   // kernel start its own prologue underneath this one
   TC_TRACE(1);      // prologue done
+  PROF_STAMP(25);
   pdl_wait();
   pdl_trigger();
+  PROF_STAMP(26);
   TC_TRACE(2);      // dependency satisfied
   const uint32_t tmem_base = tmem_slot;
   const uint32_t smem_base = smem_u32(smem);
@@ -690,6 +724,7 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
     Producer<Cfg::A_ROWS, Cfg::A_CHUNKS, A_MN, A_SPLIT, ASRC> pa;
     Producer<Cfg::B_ROWS, Cfg::B_CHUNKS, B_MN, B_SPLIT, BSRC> pb;
     int stage = 0; uint32_t phase = 0; int it = 0;
+    PROF_DECL
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int z = tile / mn_tiles, rem = tile - z * mn_tiles;
       const int nt_i = rem / m_tiles, mt_i = rem - nt_i * m_tiles;
@@ -711,12 +746,15 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       if (!A_MN) pa.load_rows_k(asrc, m0, m_ext, tid);
       if (!B_MN) pb.load_rows_k(bsrc, n0, n_ext, tid);
       if (ASRC::TABLE || BSRC::TABLE) producer_bar_sync();
+      PROF(0);
       for (int t = 0; t < n_kt; t++) {
         const int k0 = kbeg + t * KT;
         if (A_MN) { pa.fill_rows(asrc, a_rows[t & 1], k0, kend, tid); producer_bar_sync(); }
         if (warp == 0) TC_TRACE(11);
         if (B_MN) pb.init_rows(bsrc, k0, kend, tid);
+        PROF(4);
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        PROF(1);
         if (warp == 0) TC_TRACE(12);
         uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
         uint32_t sa_lo = sa + Cfg::A_BYTES;
@@ -727,62 +765,80 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
         else pa.produce_k(asrc, ta, kbeg, sa, sa_lo, k0, kend, tid);
 #endif
         if (warp == 0) TC_TRACE(13);
+        PROF(2);
+#ifndef XTB_EXP_NO_B
         if (B_MN) pb.produce(bsrc, tb, n0, sb, sb_lo, n0, n_ext, tid);
         else pb.produce_k(bsrc, tb, kbeg, sb, sb_lo, k0, kend, tid);
+#endif
+        PROF(3);
         cp_async_mbar_arrive_noinc(full0 + 8 * stage);
+        PROF(5);
         if (warp == 0) TC_TRACE(10);   // stage issued
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    if (warp == 0) PROF_FLUSH(0);
   } else if (warp == TC_MMA_WARP) {
     // ================= MMA issuer =================
     constexpr uint32_t IDESC = make_idesc(NT, A_MN, B_MN);
+    constexpr uint32_t IDESC_HL = make_idesc(Cfg::ACC_COLS, A_MN, B_MN);    // N covers [B_hi | B_lo]
     constexpr uint32_t A_LBO = A_MN ? 128 : Cfg::A_ROWS * 16, A_SBO = A_MN ? Cfg::A_ROWS * 16 : 128;
     constexpr uint32_t B_LBO = B_MN ? 128 : Cfg::B_ROWS * 16, B_SBO = B_MN ? Cfg::B_ROWS * 16 : 128;
     constexpr uint32_t A_KSTEP = A_MN ? 256 : 2 * Cfg::A_ROWS * 16;   // advance of one K=16 step
     constexpr uint32_t B_KSTEP = B_MN ? 256 : 2 * Cfg::B_ROWS * 16;
     int stage = 0; uint32_t phase = 0; int it = 0;
+    PROF_DECL
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int z = tile / mn_tiles;
       const int kbeg = CLASSES ? 0 : z * k_chunk, kend = CLASSES ? k_ext : min(k_ext, kbeg + k_chunk);
       const int n_kt = (kend - kbeg + KT - 1) / KT;
       const int buf = it & 1;
-      const uint32_t acc = tmem_base + buf * NT;
+      const uint32_t acc = tmem_base + buf * Cfg::ACC_COLS;
+      PROF(3);
       mbar_wait(tempty0 + 8 * buf, ((it >> 1) & 1) ^ 1);      // the epilogue drained this accumulator
       tc_fence_after();
+      PROF(0);
       for (int t = 0; t < n_kt; t++) {
         mbar_wait(full0 + 8 * stage, phase);
+        PROF(1);
         TC_TRACE(20);                  // stage data landed
         if (lane == 0) {
+#ifndef XTB_EXP_NO_PFENCE
           fence_proxy_async();      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+#endif
           tc_fence_after();
           uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           uint32_t sa_lo = sa + Cfg::A_BYTES;
           uint32_t sb = sa + Cfg::A_BYTES * (A_SPLIT ? 2 : 1);
           uint32_t sb_lo = sb + Cfg::B_BYTES;
+#ifndef XTB_EXP_NO_MMA
 #pragma unroll
           for (int j = 0; j < KT / 16; j++) {
             // MN-major: no-swizzle canonical tile, 16 K rows per step; K-major: 128B-swizzled tile, 32 B per step
             uint64_t ah = A_MN ? make_desc_mn_sw128(sa + j * 2048) : make_desc_sw128(sa + j * 32);
             uint64_t bh = B_MN ? make_desc(sb + j * B_KSTEP, B_LBO, B_SBO) : make_desc_sw128(sb + j * 32);
-            umma_bf16(acc, ah, bh, IDESC, (t > 0 || j > 0) ? 1u : 0u);
-            if (B_SPLIT) umma_bf16(acc, ah, B_MN ? make_desc(sb_lo + j * B_KSTEP, B_LBO, B_SBO) : make_desc_sw128(sb_lo + j * 32), IDESC, 1u);
+            // columns [0,NT) += A_hi*B_hi, columns [NT,2NT) += A_hi*B_lo in one instruction (the lo tile continues the hi tile)
+            umma_bf16(acc, ah, bh, IDESC_HL, (t > 0 || j > 0) ? 1u : 0u);
             if (A_SPLIT) umma_bf16(acc, A_MN ? make_desc_mn_sw128(sa_lo + j * 2048) : make_desc_sw128(sa_lo + j * 32), bh, IDESC, 1u);
           }
+#endif
           umma_commit(empty0 + 8 * stage);            // frees the smem stage when these MMAs retire
           if (t == n_kt - 1) umma_commit(tfull0 + 8 * buf);   // accumulator complete
         }
         __syncwarp();
+        PROF(2);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (n_kt == 0 && lane == 0) mbar_arrive(tfull0 + 8 * buf);
     }
+    PROF_FLUSH(1);
   } else {
     // ================= epilogue (the 4 warps after the MMA warp; warp & 3 = TMEM lane quarter) =================
     const int quarter = warp & 3;
     typename EPI::State est;
     epi.init(est);
     int it = 0;
+    PROF_DECL
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int z = tile / mn_tiles, rem = tile - z * mn_tiles;
       const int nt_i = rem / m_tiles, mt_i = rem - nt_i * m_tiles;
@@ -790,29 +846,44 @@ tc_gemm_kernel(ASRC asrc, BSRC bsrc, EPI epi, int m_ext, int n_ext, int k_ext, i
       const int kbeg = CLASSES ? 0 : z * k_chunk, kend = CLASSES ? k_ext : min(k_ext, kbeg + k_chunk);
       const int buf = it & 1;
       if (CLASSES) epi.set_class(z);
+      PROF(3);
       mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
+      PROF(0);
       if (warp == TC_MMA_WARP + 1) TC_TRACE(30);     // accumulator ready
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * Cfg::ACC_COLS;
 #pragma unroll
       for (int c = 0; c < NT; c += 16) {
         float v[16];
         tmem_ld16(lane_addr + c, v);
+        if (B_SPLIT) {
+          float w[16];
+          tmem_ld16(lane_addr + NT + c, w);
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[j] += w[j];
+        }
+        PROF(1);
         if (warp == TC_MMA_WARP + 1) TC_TRACE(32);
 #ifndef XTB_EXP_NO_EPI
         if (kend > kbeg) epi.store16(est, c, row, n0 + c, v);
 #endif
+        PROF(2);
         if (warp == TC_MMA_WARP + 1) TC_TRACE(33);
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * buf);
       if (warp == TC_MMA_WARP + 1) TC_TRACE(31);     // tile stored
     }
+    PROF(3);
     epi.finish(est, epi_sh, NT);
+    PROF(4);
+    if (warp == TC_MMA_WARP + 1) PROF_FLUSH(2);
   }
   tc_fence_before();
+  PROF_STAMP(27);     // this thread's role loop finished
   __syncthreads();
+  PROF_STAMP(28);     // all roles finished
   if (warp == TC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -861,6 +932,34 @@ __global__ void decode_u8_kernel(const uint8_t* __restrict__ obs, const int32_t*
   } else {
     for (int j = i; j < per_sample; j++) d[j] = __float2bfloat16_rn((float)s[j]);
   }
+}
+
+// Space-to-depth variant for a first conv layer with stride S = 4 over C = 4 channels (KH, KW, H, W multiples of 4):
+// dst[b, Y, X, (dy, dx, c)] = obs[idx[b], 4Y+dy, 4X+dx, c].  The 8x8/4 conv over [H, W, 4] becomes a 2x2/1 conv over
+// [H/4, W/4, 64]: every im2col row piece is then one aligned 128-byte line instead of overlapping 64-byte pieces at
+// 32-byte offsets (which cost ~17 L2 requests per 512-byte copy instruction).  One thread moves one (y, 4-pixel) unit.
+__global__ void decode_u8_s2d_kernel(const uint8_t* __restrict__ obs, const int32_t* __restrict__ idx, int H, int W,
+                                     bf16* __restrict__ dst) {
+  pdl_wait(); pdl_trigger();
+  const int b = blockIdx.y;
+  const int wb = W >> 2;                       // 16-byte units (4 pixels x 4 channels) per image row
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= H * wb) return;
+  const int y = u / wb, X = u - y * wb;
+  const long long per = (long long)H * W * 4;
+  const long long srow = idx ? idx[b] : b;
+  const uint4 v = *reinterpret_cast<const uint4*>(obs + srow * per + ((long long)y * W + 4 * X) * 4);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[8];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    o[2 * q] = pack_bf16((float)(w[q] & 0xff), (float)((w[q] >> 8) & 0xff));
+    o[2 * q + 1] = pack_bf16((float)((w[q] >> 16) & 0xff), (float)(w[q] >> 24));
+  }
+  bf16* d = dst + (long long)b * per + ((long long)((y >> 2) * wb + X) * 64 + (y & 3) * 16);
+  uint4* dp = reinterpret_cast<uint4*>(d);
+  dp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dp[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
 }  // namespace tc

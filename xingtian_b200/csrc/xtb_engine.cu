@@ -77,6 +77,10 @@ struct LayerPlan {
   int sshift = 0;
   int cshift = -1, oshift = -1;   // log2(Cin), log2(Cout) when powers of two (tensor-core gathers), else -1
   bool pad = false;
+  // space-to-depth view of a stride-4, 4-channel first layer (see tc::decode_u8_s2d_kernel): geometry of the equivalent
+  // (k/4 x k/4, stride 1) conv over [H/4, W/4, 64]; its weight rows map to the real ones through tc::s2d_row
+  bool s2d = false;
+  ConvGeom g2{};
 };
 
 struct xtb_net {
@@ -91,6 +95,7 @@ struct xtb_net {
   std::vector<long long> plane_elems;     // elements per bf16 plane of tensor t (max_batch*tsize rounded to 8)
   size_t obs_hi_off = 0, w_hi_off = 0;    // decoded-frame plane, weight planes
   long long w_plane_elems = 0;
+  bool s2d = false;                       // the observation plane is stored space-to-depth (every first-layer conv agrees)
   bool gout_planes_fresh = false;         // set while a caller guarantees head-gradient planes are current
   float* params = nullptr; float* grads = nullptr; char* ws = nullptr;
 };
@@ -183,6 +188,13 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
         delete net;
         return fail(XTB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
       }
+      if (d.src == 0 && desc->input_u8 && !d.pad_same && g.C == 4 && d.stride == 4 && d.k % 4 == 0 && g.H % 4 == 0 && g.W % 4 == 0) {
+        lp.s2d = true;
+        ConvGeom& q = lp.g2;
+        q = g;
+        q.H = g.H / 4; q.W = g.W / 4; q.C = 64; q.KH = q.KW = d.k / 4; q.S = 1;
+        q.mHW = fastdiv_magic(q.H * q.W); q.mW = fastdiv_magic(q.W);
+      }
     } else if (d.kind == XTB_DENSE) {
       lp.K = lp.in_size; lp.N = d.cout;
       shp[i + 1] = {1, 1, d.cout};
@@ -199,6 +211,12 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
     net->L.push_back(lp);
   }
   net->n_params = off;
+  {   // one observation plane serves every first layer: space-to-depth only when all tensor-core first layers use it
+    bool any = false, all = true;
+    for (const auto& lp : net->L) if (lp.d.src == 0 && lp.d.kind == XTB_CONV) { any = true; all = all && lp.s2d; }
+    net->s2d = any && all;
+    if (!net->s2d) for (auto& lp : net->L) lp.s2d = false;
+  }
   // workspace
   size_t w = 0;
   net->out_off.assign(desc->n_layers + 1, 0);
@@ -360,8 +378,10 @@ template <bool PAD>
 static cudaError_t tc_conv_fwd_t(const LayerPlan& lp, Planes x, bool x_split, Planes w, const float* b, float alpha,
                                  float* out, Planes po, int B, cudaStream_t st) {
   int M = B * lp.g.P;
-  tc::SrcIm2col<PAD> a{x.hi, x.lo_off, lp.g, lp.cshift, M};
-  tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K};
+  // first layer over a space-to-depth observation plane: k/4 x k/4 stride-1 conv over 64 channels, weight rows permuted
+  const bool s2d = lp.s2d && !x_split;
+  tc::SrcIm2col<PAD> a{x.hi, x.lo_off, s2d ? lp.g2 : lp.g, s2d ? 6 : lp.cshift, M};
+  tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K, s2d ? lp.g2.KH : 0};
   tc::TcEpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, M, lp.N, po.hi, po.lo_off};
   if (x_split) {
     if (lp.N <= 16) return tc::launch_tc<16, 64, false, true, true, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
@@ -382,7 +402,7 @@ static cudaError_t tc_dense_fwd(const LayerPlan& lp, Planes x, Planes w, const f
   if (ks > 1) {   // split-K: atomics into a zeroed buffer, then bias + activation (+ planes) in place
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * lp.N * sizeof(float), st);
     if (e != cudaSuccess) return e;
-    tc::TcEpiAtomic ep{out, 1.f, lp.N, B, lp.N};
+    tc::TcEpiAtomic ep{out, 1.f, lp.N, B, lp.N, 0};
     e = tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, ks, st);
     if (e != cudaSuccess) return e;
     long long total = (long long)B * lp.N;
@@ -398,9 +418,10 @@ template <bool PAD>
 static cudaError_t tc_conv_wgrad_t(const LayerPlan& lp, Planes x, bool x_split, Planes dy, float alpha, float* dw, int B,
                                    cudaStream_t st) {
   int Mr = B * lp.g.P;
-  tc::SrcIm2col<PAD> a{x.hi, x.lo_off, lp.g, lp.cshift, Mr};
+  const bool s2d = lp.s2d && !x_split;
+  tc::SrcIm2col<PAD> a{x.hi, x.lo_off, s2d ? lp.g2 : lp.g, s2d ? 6 : lp.cshift, Mr};
   tc::SrcDense bs{dy.hi, dy.lo_off, nullptr, lp.N, Mr};
-  tc::TcEpiAtomic ep{dw, alpha, lp.N, lp.K, lp.N};
+  tc::TcEpiAtomic ep{dw, alpha, lp.N, lp.K, lp.N, s2d ? lp.g2.KH : 0};
   long long ctas = (long long)((lp.K + 127) / 128);
   int ks = tc::pick_ksplit(ctas, Mr, 64, 148);
   if (x_split) {
@@ -416,7 +437,7 @@ static cudaError_t tc_conv_wgrad_t(const LayerPlan& lp, Planes x, bool x_split, 
 static cudaError_t tc_dense_wgrad(const LayerPlan& lp, Planes x, Planes dy, float* dw, int B, cudaStream_t st) {
   tc::SrcDense a{x.hi, x.lo_off, nullptr, lp.K, B};
   tc::SrcDense bs{dy.hi, dy.lo_off, nullptr, lp.N, B};
-  tc::TcEpiAtomic ep{dw, 1.f, lp.N, lp.K, lp.N};
+  tc::TcEpiAtomic ep{dw, 1.f, lp.N, lp.K, lp.N, 0};
   long long ctas = (long long)((lp.K + 127) / 128) * ((lp.N + 63) / 64);
   int ks = tc::pick_ksplit(ctas, B, 64, 148);
   return tc::launch_tc<64, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st);
@@ -475,6 +496,13 @@ extern "C" int xtb_tc_trace_set(unsigned long long* buf) {
 }
 #endif
 
+#ifdef XTB_TC_PROF
+extern "C" int xtb_tc_prof_set(long long* buf) {
+  CUDA_TRY(cudaMemcpyToSymbol(tc::g_tc_prof, &buf, sizeof buf));
+  return XTB_OK;
+}
+#endif
+
 // Self-test of the three operand-major combinations on plain matrices (see tests/test_gpu_tc.py):
 //   mode 0: C[M,N] = A[M,K]   * B[K,N]      (A K-major, B MN-major : forward)
 //   mode 1: C[M,N] = A[M,K]   * Bt[N,K]^T   (both K-major         : data gradient)
@@ -495,7 +523,7 @@ extern "C" int xtb_tc_gemm_test(int mode, const float* a, const float* b, float*
   tc::SrcDense bs{pb, nb, nullptr, mode == 1 ? K : N, mode == 1 ? N : K};
   if (ksplit > 1) {
     CUDA_TRY(cudaMemsetAsync(c, 0, (size_t)M * N * sizeof(float), st));
-    tc::TcEpiAtomic ep{c, 1.f, N, M, N};
+    tc::TcEpiAtomic ep{c, 1.f, N, M, N, 0};
     if (mode == 0) e = tc::launch_tc<64, 64, false, true, true, true>(as, bs, ep, M, N, K, ksplit, st);
     else if (mode == 1) e = tc::launch_tc<64, 64, false, false, true, true>(as, bs, ep, M, N, K, ksplit, st);
     else e = tc::launch_tc<64, 64, true, true, true, true>(as, bs, ep, M, N, K, ksplit, st);
@@ -621,6 +649,12 @@ static int op_decode(xtb_net* net, const void* obs, const int32_t* idx, int B, c
   for (const auto& lp : net->L) if (lp.d.src == 0 && tc_conv_ok(net, lp)) need = true;
   if (!need) return XTB_OK;
   int per = net->tsize[0];
+  if (net->s2d) {
+    dim3 grid((per / 16 + 255) / 256, B);
+    XLAUNCH(tc::decode_u8_s2d_kernel, grid, 256, 0, st, (const uint8_t*)obs, idx, net->desc.in_h, net->desc.in_w, obs_planes(net).hi);
+    LAUNCH_CHECK();
+    return XTB_OK;
+  }
   dim3 grid((per / 16 + 255) / 256, B);
   XLAUNCH(tc::decode_u8_kernel, grid, 256, 0, st, (const uint8_t*)obs, idx, per, obs_planes(net).hi);
   LAUNCH_CHECK();
