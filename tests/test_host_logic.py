@@ -146,3 +146,34 @@ def test_stager_thread_pool_with_mock_dma(repo_root, tmp_path):
     for threads in ("0", "1", "6"):
         res = subprocess.run([str(exe)], env=dict(os.environ, XTB_STAGE_THREADS=threads), capture_output=True, text=True, timeout=300)
         assert res.returncode == 0 and "all ok" in res.stdout, res.stdout[-500:]
+
+
+def test_space_to_depth_identity_of_the_first_conv_layer():
+    """The tensor-core path runs the 8x8 stride-4 conv over [84,84,4] as a 2x2 stride-1 conv over the space-to-depth
+    plane [21,21,64] (csrc/gemm_tc.cuh: decode_u8_s2d_kernel, s2d_row).  Restated in numpy: plane layout, weight-row
+    map and the resulting GEMM equal the oracle's conv (xt/model/model_utils.py:141-160 Conv2D 32 x 8x8 / 4)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(0)
+    B, H, W, C, k, S, co = 2, 84, 84, 4, 8, 4, 32
+    x = rng.integers(0, 256, (B, H, W, C)).astype(np.float32)
+    w = rng.standard_normal((k, k, C, co)).astype(np.float32)
+    ref = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w).permute(3, 2, 0, 1), stride=S)
+    ref = ref.permute(0, 2, 3, 1).numpy()                                     # [B,20,20,32]
+    # plane: dst[b, Y, X, (dy, dx, c)] = x[b, 4Y+dy, 4X+dx, c]
+    plane = x.reshape(B, H // 4, 4, W // 4, 4, C).transpose(0, 1, 3, 2, 4, 5).reshape(B, H // 4, W // 4, 64)
+    k4 = k // 4
+
+    def s2d_row(m):     # the device function, verbatim arithmetic
+        tap, ty = m >> 6, (m >> 6) // k4
+        tx = tap - ty * k4
+        dy, dx, c = (m >> 4) & 3, (m >> 2) & 3, m & 3
+        return (((4 * ty + dy) * 4 * k4 + 4 * tx + dx) << 2) + c
+
+    rows = np.array([s2d_row(m) for m in range(k * k * C)])
+    assert sorted(rows.tolist()) == list(range(k * k * C))                    # a permutation of the weight rows
+    w2 = w.reshape(k * k * C, co)[rows]                                       # [(ty,tx,dy,dx,c), co]
+    OH = OW = (H - k) // S + 1
+    cols = np.stack([plane[:, ty:ty + OH, tx:tx + OW, :] for ty in range(k4) for tx in range(k4)], axis=3)
+    out = cols.reshape(B, OH, OW, k4 * k4 * 64) @ w2
+    assert np.allclose(out, ref, rtol=1e-4, atol=1e-2)
