@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+    # the oracle runs on torch-CPU: on many-core hosts the default thread count (all cores) is ~50x slower than 16
+    # threads for these layer sizes (oversubscribed intra-op pool), so cap it for the whole session
+    import torch
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
 
 
 @pytest.fixture(scope="session")

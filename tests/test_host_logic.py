@@ -26,6 +26,8 @@ def test_library_builds_loads_and_exports_every_declared_symbol(repo_root):
     # argument validation happens before any CUDA call
     assert lib.xtb_gae(None, None, None, 1, 1, 0.99, 0.95, 0, None, None, None, None) == -1
     assert b"null" in lib.xtb_last_error()
+    assert lib.xtb_copy_h2d_staged(None, None, 16, None) == -1      # argument check happens before any CUDA call
+    assert lib.xtb_ppo_predict_host(None, None, 0, None, 1, 1, 2, 0, None, None, None, 0, None) == -1
 
 
 def test_product_has_no_oracle_or_cpu_fallback(repo_root):
