@@ -4,13 +4,15 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import xingtian_b200 as xb
-from oracle import xt_oracle as orc
 E, T = 32, 128
 info = {"actor": {"model_name": "PpoCnn", "state_dim": [84, 84, 4], "action_dim": 4, "input_dtype": "uint8",
                   "model_config": {"BATCH_SIZE": 320, "ENTROPY_LOSS": 0.003, "LOSS_CLIPPING": 0.1, "LR": 0.00025, "NUM_SGD_ITER": 4,
                                    "hidden_sizes": [256], "action_type": "Categorical", "init_seed": 0}, "max_predict_batch": 320}}
 alg = xb.alg_builder("PPO", info, {"instance_num": E, "agent_num": 1})
-ro = orc.synth_ppo_rollout(0, E, T)
+rng = np.random.default_rng(0)      # synthetic rollout of the C2 shapes (the numbers do not matter for host timing)
+ro = dict(obs=rng.integers(0, 256, (E * T, 84, 84, 4), dtype=np.uint8), action=rng.integers(0, 4, E * T).astype(np.int32),
+          logp=np.full((E * T, 1), -1.386, np.float32), value=rng.standard_normal((E, T + 1, 1)).astype(np.float32),
+          reward=rng.integers(-1, 2, (E * T, 1)).astype(np.float32), done=rng.random((E * T, 1)) < 0.01)
 host_obs = [np.ascontiguousarray(ro["obs"][np.arange(E) * T + t]) for t in range(T)]
 traj = [dict(cur_state=ro["obs"][e * T:(e + 1) * T], action=ro["action"][e * T:(e + 1) * T], logp=ro["logp"][e * T:(e + 1) * T],
              value=ro["value"][e], reward=ro["reward"][e * T:(e + 1) * T], done=ro["done"][e * T:(e + 1) * T]) for e in range(E)]

@@ -2,9 +2,9 @@
 """Data-parallel equivalence on real GPUs (run under torchrun, 2+ ranks):
 every rank trains on its own env shard with gradients all-reduced over NCCL; rank 0 also trains a single-GPU
 replica on the concatenated rollout with the interleaved minibatch order.  Loss traces and final weights must agree.
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/dp_check.py"""
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/tools/dp_check.py"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, torch.distributed as dist
 
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
