@@ -13,10 +13,11 @@
 #include <unistd.h>
 struct Ev { std::atomic<uint64_t> target{0}; };
 struct Op { int kind; void* d; const void* s; size_t n; Ev* ev; uint64_t id; };
+static std::atomic<long> n_copies{0};
 static std::deque<Op> q; static std::mutex qm; static std::atomic<uint64_t> done_id{0}, next_id{0};
 static void dma() { for (;;) { Op o; { std::lock_guard<std::mutex> l(qm); if (q.empty()) { o.kind = -1; } else { o = q.front(); q.pop_front(); } }
   if (o.kind < 0) { usleep(5); continue; }
-  if (o.kind == 0) { usleep(3); memcpy(o.d, o.s, o.n); }
+  if (o.kind == 0) { usleep((o.id % 37 == 0) ? 200 : 3); memcpy(o.d, o.s, o.n); n_copies++; }
   done_id.store(o.id); } }
 static void ensure() { static bool st = false; if (!st) { st = true; std::thread(dma).detach(); } }
 extern "C" {
@@ -44,5 +45,6 @@ int main() {
     if (memcmp(dst.data(), keep.data(), n)) { printf("MISMATCH it=%d n=%zu\n", it, n); return 1; }
     if (it % 50 == 0) { printf("it %d ok (n=%zu, threads=%d)\n", it, n, st.threads()); usleep(it % 100 == 0 ? 2000 : 0); }
   }
+  printf("dma copies issued: %ld\n", n_copies.load());
   printf("all ok\n"); return 0;
 }

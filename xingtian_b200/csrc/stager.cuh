@@ -3,7 +3,7 @@
 // The reference feeds every sess.run() from pageable numpy arrays (feed_dict, xt/model/ppo/ppo.py:104-132,
 // xt/model/tf_compat usage in xt/model/model.py:47-65); TF stages them with one host thread.  Here the
 // calling thread splits the source into chunks, worker threads memcpy chunks into pinned slots in
-// parallel, and the caller issues one cudaMemcpyAsync per chunk as soon as it is staged, so the host
+// parallel, and the caller issues one cudaMemcpyAsync per run of staged chunks (contiguous in the ring), so the host
 // memcpy (the slow leg: ~10 GB/s per core) runs on several cores and overlaps the DMA.
 //
 // Semantics of stage_h2d(): on return the source buffer has been fully consumed (it may be reused or
@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -48,7 +49,7 @@ class Stager {
         if ((err = wait_slot(slot)) != cudaSuccess) return err;
         size_t off = c * CHUNK, len = bytes - off < CHUNK ? bytes - off : CHUNK;
         memcpy(ring_ + (size_t)slot * CHUNK, s + off, len);
-        if ((err = issue(slot, d + off, len, stream)) != cudaSuccess) return err;
+        if ((err = issue(slot, 1, d + off, len, stream)) != cudaSuccess) return err;
       }
       seq_ += n;
       return cudaSuccess;
@@ -70,21 +71,29 @@ class Stager {
     if (sleepers_.load(std::memory_order_acquire) > 0) { std::lock_guard<std::mutex> lk(mu_); cv_.notify_all(); }
 
     cudaError_t first = cudaSuccess;
-    for (size_t c = 0; c < n; c++) {
-      // the caller helps with the memcpy while it waits for chunk c
+    const size_t nw = workers_.size();
+    for (size_t c = 0; c < n;) {
+      // wait for chunk c; the caller stages chunks itself only while more are unclaimed than the workers can take
+      // (or the workers are still asleep): a chunk in hand would delay the copies that are ready to be issued
       while (!done_[c].load(std::memory_order_acquire)) {
-        if (!work_one(g)) cpu_relax();
+        const size_t claimed = (size_t)(next_.load(std::memory_order_acquire) & 0xffffffffu);
+        const bool help = sleepers_.load(std::memory_order_acquire) > 0 || n - std::min(claimed, n) > nw;
+        if (!(help && work_one(g))) cpu_relax();
         if (allowed < n && allowed < c + SLOTS) {            // hand out slots whose previous DMA (issued: chunk < c) finished
           int slot = (int)((seq_ + allowed) % SLOTS);
-          if (cudaEventQuery(ev_[slot]) == cudaSuccess) allowed_.store(++allowed, std::memory_order_release);
+          if (query_slot(slot) == cudaSuccess) allowed_.store(++allowed, std::memory_order_release);
         }
       }
-      int slot = (int)((seq_ + c) % SLOTS);
-      size_t off = c * CHUNK, len = bytes - off < CHUNK ? bytes - off : CHUNK;
-      if (first == cudaSuccess) first = issue(slot, d + off, len, stream);
-      if (allowed < n && allowed <= c + 1) {                 // nothing else staged: block on the oldest DMA
+      // one DMA for the run of finished chunks that is contiguous in the ring: c .. e
+      size_t e = c;
+      while (e + 1 < n && (int)((seq_ + e + 1) % SLOTS) != 0 && done_[e + 1].load(std::memory_order_acquire)) e++;
+      const int slot0 = (int)((seq_ + c) % SLOTS);
+      const size_t off = c * CHUNK, end = std::min(bytes, (e + 1) * CHUNK);
+      if (first == cudaSuccess) first = issue(slot0, (int)(e - c + 1), d + off, end - off, stream);
+      c = e + 1;
+      if (allowed < n && allowed <= c) {                     // nothing else can be staged: block on the oldest DMA
         int s2 = (int)((seq_ + allowed) % SLOTS);
-        cudaError_t e2 = cudaEventSynchronize(ev_[s2]);
+        cudaError_t e2 = wait_slot(s2);
         if (first == cudaSuccess) first = e2;
         allowed_.store(++allowed, std::memory_order_release);
       }
@@ -113,7 +122,7 @@ class Stager {
     for (int i = 0; i < SLOTS; i++) {
       e = cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming);
       if (e != cudaSuccess) return e;
-      used_[i] = false;
+      used_[i] = false; owner_[i] = i;
     }
     int nt = 4;
     if (const char* env = getenv("XTB_STAGE_THREADS")) nt = atoi(env);
@@ -125,16 +134,24 @@ class Stager {
     return cudaSuccess;
   }
 
+  // A run of slots issued as one DMA shares the event of its last slot (owner_[slot]); that event may be re-recorded
+  // by a later run ending in the same slot, which only makes a wait on it more conservative.
   cudaError_t wait_slot(int slot) {
     if (!used_[slot]) return cudaSuccess;
-    return cudaEventSynchronize(ev_[slot]);
+    return cudaEventSynchronize(ev_[owner_[slot]]);
+  }
+  cudaError_t query_slot(int slot) {
+    if (!used_[slot]) return cudaSuccess;
+    return cudaEventQuery(ev_[owner_[slot]]);
   }
 
-  cudaError_t issue(int slot, void* dst, size_t len, cudaStream_t stream) {
+  // one async copy out of `count` consecutive ring slots starting at `slot`
+  cudaError_t issue(int slot, int count, void* dst, size_t len, cudaStream_t stream) {
     cudaError_t e = cudaMemcpyAsync(dst, ring_ + (size_t)slot * CHUNK, len, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
-    used_[slot] = true;
-    return cudaEventRecord(ev_[slot], stream);
+    const int last = slot + count - 1;
+    for (int i = slot; i <= last; i++) { used_[i] = true; owner_[i] = last; }
+    return cudaEventRecord(ev_[last], stream);
   }
 
   // claim and stage one chunk of the open job; false if none is claimable right now
@@ -195,6 +212,7 @@ class Stager {
   char* ring_ = nullptr;
   cudaEvent_t ev_[SLOTS];
   bool used_[SLOTS];
+  int owner_[SLOTS];
   std::vector<std::thread> workers_;
 };
 
