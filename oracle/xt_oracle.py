@@ -11,10 +11,16 @@ absent) and its tests hold no numeric golden vectors.  The pure-numpy pieces
 of the reference (GAE ``data_proc``, the PPO minibatch loop, the DQN TD-target
 loop, ``ReplayBuffer``, ``IMPALAOpt._data_proc``) ARE executed from
 ``/root/reference`` by ``tests/golden/make_golden.py`` (with stubbed TF
-sessions) and this oracle is checked against those fixtures.  Everything that
-bottoms out in tensorflow ops (conv/dense/softmax-xent/Adam/clip/tf.scan) is
-restated from TF-1.15's documented semantics: for those rows parity is
-UNPINNED and the restatement is the pin.
+sessions) and this oracle is checked against those fixtures.  The reference's
+loss code -- ``CategoricalDist`` (tf_dist.py:89-113), ``actor_loss_with_entropy``
+/ ``critic_loss`` (model/ppo/__init__.py:4-25), ``vtrace.from_logic_outputs``
+(impala/vtrace.py:39-115) and ``vtrace_loss`` (impala_cnn_opt.py:299-351) -- is
+executed too, over a numpy stand-in for the dozen TensorFlow ops it calls
+(``tf_losses.npz``): the STRUCTURE of those functions is pinned, the TF kernels
+behind the individual ops are not.  What still bottoms out in tensorflow alone
+(conv/dense layers, autodiff, ``AdamOptimizer``, ``clip_by_global_norm``,
+``tf.random.categorical``) is restated from TF-1.15's documented semantics:
+for those rows parity is UNPINNED and the restatement is the pin.
 
 Each function cites the reference file:line it follows (paths relative to
 /root/reference).

@@ -11,6 +11,16 @@ base classes) and records what the reference code itself computes:
   dqn_target.npz     DQN.train TD-target loop     (xt/algorithm/dqn/dqn.py:61-103) [actor.predict stubbed]
   impala_proc.npz    IMPALAOpt._data_proc/train slicing (xt/algorithm/impala/impala_opt.py:73-147)
 
+and, with a small numpy stand-in for the dozen TensorFlow ops they call (class TFShim below: eager float32, the documented
+TF-1.15 semantics of exp/log/min/max/clip/reduce_*/one_hot/softmax-xent/scan(reverse)), the reference's loss code itself:
+
+  tf_losses.npz      CategoricalDist.neglog_prob/entropy      (xt/model/tf_dist.py:89-113)
+                     actor_loss_with_entropy, critic_loss     (xt/model/ppo/__init__.py:4-25)
+                     vtrace.from_logic_outputs                (xt/model/impala/vtrace.py:39-115)
+                     vtrace_loss and its three terms          (xt/model/impala/impala_cnn_opt.py:299-351)
+  This pins the structure of those functions (indexing, clipping, bootstrap handling, sums vs means); the TF kernels
+  behind the individual ops stay unpinned.
+
 Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
 The fixtures are committed; nothing on the GPU box reads /root/reference."""
 import importlib.util
@@ -218,6 +228,175 @@ def golden_impala():
     print("impala_proc.npz", out["slice_sizes"])
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# numpy stand-in for the TensorFlow ops used by the reference's loss / distribution / V-trace code
+# ------------------------------------------------------------------------------------------------------------------
+class _NN(object):
+    @staticmethod
+    def log_softmax(x, axis=-1):
+        x = np.asarray(x, np.float32)
+        m = x.max(axis=axis, keepdims=True)
+        return (x - m - np.log(np.exp(x - m).sum(axis=axis, keepdims=True), dtype=np.float32)).astype(np.float32)
+
+    @staticmethod
+    def softmax(x, axis=-1):
+        return np.exp(_NN.log_softmax(x, axis)).astype(np.float32)
+
+    @staticmethod
+    def softmax_cross_entropy_with_logits_v2(labels, logits):
+        return (-(np.asarray(labels, np.float32) * _NN.log_softmax(logits)).sum(-1)).astype(np.float32)
+
+    @staticmethod
+    def sparse_softmax_cross_entropy_with_logits(labels, logits):
+        ls = _NN.log_softmax(logits)
+        return (-np.take_along_axis(ls, np.asarray(labels, np.int64)[..., None], -1)[..., 0]).astype(np.float32)
+
+
+class _Shape(tuple):
+    def assert_has_rank(self, rank):
+        assert len(self) == rank, (tuple(self), rank)
+
+    def as_list(self):
+        return list(self)
+
+
+class _Tensor(np.ndarray):
+    """ndarray whose .shape answers TensorShape.assert_has_rank (vtrace.py:67-69)."""
+
+    @property
+    def shape(self):
+        return _Shape(np.ndarray.shape.__get__(self))
+
+
+class TFShim(object):
+    float32, int32 = np.float32, np.int32
+    nn = _NN
+
+    class _Ctx(object):
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+
+    @staticmethod
+    def device(name): return TFShim._Ctx()
+    @staticmethod
+    def convert_to_tensor(x, dtype=None): return np.asarray(x, dtype).view(_Tensor)
+    @staticmethod
+    def exp(x): return np.exp(np.asarray(x, np.float32)).astype(np.float32)
+    @staticmethod
+    def log(x): return np.log(np.asarray(x, np.float32)).astype(np.float32)
+    @staticmethod
+    def square(x): return np.square(np.asarray(x, np.float32))
+    @staticmethod
+    def add(a, b): return np.asarray(a, np.float32) + np.asarray(b, np.float32)
+    @staticmethod
+    def minimum(a, b): return np.minimum(np.float32(a) if np.isscalar(a) else a, np.float32(b) if np.isscalar(b) else b)
+    @staticmethod
+    def maximum(a, b): return np.maximum(np.float32(a) if np.isscalar(a) else a, np.float32(b) if np.isscalar(b) else b)
+    @staticmethod
+    def clip_by_value(x, lo, hi): return np.clip(np.asarray(x, np.float32), np.float32(lo), np.float32(hi))
+    @staticmethod
+    def reduce_mean(x, axis=None, keepdims=False): return np.mean(np.asarray(x, np.float32), axis=axis, keepdims=keepdims, dtype=np.float32)
+    @staticmethod
+    def reduce_sum(x, axis=None, keepdims=False): return np.sum(np.asarray(x, np.float32), axis=axis, keepdims=keepdims, dtype=np.float32)
+    @staticmethod
+    def reduce_max(x, axis=None, keepdims=False): return np.max(np.asarray(x, np.float32), axis=axis, keepdims=keepdims)
+    @staticmethod
+    def one_hot(x, depth): return np.eye(depth, dtype=np.float32)[np.asarray(x, np.int64)]
+    @staticmethod
+    def expand_dims(x, axis): return np.expand_dims(x, axis)
+    @staticmethod
+    def concat(xs, axis=0): return np.concatenate(xs, axis=axis)
+    @staticmethod
+    def zeros_like(x): return np.zeros_like(x)
+    @staticmethod
+    def stop_gradient(x): return x
+
+    @staticmethod
+    def scan(fn, elems, initializer, parallel_iterations=None, back_prop=None, reverse=False):
+        """tf.scan over the leading axis of a tuple of tensors; reverse=True walks from the last element to the first
+        and places each result at the index of the element it consumed."""
+        n = elems[0].shape[0]
+        out = [None] * n
+        acc = initializer
+        for i in (range(n - 1, -1, -1) if reverse else range(n)):
+            acc = fn(acc, tuple(e[i] for e in elems))
+            out[i] = acc
+        return np.stack(out, 0).astype(np.float32)
+
+
+class _AnyName(types.ModuleType):
+    """xt.model.tf_compat stand-in: `tf` is the shim, every other imported name (Conv2D, Saver, ...) is an inert placeholder."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return type(name, (), {})
+
+
+def golden_tf_losses():
+    compat = _AnyName("xt.model.tf_compat")
+    compat.tf = TFShim
+    compat.DTYPE_MAP = {"float32": np.float32}
+    sys.modules["xt.model.tf_compat"] = compat
+    dist_mod = _load("xt.model.tf_dist", "xt/model/tf_dist.py")
+    ppo_mod = _load("xt.model.ppo", "xt/model/ppo/__init__.py")
+    _mod("xt.model.impala").__path__ = []
+    vtrace = _load("xt.model.impala.vtrace", "xt/model/impala/vtrace.py")
+    sys.modules["xt.model.impala"].vtrace = vtrace
+    # imports of impala_cnn_opt.py that are irrelevant to its loss functions
+    for name in ("tensorflow", "tensorflow.python", "tensorflow.python.util"):
+        _mod(name).__path__ = []
+    _mod("tensorflow.python.util.deprecation", _PRINT_DEPRECATION_WARNINGS=False)
+    sys.modules["tensorflow.python.util"].deprecation = sys.modules["tensorflow.python.util.deprecation"]
+    sys.modules["xt.model"].XTModel = type("XTModel", (), {})
+    _load("xt.model.impala.default_config", "xt/model/impala/default_config.py")
+    _mod("xt.model.atari_model", get_atari_filter=None)
+    _mod("xt.model.tf_utils", TFVariables=None, restore_tf_variable=None)
+    _mod("xt.model.model_utils", state_transform=None, custom_norm_initializer=None)
+    imp = _load("xt.model.impala.impala_cnn_opt", "xt/model/impala/impala_cnn_opt.py")
+
+    rng = np.random.default_rng(77)
+    out = {}
+    # --- categorical distribution + PPO losses (shapes of xt/model/ppo/ppo.py:62-92: actions [B], the rest [B,1])
+    for case, (B, A, scale) in enumerate([(5, 4, 1.0), (320, 4, 3.0), (257, 6, 30.0), (1, 2, 0.1)]):
+        logits = (rng.standard_normal((B, A)) * scale).astype(np.float32)
+        act = rng.integers(0, A, B).astype(np.int32)
+        adv = rng.standard_normal((B, 1)).astype(np.float32)
+        old_logp = (-np.abs(rng.standard_normal((B, 1))) - 0.3).astype(np.float32)
+        old_v, target_v = rng.standard_normal((B, 1)).astype(np.float32), rng.standard_normal((B, 1)).astype(np.float32)
+        out_v = (old_v + 4.0 * rng.standard_normal((B, 1))).astype(np.float32)
+        dist = dist_mod.CategoricalDist(A)
+        dist.init_by_param(logits)
+        pre = "ppo%d_" % case
+        out[pre + "logits"], out[pre + "action"], out[pre + "adv"], out[pre + "old_logp"] = logits, act, adv, old_logp
+        out[pre + "old_v"], out[pre + "target_v"], out[pre + "out_v"] = old_v, target_v, out_v
+        out[pre + "neglogp"] = dist.neglog_prob(act)
+        out[pre + "entropy"] = dist.entropy()
+        for clip, ent in ((0.1, 0.003), (0.2, 0.01)):
+            out[pre + "actor_loss_%g_%g" % (clip, ent)] = np.float32(ppo_mod.actor_loss_with_entropy(dist, adv, old_logp, act, clip, ent))
+        for vclip in (5.0, 0.5):
+            out[pre + "critic_loss_%g" % vclip] = np.float32(ppo_mod.critic_loss(target_v, out_v, old_v, vclip))
+    # --- V-trace (time-major [T', B, ...]) and the IMPALA loss terms
+    for case, (T, B, A) in enumerate([(7, 1, 4), (127, 4, 4), (19, 3, 6)]):
+        bp = rng.standard_normal((T, B, A)).astype(np.float32)
+        tp = (bp + 0.5 * rng.standard_normal((T, B, A))).astype(np.float32)
+        act = rng.integers(0, A, (T, B)).astype(np.int32)
+        disc = ((rng.random((T, B)) > 0.05) * 0.99).astype(np.float32)
+        rew = np.clip(rng.standard_normal((T, B)), -1, 1).astype(np.float32)
+        val = rng.standard_normal((T, B)).astype(np.float32)
+        boot = rng.standard_normal(B).astype(np.float32)
+        vs, pg = vtrace.from_logic_outputs(bp, tp, act, disc, rew, val, boot)
+        pre = "vt%d_" % case
+        for k, v in dict(bp=bp, tp=tp, action=act, discount=disc, reward=rew, value=val, bootstrap=boot, vs=vs, pg_adv=pg).items():
+            out[pre + k] = v
+        out[pre + "pi_loss"] = np.float32(imp.calc_pi_loss(tp, act, pg))
+        out[pre + "baseline_loss"] = np.float32(imp.calc_baseline_loss(vs - val))
+        out[pre + "entropy_loss"] = np.float32(imp.calc_entropy_loss(tp))
+        out[pre + "total_loss"] = np.float32(imp.vtrace_loss(bp, tp, act, disc, rew, val, boot))
+    np.savez(os.path.join(OUT, "tf_losses.npz"), **{k: np.asarray(v) for k, v in out.items()})
+    print("tf_losses.npz", len(out), "arrays; vt1 total", out["vt1_total_loss"], "ppo1 actor", out["ppo1_actor_loss_0.1_0.003"])
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference")
@@ -226,3 +405,4 @@ if __name__ == "__main__":
     golden_ppo_minibatch()
     golden_dqn()
     golden_impala()
+    golden_tf_losses()

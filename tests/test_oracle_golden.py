@@ -160,3 +160,52 @@ def test_data_parallel_gradient_identity():
         parts.append([x * 0.5 for x in g])     # local mean over 20 -> global mean over 40
     for a, b, c in zip(g_full, *parts):
         torch.testing.assert_close(a, b + c, rtol=1e-4, atol=1e-6)
+
+
+def _tf_losses():
+    return np.load(os.path.join(G, "tf_losses.npz"))
+
+
+def test_categorical_and_ppo_losses_vs_reference_code():
+    """tf_losses.npz holds what xt/model/tf_dist.py:89-113 and xt/model/ppo/__init__.py:4-25 THEMSELVES return when
+    executed over the numpy stand-in for their TensorFlow ops (tests/golden/make_golden.py): the oracle's categorical
+    log-prob / entropy and the PPO loss (actor + c_v * critic, xt/model/ppo/ppo.py:89-92) must reproduce them."""
+    import torch
+    g = _tf_losses()
+    for case in range(4):
+        p = "ppo%d_" % case
+        t = lambda k: torch.from_numpy(g[p + k])
+        logits, act = t("logits"), torch.from_numpy(g[p + "action"].astype(np.int64))
+        assert np.allclose(-orc.categorical_logp(logits, act).numpy(), g[p + "neglogp"], rtol=1e-5, atol=2e-5)
+        assert np.allclose(orc.categorical_entropy(logits).numpy(), g[p + "entropy"], rtol=1e-5, atol=1e-6)
+        for (clip, ent), vclip, cc in (((0.1, 0.003), 5.0, 1.0), ((0.2, 0.01), 0.5, 0.5)):
+            want = float(g[p + "actor_loss_%g_%g" % (clip, ent)]) + cc * float(g[p + "critic_loss_%g" % vclip])
+            got = float(orc.ppo_loss(logits, t("out_v"), act, t("old_logp"), t("adv"), t("old_v"), t("target_v"),
+                                     clip, ent, vclip, cc))
+            assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (case, got, want)
+
+
+def test_vtrace_and_impala_loss_vs_reference_code():
+    """vtrace.from_logic_outputs (xt/model/impala/vtrace.py:39-115) and vtrace_loss with its three terms
+    (impala_cnn_opt.py:299-351) executed over the numpy TF stand-in: vs / pg_advantages of the oracle's V-trace and the
+    total of the oracle's impala_loss (fed the env-major flat layout the learner sees, one dropped step appended)."""
+    import torch
+    g = _tf_losses()
+    for case in range(3):
+        p = "vt%d_" % case
+        bp, tp, act = g[p + "bp"], g[p + "tp"], g[p + "action"]
+        disc, rew, val, boot = g[p + "discount"], g[p + "reward"], g[p + "value"], g[p + "bootstrap"]
+        vs, pg = orc.vtrace_from_logits(bp, tp, act, disc, rew, val, boot)
+        assert np.allclose(vs, g[p + "vs"], rtol=2e-5, atol=2e-5) and np.allclose(pg, g[p + "pg_adv"], rtol=2e-5, atol=2e-5)
+        # env-major flat inputs [B*(T+1), ...]: step T carries the bootstrap value, its other entries are dropped
+        T, B, A = tp.shape
+        pad = lambda x, fill: np.concatenate([x, np.full((1,) + x.shape[1:], fill, x.dtype)], 0)
+        flat = lambda x: np.ascontiguousarray(np.swapaxes(x, 0, 1)).reshape((B * (T + 1),) + x.shape[2:])
+        tp_f = torch.from_numpy(flat(pad(tp, 0.25)))
+        base_f = torch.from_numpy(flat(np.concatenate([val, boot[None]], 0)))
+        total = orc.impala_loss(tp_f, base_f, flat(pad(bp, 0.5)), flat(pad(act, 0)), flat(pad(disc == 0, False)),
+                                flat(pad(rew, 0.0)), T + 1, gamma=0.99)
+        want = float(g[p + "total_loss"])
+        parts = float(g[p + "pi_loss"]) + 0.5 * float(g[p + "baseline_loss"]) + 0.01 * float(g[p + "entropy_loss"])
+        assert abs(parts - want) <= 1e-5 * abs(want)
+        assert abs(float(total) - want) <= 5e-5 * max(1.0, abs(want)), (case, float(total), want)
