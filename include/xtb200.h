@@ -69,6 +69,8 @@ int xtb_version(void);
 const char* xtb_last_error(void);
 /* Number of kernels this library has launched in the calling process (all threads). */
 long long xtb_launch_count(void);
+/* Number of CUDA-graph replays (fused training loop / rollout inference) the library has issued. */
+long long xtb_graph_replay_count(void);
 
 /* ---- network: replaces XTModel's TF graph (xt/model/model.py:30-127) ---------- */
 /* Flat fp32 parameter layout: per layer, kernel [K,N] (HWIO flattened) then bias [N];
@@ -84,6 +86,8 @@ int xtb_net_tensor_size(const xtb_net* net, int t);
 size_t xtb_net_workspace_bytes(const xtb_net* net);
 /* params/grads: [param_count] floats; workspace: xtb_net_workspace_bytes() bytes */
 int xtb_net_bind(xtb_net* net, float* params, float* grads, void* workspace, size_t workspace_bytes);
+/* same, with the initialisation work (workspace clear, weight blobs) ordered on `stream`; returns after it completed */
+int xtb_net_bind_stream(xtb_net* net, float* params, float* grads, void* workspace, size_t workspace_bytes, void* stream);
 /* Every tensor the tensor-core kernels read is kept as two bf16 planes (hi = bf16(x), lo = bf16(x-hi)) next
  * to its fp32 copy.  The planes of the bound parameters are refreshed by xtb_net_bind, by the fused training
  * loops after each optimiser step, and by this call -- which a host that writes the parameter buffer itself

@@ -289,6 +289,45 @@ def test_rollout_infer_graph_matches_per_step_predict():
     assert (act[0].cpu().numpy() == ract).mean() >= 0.85
 
 
+def test_cuda_graph_path_is_taken_and_equals_eager():
+    """The fused training loop and the rollout inference are replayed as CUDA graphs when the host passes the default
+    (NULL) stream -- the library moves them onto its fenced private stream -- and give the eager path's results."""
+    import xingtian_b200 as xb
+    from xingtian_b200 import capi
+    lib = capi.lib()
+    outs = []
+    for graph in (True, False):
+        info = ppo_cnn_info(batch=24, iters=2)
+        info["actor"]["model_config"]["use_cuda_graph"] = graph
+        alg = xb.alg_builder("PPO", info, alg_cfg())
+        r0 = lib.xtb_graph_replay_count()
+        losses = []
+        for it in range(2):                 # second iteration replays the instantiated graph
+            for tr in make_trajs(4, 16, seed=3 + it):
+                alg.prepare_data({k: tr[k] for k in ("cur_state", "action", "logp", "adv", "old_value", "target_value")})
+            np.random.seed(5 + it)
+            losses.append(alg.train())
+        replays = lib.xtb_graph_replay_count() - r0
+        assert replays == (2 if graph else 0), replays
+        w = alg.get_weights()
+        outs.append((np.array(losses), np.concatenate([v.ravel() for v in w.values()])))
+    assert rel_err(outs[0][0], outs[1][0]) < 1e-3
+    assert l2_rel(outs[0][1], outs[1][1]) < 1e-3
+    # Adam's learning rate lives in device memory: a captured graph must see xtb_adam_set_lr
+    alg = xb.alg_builder("PPO", ppo_cnn_info(batch=24, iters=1), alg_cfg())
+    w0 = np.concatenate([v.ravel() for v in alg.get_weights().values()])
+    steps = []
+    for lr in (2.5e-4, 0.0):
+        capi.check(lib.xtb_adam_set_lr(alg.actor.opt.handle, lr))
+        for tr in make_trajs(4, 16, seed=9):
+            alg.prepare_data({k: tr[k] for k in ("cur_state", "action", "logp", "adv", "old_value", "target_value")})
+        alg.train()
+        w1 = np.concatenate([v.ravel() for v in alg.get_weights().values()])
+        steps.append(float(np.abs(w1 - w0).max()))
+        w0 = w1
+    assert steps[0] > 0 and steps[1] == 0.0, steps
+
+
 def test_fused_heads_equals_unfused():
     """The fused heads+loss kernel and the layer-by-layer path give the same loss trace and weights."""
     import xingtian_b200 as xb

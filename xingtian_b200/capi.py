@@ -41,6 +41,7 @@ _SIGS = {
     "xtb_version": (C.c_int, []),
     "xtb_last_error": (C.c_char_p, []),
     "xtb_launch_count": (C.c_longlong, []),
+    "xtb_graph_replay_count": (C.c_longlong, []),
     "xtb_net_create": (C.c_int, [C.POINTER(NetDesc), C.c_int, C.POINTER(_P)]),
     "xtb_net_destroy": (None, [_P]),
     "xtb_net_param_count": (C.c_longlong, [_P]),
@@ -49,6 +50,7 @@ _SIGS = {
     "xtb_net_tensor_size": (C.c_int, [_P, C.c_int]),
     "xtb_net_workspace_bytes": (C.c_size_t, [_P]),
     "xtb_net_bind": (C.c_int, [_P, _P, _P, _P, C.c_size_t]),
+    "xtb_net_bind_stream": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
     "xtb_net_sync_weights": (C.c_int, [_P, _P]),
     "xtb_net_tensor": (_P, [_P, C.c_int]),
     "xtb_net_tensor_grad": (_P, [_P, C.c_int]),

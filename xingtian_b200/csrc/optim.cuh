@@ -19,6 +19,9 @@ constexpr int OPT_THREADS = 256;
 struct AdamState {          // lives in device memory
   float beta1_pow, beta2_pow, lr_t, grad_norm;
 };
+struct AdamHyper {          // lives in device memory too: a captured CUDA graph must see xtb_adam_set_lr
+  float lr, beta1, beta2, eps, clip;
+};
 
 __global__ void __launch_bounds__(OPT_THREADS)
 sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ blk_seg,
@@ -42,11 +45,11 @@ sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ blk_seg,
   }
 }
 
-__global__ void adam_prep_kernel(AdamState* st, double* norm_sq, float* seg_scale, int n_seg,
-                                 int clip_mode, float clip, float grad_scale, float lr, float beta1,
-                                 float beta2) {
+__global__ void adam_prep_kernel(AdamState* st, const AdamHyper* __restrict__ hyp, double* norm_sq, float* seg_scale, int n_seg,
+                                 int clip_mode, float grad_scale) {
   pdl_wait(); pdl_trigger();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float clip = hyp->clip, lr = hyp->lr, beta1 = hyp->beta1, beta2 = hyp->beta2;
   double tot = 0.0;
   for (int s = 0; s < n_seg; s++) tot += norm_sq[s];
   float gs = fabsf(grad_scale);
@@ -73,9 +76,10 @@ __global__ void __launch_bounds__(OPT_THREADS)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, const int* __restrict__ blk_seg,
             const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
-            const float* __restrict__ seg_scale, const AdamState* __restrict__ st, float beta1,
-            float beta2, float eps, __nv_bfloat16* __restrict__ w_hi, long long w_lo_off) {
+            const float* __restrict__ seg_scale, const AdamState* __restrict__ st, const AdamHyper* __restrict__ hyp,
+            __nv_bfloat16* __restrict__ w_hi, long long w_lo_off) {
   pdl_wait(); pdl_trigger();
+  const float beta1 = hyp->beta1, beta2 = hyp->beta2, eps = hyp->eps;
   long long beg = blk_beg[blockIdx.x];
   int n = blk_len[blockIdx.x];
   float sc = seg_scale[blk_seg[blockIdx.x]];

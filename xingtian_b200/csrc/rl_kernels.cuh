@@ -404,7 +404,8 @@ __global__ void dqn_loss_kernel(const float* __restrict__ q, const float* __rest
 struct PpoHeadsArgs {
   const float* h_pi; const float* h_v;     // [B,K] hidden activations (may alias)
   float* g_pi; float* g_v;                 // [B,K] gradient wrt hidden pre-activation (may alias)
-  __nv_bfloat16* gp_hi; long long gp_lo; __nv_bfloat16* gv_hi; long long gv_lo;   // their bf16 planes
+  __nv_bfloat16* gp_hi; long long gp_lo; __nv_bfloat16* gv_hi; long long gv_lo;   // their batch-planar bf16 planes (bp_gemm.cuh), may be NULL
+  int pitch;                               // rows per feature chunk of those planes
   const float* w_pi; const float* b_pi; const float* w_v; const float* b_v;
   float* dw_pi; float* db_pi; float* dw_v; float* db_v;
   float* dbh_pi; float* dbh_v;             // bias gradients of the layers that produced h_pi / h_v (column sums of g)
@@ -522,14 +523,26 @@ __global__ void __launch_bounds__(256) ppo_heads_kernel(PpoHeadsArgs a) {
         long long eo = (long long)b * K + k;
         if (a.shared) {
           float r = (gp + gv) * act_grad_from_out(a.act_pi, hp_[j]);
-          a.g_pi[eo] = r; f32_store_plane(a.gp_hi, a.gp_lo, eo, r);
+          a.g_pi[eo] = r; f32_store_plane(a.gp_hi, a.gp_lo, ((long long)(k >> 3) * a.pitch + b) * 8 + (k & 7), r);
           bh_pi[j] += r;
         } else {
           float r1 = gp * act_grad_from_out(a.act_pi, hp_[j]), r2 = gv * act_grad_from_out(a.act_v, hv_[j]);
-          a.g_pi[eo] = r1; f32_store_plane(a.gp_hi, a.gp_lo, eo, r1);
-          a.g_v[eo] = r2; f32_store_plane(a.gv_hi, a.gv_lo, eo, r2);
+          a.g_pi[eo] = r1; f32_store_plane(a.gp_hi, a.gp_lo, ((long long)(k >> 3) * a.pitch + b) * 8 + (k & 7), r1);
+          a.g_v[eo] = r2; f32_store_plane(a.gv_hi, a.gv_lo, ((long long)(k >> 3) * a.pitch + b) * 8 + (k & 7), r2);
           bh_pi[j] += r1; bh_v[j] += r2;
         }
+      }
+    }
+  }
+  // plane rows [B, round16(B)) are read by the weight-gradient K loop (16 samples per MMA step): keep them zero
+  for (int b = a.B + blockIdx.x * nwarp + warp; b < ((a.B + 15) & ~15); b += gridDim.x * nwarp) {
+#pragma unroll
+    for (int j = 0; j < HEAD_KPL; j++) {
+      if (j < kpl) {
+        int k = lane + 32 * j;
+        long long e = ((long long)(k >> 3) * a.pitch + b) * 8 + (k & 7);
+        f32_store_plane(a.gp_hi, a.gp_lo, e, 0.f);
+        if (!a.shared) f32_store_plane(a.gv_hi, a.gv_lo, e, 0.f);
       }
     }
   }

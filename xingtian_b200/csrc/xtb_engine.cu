@@ -17,7 +17,7 @@
 #include "optim.cuh"
 #include "rl_kernels.cuh"
 #include "stager.cuh"
-#include "tc_dispatch.cuh"
+#include "bp_gemm.cuh"
 #include <cstdlib>
 #include <type_traits>
 
@@ -62,6 +62,9 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // ------------------------------------------------------------------------------------------
 // network
 // ------------------------------------------------------------------------------------------
+static const int kSMs = 148;
+static const int kMaxDynSmem = 232448 - 2048;   // 227 KiB per CTA minus the kernels' static shared memory
+
 struct LayerPlan {
   xtb_layer_desc d;
   ConvGeom g{};          // conv only
@@ -70,34 +73,47 @@ struct LayerPlan {
   int K = 0, N = 0;      // weight matrix [K,N]
   long long w_off = 0, b_off = 0;
   int src_act = 0;       // activation of the producing layer of the source tensor
-  // device tables (conv)
+  // device tables (conv, fp32 path)
   int* koff = nullptr; int* kyx = nullptr;            // forward / wgrad, indexed by k=(ky,kx,ci)
   int* dkyx = nullptr; int* dco = nullptr; int* wk = nullptr;  // dgrad, indexed by k=(ky,kx,co)
   int Kd = 0;            // KH*KW*Cout
   int sshift = 0;
-  int cshift = -1, oshift = -1;   // log2(Cin), log2(Cout) when powers of two (tensor-core gathers), else -1
   bool pad = false;
-  // space-to-depth view of a stride-4, 4-channel first layer (see tc::decode_u8_s2d_kernel): geometry of the equivalent
-  // (k/4 x k/4, stride 1) conv over [H/4, W/4, 64]; its weight rows map to the real ones through tc::s2d_row
-  bool s2d = false;
-  ConvGeom g2{};
+  // ---- tensor-core (batch-planar) plan; tc = the layer's shapes are covered
+  bool tc = false;
+  bool s2d = false;      // stride-4 4-channel first layer run as a (k/4 x k/4, stride 1) conv over a space-to-depth plane
+  int k4 = 0;
+  ConvGeom q{};          // geometry the tensor-core kernels use (space-to-depth view for s2d layers)
+  long long blob_off = 0;   // element offset of this layer's weight blob (hi plane)
+  bool w_res = false;       // conv: blob resident in shared memory
+  int n_fwd = 0, n_dg = 0;  // accumulator columns: forward (Cout / dense N tile), data gradient (Cin / dense K tile)
+  int run_chunks = 0, mts = 0, R = 0;   // conv weight gradient: chunks per filter row, M tiles per row, accumulators
+  size_t part_off = 0, dbpart_off = 0;  // workspace offsets of the partial-sum areas
 };
+
+struct PendingRed { bp::RedSeg s; };
 
 struct xtb_net {
   xtb_net_desc desc;
-  int max_batch = 0;
+  int max_batch = 0, pitch = 0;
   std::vector<LayerPlan> L;
   std::vector<int> tsize;       // per tensor floats/sample (0 = obs)
   long long n_params = 0;
   size_t ws_bytes = 0;
-  std::vector<size_t> out_off, gout_off;  // byte offsets in workspace per tensor (fp32)
-  std::vector<size_t> ohi_off, ghi_off;   // byte offsets of the bf16 hi planes (lo plane follows at plane_elems)
-  std::vector<long long> plane_elems;     // elements per bf16 plane of tensor t (max_batch*tsize rounded to 8)
-  size_t obs_hi_off = 0, w_hi_off = 0;    // decoded-frame plane, weight planes
-  long long w_plane_elems = 0;
-  bool s2d = false;                       // the observation plane is stored space-to-depth (every first-layer conv agrees)
-  bool gout_planes_fresh = false;         // set while a caller guarantees head-gradient planes are current
+  std::vector<size_t> out_off, gout_off;  // byte offsets in workspace per tensor (fp32 row-major)
+  std::vector<size_t> obp_off, gbp_off;   // byte offsets of the batch-planar hi planes (lo plane follows at plane_elems)
+  std::vector<long long> plane_elems;     // elements per plane of tensor t = tsize * pitch
+  size_t obs_bp_off = 0; int obs_feats = 0;            // decoded-frame plane (space-to-depth canvas)
+  int H4 = 0, W4 = 0;
+  size_t blob_off = 0; long long blob_elems = 0;       // weight blobs: hi plane, lo plane follows
+  size_t splitk_off = 0, zeros_off = 0, segs_off = 0;
+  std::vector<bp::BlobSeg> blob_segs;
+  bool any_tc = false;
   float* params = nullptr; float* grads = nullptr; char* ws = nullptr;
+  // which representation of every tensor / tensor gradient is current
+  std::vector<char> f32_ok, bp_ok, gf32_ok, gbp_ok;
+  bool obs_bp_ok = false;
+  std::vector<bp::RedSeg> pending;        // ordered reductions queued by the running backward pass
 };
 
 static int same_pad(int size, int k, int s, int* out, int* before) {
@@ -108,12 +124,30 @@ static int same_pad(int size, int k, int s, int* out, int* before) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// tcgen05 path (bp_gemm.cuh).  g_tc_mode: 1 = use tensor cores where the shape is covered,
+// 0 = fp32 CUDA-core kernels only (XTB_TC=0 in the environment, or xtb_set_tc_mode).
+// ------------------------------------------------------------------------------------------
+static int g_tc_mode = [] { const char* e = getenv("XTB_TC"); return e ? atoi(e) : 1; }();
+extern "C" int xtb_set_tc_mode(int mode) { g_tc_mode = mode; return XTB_OK; }
+extern "C" int xtb_get_tc_mode(void) { return g_tc_mode; }
+
+static inline bp::BpT out_bp(const xtb_net* n, int t) { return bp::BpT{(bp::bf16*)(n->ws + n->obp_off[t]), n->plane_elems[t], n->pitch}; }
+static inline bp::BpT gout_bp(const xtb_net* n, int t) { return bp::BpT{(bp::bf16*)(n->ws + n->gbp_off[t]), n->plane_elems[t], n->pitch}; }
+static inline bp::BpT obs_bp(const xtb_net* n) { return bp::BpT{(bp::bf16*)(n->ws + n->obs_bp_off), 0, n->pitch}; }
+static inline bp::BpT no_bp() { return bp::BpT{nullptr, 0, 0}; }
+static inline const bp::bf16* blob_hi(const xtb_net* n, const LayerPlan& lp) { return (const bp::bf16*)(n->ws + n->blob_off) + lp.blob_off; }
+static inline bool use_tc(const LayerPlan& lp) { return g_tc_mode && lp.tc; }
+
+static int pick_tile(int n) { return n % 64 == 0 ? 64 : (n % 32 == 0 ? 32 : (n % 16 == 0 ? 16 : 0)); }
+
 extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net** out) {
   if (!desc || !out || max_batch <= 0) return fail(XTB_ERR_ARG, "xtb_net_create: null/invalid argument");
   if (desc->n_layers <= 0 || desc->n_layers > XTB_MAX_LAYERS) return fail(XTB_ERR_ARG, "n_layers out of range");
   auto* net = new xtb_net();
   net->desc = *desc;
   net->max_batch = max_batch;
+  net->pitch = (max_batch + 15) / 16 * 16;
   struct Shape { int h, w, c; };
   std::vector<Shape> shp(desc->n_layers + 1);
   std::vector<int> tact(desc->n_layers + 1, 0);
@@ -134,7 +168,7 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
       // HWC-flattened input with the identical [kh*kw*cin, cout] weight matrix
       lp.d.kind = XTB_DENSE;
     }
-    if (d.kind == XTB_CONV) {
+    if (lp.d.kind == XTB_CONV) {
       if (d.stride != 1 && d.stride != 2 && d.stride != 4) { delete net; return fail(XTB_ERR_ARG, "layer %d: stride must be 1,2,4", i); }
       ConvGeom& g = lp.g;
       g.H = is.h; g.W = is.w; g.C = is.c; g.KH = g.KW = d.k; g.S = d.stride; g.Cout = d.cout;
@@ -148,19 +182,10 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
       if (g.OH <= 0 || g.OW <= 0) { delete net; return fail(XTB_ERR_ARG, "layer %d: empty conv output", i); }
       g.K = d.k * d.k * g.C; g.P = g.OH * g.OW;
       g.mP = fastdiv_magic(g.P); g.mOW = fastdiv_magic(g.OW); g.mHW = fastdiv_magic(g.H * g.W); g.mW = fastdiv_magic(g.W);
-      {
-        // exact range of the fast division used by the tensor-core gathers: numerator < 2^24, divisor < 2^16
-        long long rows = (long long)max_batch * std::max(g.P, d.src != 0 ? g.H * g.W : 0);
-        if (rows >= (1LL << 24) || g.P >= (1 << 16) || g.H * g.W >= (1 << 16)) {
-          delete net;
-          return fail(XTB_ERR_ARG, "layer %d: max_batch*positions (%lld) exceeds 2^24 -- lower max_batch", i, rows);
-        }
-      }
       lp.K = g.K; lp.N = d.cout; lp.Kd = d.k * d.k * d.cout;
       lp.sshift = d.stride == 1 ? 0 : (d.stride == 2 ? 1 : 2);
-      for (int sft = 0; sft < 12; sft++) { if ((1 << sft) == g.C) lp.cshift = sft; if ((1 << sft) == d.cout) lp.oshift = sft; }
       shp[i + 1] = {g.OH, g.OW, d.cout};
-      // tables
+      // tables (fp32 path)
       std::vector<int> koff(g.K), kyx(g.K), dkyx(lp.Kd), dco(lp.Kd), wk(lp.Kd);
       for (int ky = 0; ky < d.k; ky++)
         for (int kx = 0; kx < d.k; kx++) {
@@ -188,16 +213,36 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
         delete net;
         return fail(XTB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
       }
-      if (d.src == 0 && desc->input_u8 && !d.pad_same && g.C == 4 && d.stride == 4 && d.k % 4 == 0 && g.H % 4 == 0 && g.W % 4 == 0) {
-        lp.s2d = true;
-        ConvGeom& q = lp.g2;
-        q = g;
-        q.H = g.H / 4; q.W = g.W / 4; q.C = 64; q.KH = q.KW = d.k / 4; q.S = 1;
-        q.mHW = fastdiv_magic(q.H * q.W); q.mW = fastdiv_magic(q.W);
+      // ---- tensor-core plan
+      lp.q = g;
+      const bool cout_ok = d.cout % 16 == 0 && d.cout <= 64;
+      if (d.src == 0) {
+        // uint8 frames, 4 channels, stride 4: space-to-depth canvas [OH+k/4-1, OW+k/4-1] blocks of 64 features
+        if (desc->input_u8 && g.C == 4 && d.stride == 4 && d.k % 4 == 0 && g.padL % 2 == 0 && g.W % 4 == 0 && cout_ok) {
+          lp.tc = lp.s2d = true;
+          lp.k4 = d.k / 4;
+          ConvGeom& q = lp.q;
+          q.H = g.OH + lp.k4 - 1; q.W = g.OW + lp.k4 - 1; q.C = 64; q.KH = q.KW = lp.k4; q.S = 1; q.padT = q.padL = 0;
+        }
+      } else if (g.C % 16 == 0 && g.C <= 64 && cout_ok && d.stride <= d.k) {
+        lp.tc = true;
       }
-    } else if (d.kind == XTB_DENSE) {
+      if (lp.tc) {
+        const ConvGeom& q = lp.q;
+        lp.n_fwd = d.cout; lp.n_dg = q.C;
+        lp.run_chunks = q.KW * q.C / 8;
+        lp.mts = (lp.run_chunks + 15) / 16;
+        lp.R = q.KH * lp.mts;
+        if (lp.R > 32 || lp.R * d.cout > 512) lp.tc = lp.s2d = false;
+        lp.w_res = (long long)lp.K * lp.N * 4 <= 96 * 1024;
+      }
+    } else if (lp.d.kind == XTB_DENSE) {
       lp.K = lp.in_size; lp.N = d.cout;
       shp[i + 1] = {1, 1, d.cout};
+      if (d.src != 0 && lp.K % 16 == 0 && pick_tile(lp.N) && pick_tile(lp.K)) {
+        lp.tc = true;
+        lp.n_fwd = pick_tile(lp.N); lp.n_dg = pick_tile(lp.K);
+      }
     } else {
       delete net;
       return fail(XTB_ERR_ARG, "layer %d: unknown kind %d", i, d.kind);
@@ -211,33 +256,67 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
     net->L.push_back(lp);
   }
   net->n_params = off;
-  {   // one observation plane serves every first layer: space-to-depth only when all tensor-core first layers use it
-    bool any = false, all = true;
-    for (const auto& lp : net->L) if (lp.d.src == 0 && lp.d.kind == XTB_CONV) { any = true; all = all && lp.s2d; }
-    net->s2d = any && all;
-    if (!net->s2d) for (auto& lp : net->L) lp.s2d = false;
+  {   // one observation canvas serves every tensor-core first layer: they must agree on its geometry
+    const LayerPlan* f = nullptr; bool agree = true;
+    for (auto& lp : net->L) if (lp.s2d) {
+      if (!f) f = &lp;
+      else if (f->q.H != lp.q.H || f->q.W != lp.q.W || f->g.padT != lp.g.padT || f->g.padL != lp.g.padL) agree = false;
+    }
+    if (!agree) { for (auto& lp : net->L) if (lp.s2d) lp.tc = lp.s2d = false; f = nullptr; }
+    if (f) { net->H4 = f->q.H; net->W4 = f->q.W; }
+    net->obs_feats = net->H4 * net->W4 * 64;
   }
+  // a tensor-core layer reads its source in batch-planar form: features must come in chunks of 8 (always true for
+  // the shapes accepted above; a dense layer after an uncovered odd-width layer falls back)
+  for (auto& lp : net->L) if (lp.tc && lp.d.src != 0 && net->tsize[lp.d.src] % 8) lp.tc = false;
   // workspace
   size_t w = 0;
-  net->out_off.assign(desc->n_layers + 1, 0);
-  net->gout_off.assign(desc->n_layers + 1, 0);
-  net->ohi_off.assign(desc->n_layers + 1, 0);
-  net->ghi_off.assign(desc->n_layers + 1, 0);
-  net->plane_elems.assign(desc->n_layers + 1, 0);
-  for (int t = 1; t <= desc->n_layers; t++) {
+  const int nt = desc->n_layers + 1;
+  net->out_off.assign(nt, 0); net->gout_off.assign(nt, 0);
+  net->obp_off.assign(nt, 0); net->gbp_off.assign(nt, 0);
+  net->plane_elems.assign(nt, 0);
+  for (int t = 1; t < nt; t++) {
     size_t bytes = align_up((size_t)max_batch * net->tsize[t] * sizeof(float), 256);
     net->out_off[t] = w; w += bytes;
     net->gout_off[t] = w; w += bytes;
-    long long pe = (long long)align_up((size_t)max_batch * net->tsize[t], 128);
-    net->plane_elems[t] = pe;
-    size_t pbytes = align_up((size_t)pe * 2 * sizeof(uint16_t), 256);   // hi + lo
-    net->ohi_off[t] = w; w += pbytes;
-    net->ghi_off[t] = w; w += pbytes;
+    if (net->tsize[t] % 8 == 0) {
+      long long pe = (long long)net->tsize[t] * net->pitch;
+      net->plane_elems[t] = pe;
+      size_t pbytes = align_up((size_t)pe * 2 * sizeof(uint16_t), 256);   // hi + lo
+      net->obp_off[t] = w; w += pbytes;
+      net->gbp_off[t] = w; w += pbytes;
+    }
   }
-  net->obs_hi_off = w; w += align_up((size_t)max_batch * net->tsize[0] * sizeof(uint16_t), 256);
-  net->w_plane_elems = (long long)align_up((size_t)net->n_params, 128);
-  net->w_hi_off = w; w += align_up((size_t)net->w_plane_elems * 2 * sizeof(uint16_t), 256);
+  net->obs_bp_off = w; w += align_up((size_t)net->obs_feats * net->pitch * sizeof(uint16_t) + 256, 256);
+  long long be = 0;
+  for (auto& lp : net->L) if (lp.tc) {
+    net->any_tc = true;
+    lp.blob_off = be; be += (long long)lp.K * lp.N;
+    net->blob_segs.push_back(bp::BlobSeg{lp.w_off, lp.blob_off, lp.K, lp.N, lp.s2d ? lp.k4 : 0});
+  }
+  net->blob_elems = (long long)align_up((size_t)be, 128);
+  net->blob_off = w; w += align_up((size_t)net->blob_elems * 2 * sizeof(uint16_t), 256);
+  for (auto& lp : net->L) if (lp.tc) {
+    if (lp.d.kind == XTB_CONV) {
+      lp.part_off = w; w += align_up((size_t)kSMs * lp.R * 128 * lp.N * sizeof(float), 256);
+    } else {
+    }
+    lp.dbpart_off = w; w += align_up((size_t)kSMs * 64 * sizeof(float), 256);
+  }
+  // split-K partial sums of a dense forward: n_z slabs of [round16(B)][N] with n_z <= 148 / (N tiles * batch tiles) + 1
+  net->splitk_off = w;
+  {
+    size_t need = 0;
+    for (auto& lp : net->L) if (lp.tc && lp.d.kind == XTB_DENSE) {
+      size_t rows = (size_t)(kSMs / (lp.N / lp.n_fwd) + 1) * 128 + net->pitch;
+      need = std::max(need, rows * lp.N * sizeof(float));
+    }
+    w += align_up(need + 256, 256);
+  }
+  net->zeros_off = w; w += 4096;
+  net->segs_off = w; w += align_up(sizeof(bp::BlobSeg) * XTB_MAX_LAYERS, 256);
   net->ws_bytes = w;
+  net->f32_ok.assign(nt, 0); net->bp_ok.assign(nt, 0); net->gf32_ok.assign(nt, 0); net->gbp_ok.assign(nt, 0);
   *out = net;
   return XTB_OK;
 }
@@ -272,12 +351,31 @@ extern "C" int xtb_net_tensor_size(const xtb_net* net, int t) {
 
 extern "C" size_t xtb_net_workspace_bytes(const xtb_net* net) { return net ? net->ws_bytes : 0; }
 
+static cudaError_t ensure_kernel_attrs();
 extern "C" int xtb_net_sync_weights(xtb_net* net, void* stream);
-extern "C" int xtb_net_bind(xtb_net* net, float* params, float* grads, void* workspace, size_t workspace_bytes) {
+extern "C" int xtb_net_bind_stream(xtb_net* net, float* params, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
   if (!net || !params || !workspace) return fail(XTB_ERR_ARG, "xtb_net_bind: null pointer");
   if (workspace_bytes < net->ws_bytes) return fail(XTB_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, net->ws_bytes);
   net->params = params; net->grads = grads; net->ws = (char*)workspace;
-  return xtb_net_sync_weights(net, nullptr);
+  cudaStream_t st = S(stream);
+  { cudaError_t ea = ensure_kernel_attrs(); if (ea != cudaSuccess) return fail(XTB_ERR_CUDA, "kernel attributes: %s", cudaGetErrorString(ea)); }
+  // Planes start as zeros: rows beyond the current batch are read (never used) by full-tile operand copies and
+  // must be finite; the zero buffer feeds out-of-image chunks of padded weight-gradient operands.
+  CUDA_TRY(cudaMemsetAsync(net->ws, 0, net->ws_bytes, st));
+  if (!net->blob_segs.empty())
+    CUDA_TRY(cudaMemcpyAsync(net->ws + net->segs_off, net->blob_segs.data(), net->blob_segs.size() * sizeof(bp::BlobSeg),
+                             cudaMemcpyHostToDevice, st));
+  std::fill(net->f32_ok.begin(), net->f32_ok.end(), 0); std::fill(net->bp_ok.begin(), net->bp_ok.end(), 0);
+  std::fill(net->gf32_ok.begin(), net->gf32_ok.end(), 0); std::fill(net->gbp_ok.begin(), net->gbp_ok.end(), 0);
+  net->obs_bp_ok = false;
+  int rc = xtb_net_sync_weights(net, stream);
+  if (rc) return rc;
+  // the segment table came from pageable host memory of this call: do not return before it is on the device
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return XTB_OK;
+}
+extern "C" int xtb_net_bind(xtb_net* net, float* params, float* grads, void* workspace, size_t workspace_bytes) {
+  return xtb_net_bind_stream(net, params, grads, workspace, workspace_bytes, nullptr);
 }
 
 extern "C" float* xtb_net_tensor(xtb_net* net, int t) {
@@ -290,10 +388,8 @@ extern "C" float* xtb_net_tensor_grad(xtb_net* net, int t) {
 }
 
 // ------------------------------------------------------------------------------------------
-// GEMM dispatch
+// fp32 GEMM dispatch
 // ------------------------------------------------------------------------------------------
-static const int kSMs = 148;
-
 template <int BM, int BN, int TM, int TN, class AL, class BL, class EP>
 static void launch_cfg(const AL& al, const BL& bl, const EP& ep, int M, int N, int K, int ksplit, cudaStream_t st) {
   constexpr int BK = 16;
@@ -328,217 +424,286 @@ static void launch_gemm(const AL& al, const BL& bl, const EP& ep, int M, int N, 
   launch_cfg<32, 32, 2, 2>(al, bl, ep, M, N, K, 1, st);
 }
 
-
 // ------------------------------------------------------------------------------------------
-// tcgen05 path (gemm_tc.cuh).  g_tc_mode: 1 = use tensor cores where the shape is covered,
-// 0 = fp32 CUDA-core kernels only (XTB_TC=0 in the environment, or xtb_set_tc_mode).
+// tensor-core launches
 // ------------------------------------------------------------------------------------------
-static int g_tc_mode = [] { const char* e = getenv("XTB_TC"); return e ? atoi(e) : 1; }();
-extern "C" int xtb_set_tc_mode(int mode) { g_tc_mode = mode; return XTB_OK; }
-extern "C" int xtb_get_tc_mode(void) { return g_tc_mode; }
+static int tmem_cols_for(int cols) { int c = 32; while (c < cols) c <<= 1; return c; }
 
-struct Planes { tc::bf16* hi; long long lo_off; };   // lo plane = hi + lo_off (elements)
-static inline Planes out_planes(const xtb_net* n, int t) { return Planes{(tc::bf16*)(n->ws + n->ohi_off[t]), n->plane_elems[t]}; }
-static inline Planes gout_planes(const xtb_net* n, int t) { return Planes{(tc::bf16*)(n->ws + n->ghi_off[t]), n->plane_elems[t]}; }
-static inline Planes obs_planes(const xtb_net* n) { return Planes{(tc::bf16*)(n->ws + n->obs_hi_off), 0}; }
-static inline Planes w_planes(const xtb_net* n) { return Planes{(tc::bf16*)(n->ws + n->w_hi_off), n->w_plane_elems}; }
+// opt-in to the large dynamic shared-memory carve-out, once per process and outside any stream capture
+static cudaError_t ensure_kernel_attrs() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(bp::bp_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(bp::bp_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(bp::bp_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(bp::bp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+  done = true;
+  return cudaSuccess;
+}
 
-// bias + activation after a split-K forward (fp32 sums are already in `out`), planes kept current
-__global__ void bias_act_kernel(float* __restrict__ out, const float* __restrict__ bias, long long total, int N,
-                                float alpha, int act, tc::bf16* hi, long long lo_off) {
-  pdl_wait(); pdl_trigger();
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) {
-    float r = act_apply(act, alpha * out[i] + bias[i % N]);
-    out[i] = r;
-    tc::store_plane1(hi, lo_off, i, r);
+template <int KIND>
+static cudaError_t launch_rows(bp::RowsArgs& a, cudaStream_t st) {
+  auto kern = bp::bp_rows_kernel<KIND>;
+  { cudaError_t e0 = ensure_kernel_attrs(); if (e0 != cudaSuccess) return e0; }
+  const int wres_bytes = a.w_res ? (int)align_up((size_t)2 * a.w_res_chunks * a.w_pitch * 16, 128) : 0;
+  const int stage_bytes = bp::RW_STAGE_A + (a.w_res ? 0 : bp::RW_STAGE_B);
+  int n_stages = std::min(bp::RW_MAX_STAGES, (kMaxDynSmem - 128 - wres_bytes) / stage_bytes);
+  if (n_stages < 2) return cudaErrorInvalidConfiguration;
+  const int smem = 128 + wres_bytes + n_stages * stage_bytes;
+  const int acc = (KIND == 2 ? a.N : 2 * a.N);
+  const int total = a.n_units * a.n_btiles;
+  const int grid = std::min(total, kSMs);
+  XLAUNCH(kern, grid, bp::RW_THREADS, smem, st, a, n_stages, stage_bytes, wres_bytes, tmem_cols_for(2 * acc));
+  return cudaPeekAtLastError();
+}
+
+static cudaError_t launch_wgrad(const bp::WgradArgs& a, int grid, cudaStream_t st) {
+  { cudaError_t e0 = ensure_kernel_attrs(); if (e0 != cudaSuccess) return e0; }
+  const int smem = 128 + bp::WG_STAGES * bp::WG_STAGE;
+  const int cols = (a.mode == 0 ? a.R : 1) * a.N;
+  XLAUNCH(bp::bp_wgrad_kernel, grid, bp::RW_THREADS, smem, st, a, tmem_cols_for(cols));
+  return cudaPeekAtLastError();
+}
+
+static void fill_conv_geom(bp::RowsArgs& a, const ConvGeom& q, int cout) {
+  a.H = q.H; a.W = q.W; a.C = q.C; a.OH = q.OH; a.OW = q.OW; a.Cout = cout; a.KH = q.KH; a.KW = q.KW; a.S = q.S;
+  a.padT = q.padT; a.padL = q.padL;
+}
+
+// forward of a tensor-core layer.  want_f32: also store the fp32 row-major copy; want_bp: store the planes
+static cudaError_t tc_forward(xtb_net* net, int i, int B, bool want_f32, bool want_bp, cudaStream_t st, long long* launches) {
+  const LayerPlan& lp = net->L[i];
+  const int t = i + 1;
+  bp::RowsArgs a;
+  memset(&a, 0, sizeof a);
+  a.a = lp.d.src == 0 ? obs_bp(net) : out_bp(net, lp.d.src);
+  a.a_split = lp.d.src != 0;
+  a.w_hi = blob_hi(net, lp); a.w_lo = a.w_hi + net->blob_elems; a.w_pitch = lp.K;
+  a.B = B; a.n_btiles = (B + 127) / 128; a.N = lp.n_fwd;
+  a.out = want_bp ? out_bp(net, t) : no_bp();
+  a.out_f32 = want_f32 ? (float*)(net->ws + net->out_off[t]) : nullptr;
+  a.ld_f32 = net->tsize[t];
+  a.bias = net->params + lp.b_off;
+  a.alpha = lp.d.src == 0 ? net->desc.scale : 1.f;
+  a.act = lp.d.act;
+  *launches = 1;
+  if (lp.d.kind == XTB_CONV) {
+    a.mode = 0;
+    fill_conv_geom(a, lp.q, lp.N);
+    a.w_res = lp.w_res; a.w_res_chunks = lp.N / 8;
+    a.n_units = lp.q.OH * lp.q.OW;
+    return launch_rows<0>(a, st);
   }
-}
-
-// first-layer convs read the decoded uint8 frames: 2 taps per 16-byte chunk need even geometry
-static bool tc_conv_ok(const xtb_net* net, const LayerPlan& lp) {
-  // K/8 column groups of a tile are cached in shared memory (TC_MAXCOLS); forward epilogues cannot split K
-  if (!g_tc_mode || lp.d.kind != XTB_CONV || lp.N % 8 || lp.N > 64 || lp.K % 8 || lp.K / 8 > tc::TC_MAXCOLS) return false;
-  if (lp.d.src == 0) {
-    if (!net->desc.input_u8 || lp.cshift != 2) return false;
-    return lp.g.KW % 2 == 0 && lp.g.padL % 2 == 0 && lp.g.S % 2 == 0 && lp.g.W % 2 == 0;
+  a.mode = 2;
+  a.kchunks = lp.K / 8; a.n_ntiles = lp.N / lp.n_fwd;
+  const int tiles = a.n_ntiles * a.n_btiles;
+  int nz = 1;
+  a.kc_split = a.kchunks;
+  if (tiles < kSMs && a.kchunks >= 32) {
+    int want = std::min((kSMs + tiles - 1) / tiles, a.kchunks / 8);
+    if (want > 1) {
+      a.kc_split = ((a.kchunks + want - 1) / want + 7) / 8 * 8;     // whole 64-element stages per split
+      nz = (a.kchunks + a.kc_split - 1) / a.kc_split;
+    }
   }
-  return lp.cshift >= 3;
-}
-static bool tc_dense_ok(const LayerPlan& lp) {
-  return g_tc_mode && lp.d.kind == XTB_DENSE && lp.d.src != 0 && lp.K % 8 == 0 && lp.N % 8 == 0 && lp.K >= 64 && lp.N >= 16;
-}
-static bool tc_conv_dgrad_ok(const LayerPlan& lp) {
-  if (!(g_tc_mode && lp.d.kind == XTB_CONV && lp.d.src != 0 && lp.g.C % 8 == 0 && lp.g.C <= 64 && lp.oshift >= 3)) return false;
-  const bool cls = lp.g.S > 1 && lp.g.KH % lp.g.S == 0 && lp.g.KW % lp.g.S == 0;
-  return (cls ? lp.Kd / (lp.g.S * lp.g.S) : lp.Kd) / 8 <= tc::TC_MAXCOLS;
+  a.n_units = a.n_ntiles * nz;
+  if (nz == 1) return launch_rows<0>(a, st);
+  a.part = (float*)(net->ws + net->splitk_off);
+  const int b_pad = (B + 15) & ~15;
+  a.part_z = (long long)b_pad * lp.N; a.ld_part = lp.N;
+  cudaError_t e = launch_rows<1>(a, st);
+  if (e != cudaSuccess) return e;
+  long long pieces = (long long)(lp.N / 8) * b_pad;
+  XLAUNCH(bp::bp_splitk_finish_kernel, (unsigned)((pieces + 127) / 128), 128, 0, st, (const float*)a.part, nz, a.part_z, B, lp.N,
+          a.bias, lp.d.act, a.out_f32, a.out);
+  *launches = 2;
+  return cudaPeekAtLastError();
 }
 
-template <bool PAD>
-static cudaError_t tc_conv_fwd_t(const LayerPlan& lp, Planes x, bool x_split, Planes w, const float* b, float alpha,
-                                 float* out, Planes po, int B, cudaStream_t st) {
-  int M = B * lp.g.P;
-  // first layer over a space-to-depth observation plane: k/4 x k/4 stride-1 conv over 64 channels, weight rows permuted
-  const bool s2d = lp.s2d && !x_split;
-  tc::SrcIm2col<PAD> a{x.hi, x.lo_off, s2d ? lp.g2 : lp.g, s2d ? 6 : lp.cshift, M};
-  tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K, s2d ? lp.g2.KH : 0};
-  tc::TcEpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, M, lp.N, po.hi, po.lo_off};
-  if (x_split) {
-    if (lp.N <= 16) return tc::launch_tc<16, 64, false, true, true, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
-    if (lp.N <= 32) return tc::launch_tc<32, 64, false, true, true, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
-    return tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+// data gradient of tensor-core layer i into the planes of its source tensor
+static cudaError_t tc_dgrad(xtb_net* net, int i, int B, int accumulate, float* db_part, cudaStream_t st) {
+  const LayerPlan& lp = net->L[i];
+  const int t = i + 1, s = lp.d.src;
+  bp::RowsArgs a;
+  memset(&a, 0, sizeof a);
+  a.a = gout_bp(net, t); a.a_split = 1;
+  a.w_hi = blob_hi(net, lp); a.w_lo = a.w_hi + net->blob_elems; a.w_pitch = lp.K;
+  a.B = B; a.n_btiles = (B + 127) / 128; a.N = lp.n_dg;
+  a.out = gout_bp(net, s); a.src = out_bp(net, s); a.src_act = lp.src_act; a.accumulate = accumulate; a.db_part = db_part;
+  if (lp.d.kind == XTB_CONV) {
+    a.mode = 1;
+    fill_conv_geom(a, lp.q, lp.N);
+    a.w_res = lp.w_res; a.w_res_chunks = lp.N / 8;
+    a.n_units = lp.q.H * lp.q.W;
+  } else {
+    a.mode = 2;
+    a.kchunks = lp.N / 8; a.kc_split = a.kchunks; a.n_ntiles = lp.K / lp.n_dg;
+    a.n_units = a.n_ntiles;
   }
-  if (lp.N <= 16) return tc::launch_tc<16, 64, false, true, false, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
-  if (lp.N <= 32) return tc::launch_tc<32, 64, false, true, false, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
-  return tc::launch_tc<64, 64, false, true, false, true>(a, bs, ep, M, lp.N, lp.K, 1, st);
+  return launch_rows<2>(a, st);
 }
 
-static cudaError_t tc_dense_fwd(const LayerPlan& lp, Planes x, Planes w, const float* b, float* out, Planes po, int B,
-                                cudaStream_t st) {
-  tc::SrcDense a{x.hi, x.lo_off, nullptr, lp.K, B};
-  tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K};
-  long long ctas = (long long)((B + 127) / 128) * ((lp.N + 63) / 64);
-  int ks = lp.K >= 1024 ? tc::pick_ksplit(ctas, lp.K, 64, 148) : 1;
-  if (ks > 1) {   // split-K: atomics into a zeroed buffer, then bias + activation (+ planes) in place
-    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * lp.N * sizeof(float), st);
-    if (e != cudaSuccess) return e;
-    tc::TcEpiAtomic ep{out, 1.f, lp.N, B, lp.N, 0};
-    e = tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, ks, st);
-    if (e != cudaSuccess) return e;
-    long long total = (long long)B * lp.N;
-    XLAUNCH(bias_act_kernel, (unsigned)((total + 255) / 256), 256, 0, st, out, b, total, lp.N, 1.f, lp.d.act, po.hi, po.lo_off);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaPeekAtLastError();
+// weight gradient of tensor-core layer i; conv layers queue their ordered reduction
+static cudaError_t tc_wgrad(xtb_net* net, int i, int B, cudaStream_t st) {
+  LayerPlan& lp = net->L[i];
+  const int t = i + 1;
+  bp::WgradArgs a;
+  memset(&a, 0, sizeof a);
+  a.x = lp.d.src == 0 ? obs_bp(net) : out_bp(net, lp.d.src);
+  a.x_split = lp.d.src != 0;
+  a.g = gout_bp(net, t);
+  a.zeros = (const bp::bf16*)(net->ws + net->zeros_off);
+  a.B = B; a.n_bsub = (B + bp::WG_KB - 1) / bp::WG_KB;
+  if (lp.d.kind == XTB_CONV) {
+    const ConvGeom& q = lp.q;
+    a.mode = 0;
+    a.H = q.H; a.W = q.W; a.C = q.C; a.OH = q.OH; a.OW = q.OW; a.KH = q.KH; a.KW = q.KW; a.S = q.S; a.padT = q.padT; a.padL = q.padL;
+    a.run_chunks = lp.run_chunks; a.mts = lp.mts; a.R = lp.R; a.N = lp.N; a.n_opix = q.OH * q.OW;
+    a.part = (float*)(net->ws + lp.part_off);
+    const int grid = std::min(kSMs, a.n_opix * a.n_bsub);
+    bp::RedSeg r;
+    memset(&r, 0, sizeof r);
+    r.part = a.part; r.n_slabs = grid; r.slab = (long long)lp.R * 128 * lp.N; r.count = lp.R * 128 * lp.N; r.kind = 0;
+    r.N = lp.N; r.C = q.C; r.KW = q.KW; r.mts = lp.mts; r.s2d_k4 = lp.s2d ? lp.k4 : 0;
+    r.dst_off = lp.w_off; r.alpha = lp.d.src == 0 ? net->desc.scale : 1.f;
+    net->pending.push_back(r);
+    return launch_wgrad(a, grid, st);
   }
-  tc::TcEpiBiasAct ep{out, b, 1.f, lp.d.act, lp.N, B, lp.N, po.hi, po.lo_off};
-  return tc::launch_tc<64, 64, false, true, true, true>(a, bs, ep, B, lp.N, lp.K, 1, st);
+  a.mode = 1;
+  a.N = std::min(lp.n_fwd, 64);
+  a.x_chunks = lp.K / 8; a.r_tiles = (lp.K + 127) / 128; a.n_ntiles = lp.N / a.N; a.n_opix = 1; a.R = 1;
+  a.dw = net->grads + lp.w_off; a.ldw = lp.N; a.k_rows = lp.K;
+  return launch_wgrad(a, std::min(kSMs, a.r_tiles * a.n_ntiles), st);
 }
 
-template <bool PAD>
-static cudaError_t tc_conv_wgrad_t(const LayerPlan& lp, Planes x, bool x_split, Planes dy, float alpha, float* dw, int B,
-                                   cudaStream_t st) {
-  int Mr = B * lp.g.P;
-  const bool s2d = lp.s2d && !x_split;
-  tc::SrcIm2col<PAD> a{x.hi, x.lo_off, s2d ? lp.g2 : lp.g, s2d ? 6 : lp.cshift, Mr};
-  tc::SrcDense bs{dy.hi, dy.lo_off, nullptr, lp.N, Mr};
-  tc::TcEpiAtomic ep{dw, alpha, lp.N, lp.K, lp.N, s2d ? lp.g2.KH : 0};
-  long long ctas = (long long)((lp.K + 127) / 128);
-  int ks = tc::pick_ksplit(ctas, Mr, 64, 148);
-  if (x_split) {
-    if (lp.N <= 16) return tc::launch_tc<16, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
-    if (lp.N <= 32) return tc::launch_tc<32, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
-    return tc::launch_tc<64, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
-  }
-  if (lp.N <= 16) return tc::launch_tc<16, 64, true, true, false, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
-  if (lp.N <= 32) return tc::launch_tc<32, 64, true, true, false, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
-  return tc::launch_tc<64, 64, true, true, false, true>(a, bs, ep, lp.K, lp.N, Mr, ks, st);
-}
-
-static cudaError_t tc_dense_wgrad(const LayerPlan& lp, Planes x, Planes dy, float* dw, int B, cudaStream_t st) {
-  tc::SrcDense a{x.hi, x.lo_off, nullptr, lp.K, B};
-  tc::SrcDense bs{dy.hi, dy.lo_off, nullptr, lp.N, B};
-  tc::TcEpiAtomic ep{dw, 1.f, lp.N, lp.K, lp.N, 0};
-  long long ctas = (long long)((lp.K + 127) / 128) * ((lp.N + 63) / 64);
-  int ks = tc::pick_ksplit(ctas, B, 64, 148);
-  return tc::launch_tc<64, 64, true, true, true, true>(a, bs, ep, lp.K, lp.N, B, ks, st);
-}
-
-static cudaError_t tc_conv_dgrad(const LayerPlan& lp, Planes dy, Planes w, float* gsrc, const float* xsrc, Planes pg, int acc,
-                                 float* db_src, int B, cudaStream_t st) {
-  const ConvGeom& g = lp.g;
-  if (g.S > 1 && g.KH % g.S == 0 && g.KW % g.S == 0) {
-    // strided transposed conv: one dense GEMM per parity class of the input position
-    int nY = (g.H + g.S - 1) / g.S, nX = (g.W + g.S - 1) / g.S;
-    tc::DgradClass k{fastdiv_magic(nY * nX), fastdiv_magic(nX), g.S, lp.sshift, g.padT, g.padL, g.H, g.W, nY, nX, 0, 0, 0, 0};
-    int M = B * k.nY * k.nX;
-    int Kc = lp.Kd / (g.S * g.S);
-    tc::SrcDgradS a{dy.hi, dy.lo_off, g, lp.oshift, M, k, g.KW / g.S};
-    tc::SrcWDgradS bs{w.hi + lp.w_off, w.lo_off, g.C, lp.N, lp.oshift, g.C, g.KW, g.KW / g.S, k};
-    tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, g.C, acc, M, g.C, pg.hi, pg.lo_off, db_src, 1, k};
-    int cls = g.S * g.S;
-    if (g.C <= 16) return tc::launch_tc<16, 64, false, false, true, true, tc::SrcDgradS, tc::SrcWDgradS, tc::TcEpiDgrad, true>(a, bs, ep, M, g.C, Kc, 1, st, cls);
-    if (g.C <= 32) return tc::launch_tc<32, 64, false, false, true, true, tc::SrcDgradS, tc::SrcWDgradS, tc::TcEpiDgrad, true>(a, bs, ep, M, g.C, Kc, 1, st, cls);
-    return tc::launch_tc<64, 64, false, false, true, true, tc::SrcDgradS, tc::SrcWDgradS, tc::TcEpiDgrad, true>(a, bs, ep, M, g.C, Kc, 1, st, cls);
-  }
-  int M = B * g.H * g.W;
-  tc::SrcDgrad a{dy.hi, dy.lo_off, g, lp.oshift, lp.sshift, M};
-  tc::SrcWDgrad bs{w.hi + lp.w_off, w.lo_off, g.C, lp.N, lp.oshift, g.C};
-  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, g.C, acc, M, g.C, pg.hi, pg.lo_off, db_src, 0, tc::DgradClass{}};
-  if (g.C <= 16) return tc::launch_tc<16, 64, false, false, true, true>(a, bs, ep, M, g.C, lp.Kd, 1, st);
-  if (g.C <= 32) return tc::launch_tc<32, 64, false, false, true, true>(a, bs, ep, M, g.C, lp.Kd, 1, st);
-  return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, M, g.C, lp.Kd, 1, st);
-}
-
-static cudaError_t tc_dense_dgrad(const LayerPlan& lp, Planes dy, Planes w, float* gsrc, const float* xsrc, Planes pg, int acc,
-                                  float* db_src, int B, cudaStream_t st) {
-  tc::SrcDense a{dy.hi, dy.lo_off, nullptr, lp.N, B};
-  tc::SrcDense bs{w.hi + lp.w_off, w.lo_off, nullptr, lp.N, lp.K};          // rows = kw (N' entity), cols = n (K')
-  // the source of a dense layer may be a conv map [B, H*W*C]: its bias gradient is per channel, not per flattened
-  // unit, so the column-sum fusion only applies when the source layer is dense itself (db_src != NULL then)
-  tc::TcEpiDgrad ep{gsrc, xsrc, lp.src_act, lp.K, acc, B, lp.K, pg.hi, pg.lo_off, db_src, 0, tc::DgradClass{}};
-  return tc::launch_tc<64, 64, false, false, true, true>(a, bs, ep, B, lp.K, lp.N, 1, st);
-}
-
-// keep the bf16 hi/lo planes of the bound parameters current (after an optimiser step / set_weights)
+// keep the weight blobs of the bound parameters current (after an optimiser step / set_weights)
 extern "C" int xtb_net_sync_weights(xtb_net* net, void* stream) {
   if (!net || !net->ws || !net->params) return fail(XTB_ERR_STATE, "xtb_net_sync_weights: net not bound");
-  Planes w = w_planes(net);
-  long long n = net->n_params;
-  XLAUNCH(tc::split_planes_kernel, (unsigned)((n / 4 + 255) / 256 + 1), 256, 0, S(stream), net->params, w.hi, w.lo_off, n);
+  if (net->blob_segs.empty()) return XTB_OK;
+  long long mx = 0;
+  for (const auto& s : net->blob_segs) mx = std::max(mx, (long long)(s.N / 8) * s.K);
+  dim3 grid((unsigned)((mx + 127) / 128), (unsigned)net->blob_segs.size());
+  XLAUNCH(bp::bp_wprep_kernel, grid, 128, 0, S(stream), (const float*)net->params, (const bp::BlobSeg*)(net->ws + net->segs_off),
+          (bp::bf16*)(net->ws + net->blob_off), net->blob_elems);
   LAUNCH_CHECK();
   return XTB_OK;
 }
 
-#ifdef XTB_TC_TRACE
-extern "C" int xtb_tc_trace_set(unsigned long long* buf) {
-  CUDA_TRY(cudaMemcpyToSymbol(tc::g_tc_trace, &buf, sizeof buf));
+// ---- representation changes ------------------------------------------------------------------
+static int ensure_bp(xtb_net* net, int t, int B, bool grad, cudaStream_t st) {
+  std::vector<char>& ok = grad ? net->gbp_ok : net->bp_ok;
+  if (ok[t]) return XTB_OK;
+  const std::vector<char>& f = grad ? net->gf32_ok : net->f32_ok;
+  if (!f[t]) return fail(XTB_ERR_STATE, "tensor %d has no current %s", t, grad ? "gradient" : "value");
+  const float* src = (const float*)(net->ws + (grad ? net->gout_off[t] : net->out_off[t]));
+  const int F = net->tsize[t], b_pad = (B + 15) & ~15;
+  long long pieces = (long long)(F / 8) * b_pad;
+  XLAUNCH(bp::bp_split_kernel, (unsigned)((pieces + 127) / 128), 128, 0, st, src, B, F, grad ? gout_bp(net, t) : out_bp(net, t));
+  LAUNCH_CHECK();
+  ok[t] = 1;
   return XTB_OK;
 }
-#endif
-
-#ifdef XTB_TC_PROF
-extern "C" int xtb_tc_prof_set(long long* buf) {
-  CUDA_TRY(cudaMemcpyToSymbol(tc::g_tc_prof, &buf, sizeof buf));
+static int ensure_f32(xtb_net* net, int t, int B, bool grad, cudaStream_t st) {
+  std::vector<char>& ok = grad ? net->gf32_ok : net->f32_ok;
+  if (ok[t]) return XTB_OK;
+  const std::vector<char>& p = grad ? net->gbp_ok : net->bp_ok;
+  if (!p[t]) return fail(XTB_ERR_STATE, "tensor %d has no current %s", t, grad ? "gradient" : "value");
+  float* dst = (float*)(net->ws + (grad ? net->gout_off[t] : net->out_off[t]));
+  const int F = net->tsize[t];
+  long long pieces = (long long)(F / 8) * B;
+  XLAUNCH(bp::bp_merge_kernel, (unsigned)((pieces + 127) / 128), 128, 0, st, grad ? gout_bp(net, t) : out_bp(net, t), B, F, dst);
+  LAUNCH_CHECK();
+  ok[t] = 1;
   return XTB_OK;
 }
-#endif
 
-// Self-test of the three operand-major combinations on plain matrices (see tests/test_gpu_tc.py):
-//   mode 0: C[M,N] = A[M,K]   * B[K,N]      (A K-major, B MN-major : forward)
-//   mode 1: C[M,N] = A[M,K]   * Bt[N,K]^T   (both K-major         : data gradient)
-//   mode 2: C[M,N] = At[K,M]^T * B[K,N]     (both MN-major        : weight gradient)
+// Self-test of the three kernel forms on plain matrices (see tests/test_gpu_tc.py):
+//   mode 0: C[M,N] = A[M,K]   * B[K,N]      forward   (rows kernel, weights MN-major; ksplit > 1: split-K partials)
+//   mode 1: C[M,N] = A[M,K]   * Bt[N,K]^T   data grad (rows kernel, weights K-major)
+//   mode 2: C[M,N] = At[K,M]^T * B[K,N]     weight grad (samples = K are the reduction axis)
 extern "C" int xtb_tc_gemm_test(int mode, const float* a, const float* b, float* c, int M, int N, int K, int ksplit,
                                 void* stream) {
   if (!a || !b || !c || M <= 0 || N <= 0 || K <= 0) return fail(XTB_ERR_ARG, "xtb_tc_gemm_test: bad argument");
-  if (M % 8 || N % 8 || K % 8) return fail(XTB_ERR_ARG, "xtb_tc_gemm_test: sizes must be multiples of 8");
+  if (N % 16 || K % 16 || (mode == 2 && M % 16)) return fail(XTB_ERR_ARG, "xtb_tc_gemm_test: N, K (and M for mode 2) must be multiples of 16");
   cudaStream_t st = S(stream);
-  long long na = (long long)M * K, nb = (long long)N * K;
-  tc::bf16 *pa = nullptr, *pb = nullptr;
-  CUDA_TRY(cudaMalloc(&pa, 2 * na * sizeof(tc::bf16)));
-  CUDA_TRY(cudaMalloc(&pb, 2 * nb * sizeof(tc::bf16)));
-  XLAUNCH(tc::split_planes_kernel, (unsigned)((na / 4 + 255) / 256 + 1), 256, 0, st, a, pa, na, na);
-  XLAUNCH(tc::split_planes_kernel, (unsigned)((nb / 4 + 255) / 256 + 1), 256, 0, st, b, pb, nb, nb);
-  cudaError_t e;
-  tc::SrcDense as{pa, na, nullptr, mode == 2 ? M : K, mode == 2 ? K : M};
-  tc::SrcDense bs{pb, nb, nullptr, mode == 1 ? K : N, mode == 1 ? N : K};
-  if (ksplit > 1) {
-    CUDA_TRY(cudaMemsetAsync(c, 0, (size_t)M * N * sizeof(float), st));
-    tc::TcEpiAtomic ep{c, 1.f, N, M, N, 0};
-    if (mode == 0) e = tc::launch_tc<64, 64, false, true, true, true>(as, bs, ep, M, N, K, ksplit, st);
-    else if (mode == 1) e = tc::launch_tc<64, 64, false, false, true, true>(as, bs, ep, M, N, K, ksplit, st);
-    else e = tc::launch_tc<64, 64, true, true, true, true>(as, bs, ep, M, N, K, ksplit, st);
+  // rows (samples): mode 0/1 -> M rows of A; mode 2 -> K rows of At and B
+  const int rows = mode == 2 ? K : M;
+  const int pitch = (rows + 15) / 16 * 16;
+  const int fa = mode == 2 ? M : K;                 // features of the "activation" operand
+  const int fb = N;                                  // mode 2: features of B
+  const int nt = pick_tile(N);
+  if (!nt) return fail(XTB_ERR_ARG, "N must be a multiple of 16");
+  bp::bf16 *pa = nullptr, *pw = nullptr, *pc = nullptr; float* part = nullptr; float* bias = nullptr;
+  const long long ea = (long long)fa * pitch;
+  const long long ew = mode == 2 ? (long long)fb * pitch : (mode == 1 ? (long long)K * ((N + 15) / 16 * 16) : (long long)N * K);   // weight blob / second activation
+  const long long ec = (long long)N * pitch;
+  CUDA_TRY(cudaMalloc(&pa, 2 * ea * sizeof(bp::bf16)));
+  CUDA_TRY(cudaMalloc(&pw, 2 * ew * sizeof(bp::bf16) + 256));
+  CUDA_TRY(cudaMalloc(&pc, 2 * ec * sizeof(bp::bf16) + 4096));
+  CUDA_TRY(cudaMalloc(&bias, (size_t)std::max(N, 64) * sizeof(float)));
+  CUDA_TRY(cudaMemsetAsync(pa, 0, 2 * ea * sizeof(bp::bf16), st));
+  CUDA_TRY(cudaMemsetAsync(pw, 0, 2 * ew * sizeof(bp::bf16) + 256, st));
+  CUDA_TRY(cudaMemsetAsync(pc, 0, 2 * ec * sizeof(bp::bf16) + 4096, st));
+  CUDA_TRY(cudaMemsetAsync(bias, 0, (size_t)std::max(N, 64) * sizeof(float), st));
+  bp::BpT ta{pa, ea, pitch}, tw{pw, ew, mode == 2 ? pitch : K}, tcp{pc, ec, pitch};
+  auto split = [&](const float* src, int B_, int F_, bp::BpT dst) {
+    long long pieces = (long long)(F_ / 8) * ((B_ + 15) & ~15);
+    XLAUNCH(bp::bp_split_kernel, (unsigned)((pieces + 127) / 128), 128, 0, st, src, B_, F_, dst);
+  };
+  cudaError_t e = cudaSuccess;
+  int rc = XTB_OK;
+  if (mode == 0 || mode == 1) {
+    split(a, M, K, ta);
+    // weight blob = batch-planar W^T with rows k: mode 0: b = W[K][N] -> rows K, features N.  mode 1: b = Bt[N][K]: the
+    // kernel computes D[m, n] = sum_k A[m,k] Bt[n,k] with "W"[n][k] = Bt: rows = n (output), features = k (reduction)
+    if (mode == 0) { tw.pitch = K; split(b, K, N, tw); }
+    else { tw.pitch = (N + 15) / 16 * 16; split(b, N, K, tw); }
+    bp::RowsArgs r;
+    memset(&r, 0, sizeof r);
+    r.a = ta; r.a_split = 1; r.w_hi = pw; r.w_lo = pw + ew; r.w_pitch = tw.pitch;
+    r.mode = 2; r.B = M; r.n_btiles = (M + 127) / 128; r.N = nt; r.n_ntiles = N / nt;
+    r.kchunks = K / 8; r.kc_split = r.kchunks;
+    r.bias = bias; r.alpha = 1.f; r.act = 0;
+    if (mode == 0) {
+      int nz = 1;
+      if (ksplit > 1) { r.kc_split = ((r.kchunks + ksplit - 1) / ksplit + 7) / 8 * 8; nz = (r.kchunks + r.kc_split - 1) / r.kc_split; }
+      r.n_units = r.n_ntiles * nz;
+      if (nz > 1) {
+        CUDA_TRY(cudaMalloc(&part, (size_t)nz * M * N * sizeof(float)));
+        r.part = part; r.part_z = (long long)M * N; r.ld_part = N;
+        e = launch_rows<1>(r, st);
+        long long pieces = (long long)(N / 8) * ((M + 15) & ~15);
+        XLAUNCH(bp::bp_splitk_finish_kernel, (unsigned)((pieces + 127) / 128), 128, 0, st, (const float*)part, nz, r.part_z, M, N,
+                (const float*)bias, 0, c, no_bp());
+      } else {
+        r.out_f32 = c; r.ld_f32 = N;
+        e = launch_rows<0>(r, st);
+      }
+    } else {
+      r.n_units = r.n_ntiles;
+      r.out = tcp; r.src = tcp; r.src_act = 0;
+      e = launch_rows<2>(r, st);
+      long long pieces = (long long)(N / 8) * M;
+      XLAUNCH(bp::bp_merge_kernel, (unsigned)((pieces + 127) / 128), 128, 0, st, tcp, M, N, c);
+    }
   } else {
-    tc::TcEpiStore ep{c, N, M, N};
-    if (mode == 0) e = tc::launch_tc<32, 64, false, true, true, true>(as, bs, ep, M, N, K, 1, st);
-    else if (mode == 1) e = tc::launch_tc<32, 64, false, false, true, true>(as, bs, ep, M, N, K, 1, st);
-    else e = tc::launch_tc<32, 64, true, true, true, true>(as, bs, ep, M, N, K, 1, st);
+    split(a, K, M, ta);
+    split(b, K, N, tw);
+    bp::WgradArgs w;
+    memset(&w, 0, sizeof w);
+    w.x = ta; w.x_split = 1; w.g = tw; w.zeros = pc;
+    w.mode = 1; w.N = nt; w.B = K; w.n_bsub = (K + bp::WG_KB - 1) / bp::WG_KB; w.n_opix = 1; w.R = 1;
+    w.x_chunks = M / 8; w.r_tiles = (M + 127) / 128; w.n_ntiles = N / nt;
+    w.dw = c; w.ldw = N; w.k_rows = M;
+    e = launch_wgrad(w, std::min(kSMs, w.r_tiles * w.n_ntiles), st);
   }
-  g_launches.fetch_add(3, std::memory_order_relaxed);
+  g_launches.fetch_add(4, std::memory_order_relaxed);
   cudaError_t e2 = cudaStreamSynchronize(st);
-  cudaFree(pa); cudaFree(pb);
+  cudaFree(pa); cudaFree(pw); cudaFree(pc); cudaFree(bias); cudaFree(part);
   if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "tc gemm launch: %s", cudaGetErrorString(e));
   if (e2 != cudaSuccess) return fail(XTB_ERR_CUDA, "tc gemm run: %s", cudaGetErrorString(e2));
-  return XTB_OK;
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -546,19 +711,19 @@ extern "C" int xtb_tc_gemm_test(int mode, const float* a, const float* b, float*
 // ------------------------------------------------------------------------------------------
 template <typename T>
 static void conv_fwd(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
-                     float alpha, float* out, Planes po, int B, cudaStream_t st) {
+                     float alpha, float* out, int B, cudaStream_t st) {
   int M = B * lp.g.P;
   BRowMajor bl{w, lp.N};
-  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, po.hi, po.lo_off};
+  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, nullptr, 0};
   if (lp.pad) { AIm2col<T, true> al{x, idx, lp.g, lp.koff, lp.kyx}; launch_gemm(al, bl, ep, M, lp.N, lp.K, false, st); }
   else { AIm2col<T, false> al{x, idx, lp.g, lp.koff, lp.kyx}; launch_gemm(al, bl, ep, M, lp.N, lp.K, false, st); }
 }
 template <typename T>
 static void dense_fwd(const LayerPlan& lp, const T* x, const int32_t* idx, const float* w, const float* b,
-                      float alpha, float* out, Planes po, int B, cudaStream_t st) {
+                      float alpha, float* out, int B, cudaStream_t st) {
   ADense<T> al{x, idx, lp.K};
   BRowMajor bl{w, lp.N};
-  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, po.hi, po.lo_off};
+  EpiBiasAct ep{out, b, alpha, lp.d.act, lp.N, nullptr, 0};
   launch_gemm(al, bl, ep, B, lp.N, lp.K, false, st);
 }
 template <typename T>
@@ -603,103 +768,106 @@ __global__ void colsum_kernel(const float* __restrict__ dy, int M, int N, float*
 // ------------------------------------------------------------------------------------------
 // per-layer operations (tensor-core kernel when the shape is covered, fp32 kernel otherwise)
 // ------------------------------------------------------------------------------------------
-// forward of layer i; tc_allowed = parameters are the bound ones (their bf16 planes are current)
-static int op_forward(xtb_net* net, int i, const float* P, bool tc_allowed, const void* obs, const int32_t* idx, int B,
-                      cudaStream_t st) {
-  const LayerPlan& lp = net->L[i];
-  float* out = (float*)(net->ws + net->out_off[i + 1]);
-  Planes po = out_planes(net, i + 1);
-  const float* w = P + lp.w_off;
-  const float* b = P + lp.b_off;
-  cudaError_t te = cudaSuccess;
-  if (lp.d.src == 0) {
-    float alpha = net->desc.scale;
-    if (tc_allowed && tc_conv_ok(net, lp)) {
-      // the decoded frames of this minibatch are in the observation plane (op_decode ran before)
-      te = lp.pad ? tc_conv_fwd_t<true>(lp, obs_planes(net), false, w_planes(net), b, alpha, out, po, B, st)
-                  : tc_conv_fwd_t<false>(lp, obs_planes(net), false, w_planes(net), b, alpha, out, po, B, st);
-    } else if (net->desc.input_u8) {
-      if (lp.d.kind == XTB_CONV) conv_fwd<uint8_t>(lp, (const uint8_t*)obs, idx, w, b, alpha, out, po, B, st);
-      else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, idx, w, b, alpha, out, po, B, st);
-    } else {
-      if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, (const float*)obs, idx, w, b, alpha, out, po, B, st);
-      else dense_fwd<float>(lp, (const float*)obs, idx, w, b, alpha, out, po, B, st);
-    }
-  } else {
-    const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
-    Planes px = out_planes(net, lp.d.src);
-    if (lp.d.kind == XTB_CONV) {
-      if (tc_allowed && tc_conv_ok(net, lp))
-        te = lp.pad ? tc_conv_fwd_t<true>(lp, px, true, w_planes(net), b, 1.f, out, po, B, st)
-                    : tc_conv_fwd_t<false>(lp, px, true, w_planes(net), b, 1.f, out, po, B, st);
-      else conv_fwd<float>(lp, x, nullptr, w, b, 1.f, out, po, B, st);
-    } else {
-      if (tc_allowed && tc_dense_ok(lp)) te = tc_dense_fwd(lp, px, w_planes(net), b, out, po, B, st);
-      else dense_fwd<float>(lp, x, nullptr, w, b, 1.f, out, po, B, st);
-    }
-  }
-  if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 forward launch (layer %d): %s", i, cudaGetErrorString(te));
+// uint8 frame decode (+ minibatch gather) into the space-to-depth observation canvas
+static int op_decode(xtb_net* net, const void* obs, const int32_t* idx, int B, cudaStream_t st) {
+  if (net->obs_bp_ok) return XTB_OK;
+  const LayerPlan* first = nullptr;
+  for (const auto& lp : net->L) if (lp.s2d && use_tc(lp)) { first = &lp; break; }
+  if (!first) return XTB_OK;
+  dim3 grid(net->H4, (B + bp::DEC_SAMPLES - 1) / bp::DEC_SAMPLES);
+  const int smem = bp::DEC_SAMPLES * (4 * net->desc.in_w * 4 + 8);
+  XLAUNCH(bp::bp_decode_s2d_kernel, grid, bp::DEC_THREADS, smem, st, (const uint8_t*)obs, idx, B, net->desc.in_h, net->desc.in_w, net->H4,
+          net->W4, first->g.padT, first->g.padL, obs_bp(net));
   LAUNCH_CHECK();
+  net->obs_bp_ok = true;
   return XTB_OK;
 }
 
-// uint8 frame decode (+ minibatch gather) into the observation plane when a tensor-core first layer reads it
-static int op_decode(xtb_net* net, const void* obs, const int32_t* idx, int B, cudaStream_t st) {
-  bool need = false;
-  for (const auto& lp : net->L) if (lp.d.src == 0 && tc_conv_ok(net, lp)) need = true;
-  if (!need) return XTB_OK;
-  int per = net->tsize[0];
-  if (net->s2d) {
-    dim3 grid((per / 16 + 255) / 256, B);
-    XLAUNCH(tc::decode_u8_s2d_kernel, grid, 256, 0, st, (const uint8_t*)obs, idx, net->desc.in_h, net->desc.in_w, obs_planes(net).hi);
-    LAUNCH_CHECK();
+// forward of layer i; tc_allowed = parameters are the bound ones (their blobs are current)
+static int op_forward(xtb_net* net, int i, const float* P, bool tc_allowed, const void* obs, const int32_t* idx, int B,
+                      bool want_f32, cudaStream_t st) {
+  const LayerPlan& lp = net->L[i];
+  const int t = i + 1;
+  float* out = (float*)(net->ws + net->out_off[t]);
+  const float* w = P + lp.w_off;
+  const float* b = P + lp.b_off;
+  if (tc_allowed && use_tc(lp)) {
+    int rc = lp.d.src == 0 ? op_decode(net, obs, idx, B, st) : ensure_bp(net, lp.d.src, B, false, st);
+    if (rc) return rc;
+    long long nl = 0;
+    cudaError_t te = tc_forward(net, i, B, want_f32, true, st, &nl);
+    if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 forward launch (layer %d): %s", i, cudaGetErrorString(te));
+    g_launches.fetch_add(nl, std::memory_order_relaxed);
+    net->bp_ok[t] = 1; net->f32_ok[t] = want_f32 ? 1 : 0;
     return XTB_OK;
   }
-  dim3 grid((per / 16 + 255) / 256, B);
-  XLAUNCH(tc::decode_u8_kernel, grid, 256, 0, st, (const uint8_t*)obs, idx, per, obs_planes(net).hi);
+  if (lp.d.src == 0) {
+    float alpha = net->desc.scale;
+    if (net->desc.input_u8) {
+      if (lp.d.kind == XTB_CONV) conv_fwd<uint8_t>(lp, (const uint8_t*)obs, idx, w, b, alpha, out, B, st);
+      else dense_fwd<uint8_t>(lp, (const uint8_t*)obs, idx, w, b, alpha, out, B, st);
+    } else {
+      if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, (const float*)obs, idx, w, b, alpha, out, B, st);
+      else dense_fwd<float>(lp, (const float*)obs, idx, w, b, alpha, out, B, st);
+    }
+  } else {
+    int rc = ensure_f32(net, lp.d.src, B, false, st);
+    if (rc) return rc;
+    const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
+    if (lp.d.kind == XTB_CONV) conv_fwd<float>(lp, x, nullptr, w, b, 1.f, out, B, st);
+    else dense_fwd<float>(lp, x, nullptr, w, b, 1.f, out, B, st);
+  }
   LAUNCH_CHECK();
+  net->f32_ok[t] = 1; net->bp_ok[t] = 0;
   return XTB_OK;
 }
 
 static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, int B, cudaStream_t st, bool bias_done = false) {
   const LayerPlan& lp = net->L[i];
   int t = i + 1;
-  const float* dy = (const float*)(net->ws + net->gout_off[t]);
-  Planes pdy = gout_planes(net, t);
   float* dw = net->grads + lp.w_off;
   float* db = net->grads + lp.b_off;
-  cudaError_t te = cudaSuccess;
+  if (use_tc(lp)) {
+    int rc = ensure_bp(net, t, B, true, st);
+    if (rc) return rc;
+    rc = lp.d.src == 0 ? op_decode(net, obs, idx, B, st) : ensure_bp(net, lp.d.src, B, false, st);
+    if (rc) return rc;
+    cudaError_t te = tc_wgrad(net, i, B, st);
+    if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 wgrad launch (layer %d): %s", i, cudaGetErrorString(te));
+    LAUNCH_CHECK();
+    if (!bias_done) {   // bias gradient = column sums of dY over samples (and pixels); from the fp32 copy when it is current
+      if (net->gf32_ok[t]) {
+        int Mb = lp.d.kind == XTB_CONV ? B * lp.g.P : B;
+        dim3 gridb((lp.N + 31) / 32, (Mb + 1023) / 1024);
+        XLAUNCH(colsum_kernel, gridb, 256, 0, st, (const float*)(net->ws + net->gout_off[t]), Mb, lp.N, db);
+      } else {
+        XLAUNCH(bp::bp_colsum_kernel, (net->tsize[t] / 8 + 3) / 4, 128, 0, st, gout_bp(net, t), B, net->tsize[t], lp.N, db);
+      }
+      LAUNCH_CHECK();
+    }
+    return XTB_OK;
+  }
+  int rc = ensure_f32(net, t, B, true, st);
+  if (rc) return rc;
+  const float* dy = (const float*)(net->ws + net->gout_off[t]);
   bool need_colsum = false;
   if (lp.d.src == 0) {
     float alpha = net->desc.scale;
-    if (tc_conv_ok(net, lp)) {
-      te = lp.pad ? tc_conv_wgrad_t<true>(lp, obs_planes(net), false, pdy, alpha, dw, B, st)
-                  : tc_conv_wgrad_t<false>(lp, obs_planes(net), false, pdy, alpha, dw, B, st);
-      need_colsum = true;
+    if (net->desc.input_u8) {
+      if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st, !bias_done);
+      else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st, !bias_done);
     } else {
-      if (net->desc.input_u8) {
-        if (lp.d.kind == XTB_CONV) conv_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st, !bias_done);
-        else dense_wgrad<uint8_t>(lp, (const uint8_t*)obs, idx, dy, alpha, dw, B, st, !bias_done);
-      } else {
-        if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st, !bias_done);
-        else dense_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st, !bias_done);
-      }
-      need_colsum = alpha != 1.f;
+      if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st, !bias_done);
+      else dense_wgrad<float>(lp, (const float*)obs, idx, dy, alpha, dw, B, st, !bias_done);
     }
+    need_colsum = alpha != 1.f;
   } else {
+    rc = ensure_f32(net, lp.d.src, B, false, st);
+    if (rc) return rc;
     const float* x = (const float*)(net->ws + net->out_off[lp.d.src]);
-    Planes px = out_planes(net, lp.d.src);
-    if (lp.d.kind == XTB_CONV) {
-      if (tc_conv_ok(net, lp)) {
-        te = lp.pad ? tc_conv_wgrad_t<true>(lp, px, true, pdy, 1.f, dw, B, st) : tc_conv_wgrad_t<false>(lp, px, true, pdy, 1.f, dw, B, st);
-        need_colsum = true;
-      } else conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st, !bias_done);
-    } else {
-      if (tc_dense_ok(lp)) { te = tc_dense_wgrad(lp, px, pdy, dw, B, st); need_colsum = true; }
-      else dense_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st, !bias_done);
-    }
+    if (lp.d.kind == XTB_CONV) conv_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st, !bias_done);
+    else dense_wgrad<float>(lp, x, nullptr, dy, 1.f, dw, B, st, !bias_done);
   }
-  if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 wgrad launch (layer %d): %s", i, cudaGetErrorString(te));
   LAUNCH_CHECK();
   if (need_colsum && !bias_done) {   // bias gradient = column sums of dY
     int Mb = lp.d.kind == XTB_CONV ? B * lp.g.P : B;
@@ -711,60 +879,107 @@ static int op_wgrad(xtb_net* net, int i, const void* obs, const int32_t* idx, in
 }
 
 // data gradient of layer i into its source tensor (gradient wrt the source's pre-activation)
-// db_src: bias gradient of the layer producing the source tensor, accumulated by the epilogue when non-NULL
-static int op_dgrad(xtb_net* net, int i, int acc, int B, cudaStream_t st, float* db_src = nullptr) {
+// fuse_db: the epilogue also produces the bias gradient of the layer behind the source tensor (ordered partial sums)
+static int op_dgrad(xtb_net* net, int i, int acc, int B, cudaStream_t st, bool fuse_db = false) {
   const LayerPlan& lp = net->L[i];
   int t = i + 1, s = lp.d.src;
+  if (use_tc(lp)) {
+    int rc = ensure_bp(net, t, B, true, st);
+    if (rc) return rc;
+    if (lp.src_act != 0) { rc = ensure_bp(net, s, B, false, st); if (rc) return rc; }
+    if (acc) { rc = ensure_bp(net, s, B, true, st); if (rc) return rc; }
+    float* dbp = fuse_db ? (float*)(net->ws + lp.dbpart_off) : nullptr;
+    cudaError_t te = tc_dgrad(net, i, B, acc, dbp, st);
+    if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 dgrad launch (layer %d): %s", i, cudaGetErrorString(te));
+    LAUNCH_CHECK();
+    if (fuse_db) {
+      const int units = lp.d.kind == XTB_CONV ? lp.q.H * lp.q.W : lp.K / lp.n_dg;
+      bp::RedSeg r;
+      memset(&r, 0, sizeof r);
+      r.part = dbp; r.n_slabs = std::min(kSMs, units * ((B + 127) / 128)); r.slab = lp.n_dg; r.count = lp.n_dg; r.kind = 1;
+      r.dst_off = net->L[s - 1].b_off; r.alpha = 1.f;
+      net->pending.push_back(r);
+    }
+    net->gbp_ok[s] = 1; net->gf32_ok[s] = 0;
+    return XTB_OK;
+  }
+  int rc = ensure_f32(net, t, B, true, st);
+  if (rc) return rc;
+  rc = ensure_f32(net, s, B, false, st);
+  if (rc) return rc;
+  if (acc) { rc = ensure_f32(net, s, B, true, st); if (rc) return rc; }
   const float* dy = (const float*)(net->ws + net->gout_off[t]);
-  Planes pdy = gout_planes(net, t);
   const float* x = (const float*)(net->ws + net->out_off[s]);
   float* gsrc = (float*)(net->ws + net->gout_off[s]);
-  Planes pg = gout_planes(net, s);
   const float* w = net->params + lp.w_off;
-  cudaError_t te = cudaSuccess;
   if (lp.d.kind == XTB_CONV) {
-    if (tc_conv_dgrad_ok(lp)) te = tc_conv_dgrad(lp, pdy, w_planes(net), gsrc, x, pg, acc, db_src, B, st);
-    else {
-      ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
-      BConvDgrad bl{w, lp.wk, lp.N};
-      EpiDgrad ep{gsrc, x, lp.src_act, lp.g.C, acc, pg.hi, pg.lo_off};
-      launch_gemm(al, bl, ep, B * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
-    }
+    ADgrad al{dy, lp.g, lp.dkyx, lp.dco, lp.sshift};
+    BConvDgrad bl{w, lp.wk, lp.N};
+    EpiDgrad ep{gsrc, x, lp.src_act, lp.g.C, acc, nullptr, 0};
+    launch_gemm(al, bl, ep, B * lp.g.H * lp.g.W, lp.g.C, lp.Kd, false, st);
   } else {
-    if (tc_dense_ok(lp)) te = tc_dense_dgrad(lp, pdy, w_planes(net), gsrc, x, pg, acc, db_src, B, st);
-    else {
-      ADense<float> al{dy, nullptr, lp.N};
-      BTransposed bl{w, lp.N};
-      EpiDgrad ep{gsrc, x, lp.src_act, lp.K, acc, pg.hi, pg.lo_off};
-      launch_gemm(al, bl, ep, B, lp.K, lp.N, false, st);
-    }
+    ADense<float> al{dy, nullptr, lp.N};
+    BTransposed bl{w, lp.N};
+    EpiDgrad ep{gsrc, x, lp.src_act, lp.K, acc, nullptr, 0};
+    launch_gemm(al, bl, ep, B, lp.K, lp.N, false, st);
   }
-  if (te != cudaSuccess) return fail(XTB_ERR_CUDA, "tcgen05 dgrad launch (layer %d): %s", i, cudaGetErrorString(te));
   LAUNCH_CHECK();
+  net->gf32_ok[s] = 1; net->gbp_ok[s] = 0;
+  return XTB_OK;
+}
+
+// queued ordered reductions (conv weight gradients, fused bias gradients) -> flat gradient bucket, one launch
+static int flush_reductions(xtb_net* net, cudaStream_t st) {
+  if (net->pending.empty()) return XTB_OK;
+  bp::RedSegs segs;
+  memset(&segs, 0, sizeof segs);
+  int mx = 0;
+  if (net->pending.size() > bp::RED_MAX) return fail(XTB_ERR_STATE, "too many pending reductions");
+  for (size_t k = 0; k < net->pending.size(); k++) { segs.s[k] = net->pending[k]; mx = std::max(mx, net->pending[k].count); }
+  dim3 grid((mx + 255) / 256, (unsigned)net->pending.size());
+  XLAUNCH(bp::grad_reduce_kernel, grid, 256, 0, st, segs, net->grads);
+  LAUNCH_CHECK();
+  net->pending.clear();
   return XTB_OK;
 }
 
 // ------------------------------------------------------------------------------------------
 // forward / backward
 // ------------------------------------------------------------------------------------------
+// want_f32_mask: bit t set = tensor t is needed in fp32 row-major form (all tensors for the public entry point)
 static int net_forward_impl(xtb_net* net, const float* params, const void* obs, const int32_t* gather_idx,
-                            int batch, void* stream, unsigned skip_mask);
+                            int batch, void* stream, unsigned skip_mask, unsigned want_f32_mask);
 extern "C" int xtb_net_forward(xtb_net* net, const float* params, const void* obs, const int32_t* gather_idx,
                                int batch, void* stream) {
-  return net_forward_impl(net, params, obs, gather_idx, batch, stream, 0u);
+  return net_forward_impl(net, params, obs, gather_idx, batch, stream, 0u, ~0u);
 }
 static int net_forward_impl(xtb_net* net, const float* params, const void* obs, const int32_t* gather_idx,
-                            int batch, void* stream, unsigned skip_mask) {
+                            int batch, void* stream, unsigned skip_mask, unsigned want_f32_mask) {
   if (!net || !net->ws) return fail(XTB_ERR_STATE, "xtb_net_forward: net not bound");
   if (batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "batch %d out of range (max %d)", batch, net->max_batch);
   if (!obs) return fail(XTB_ERR_ARG, "obs is null");
   const float* P = params ? params : net->params;
-  const bool tc_allowed = (P == net->params);   // foreign parameters have no bf16 planes: fp32 kernels
+  const bool tc_allowed = (P == net->params);   // foreign parameters have no weight blobs: fp32 kernels
   cudaStream_t st = S(stream);
-  if (tc_allowed) { int rc = op_decode(net, obs, gather_idx, batch, st); if (rc) return rc; }
-  for (size_t i = 0; i < net->L.size(); i++) {
+  const int nl = (int)net->L.size();
+  net->obs_bp_ok = false;
+  for (int t = 1; t <= nl; t++) { net->f32_ok[t] = net->bp_ok[t] = 0; }
+  for (int i = 0; i < nl; i++) {
     if (skip_mask & (1u << i)) continue;
-    int rc = op_forward(net, (int)i, P, tc_allowed, obs, gather_idx, batch, st);
+    const LayerPlan& lp = net->L[i];
+    // dense layers write fp32 from the epilogue when asked; conv maps are merged afterwards (the only fp32 readers of
+    // conv maps are uncovered layers and the public API)
+    bool direct = lp.d.kind == XTB_DENSE && ((want_f32_mask >> (i + 1)) & 1u);
+    // ... or when a layer outside the tensor-core path consumes it (exact fp32 instead of hi + lo)
+    if (lp.d.kind == XTB_DENSE)
+      for (int j = i + 1; j < nl; j++)
+        if (net->L[j].d.src == i + 1 && !(skip_mask & (1u << j)) && !(tc_allowed && use_tc(net->L[j]))) direct = true;
+    int rc = op_forward(net, i, P, tc_allowed, obs, gather_idx, batch, direct, st);
+    if (rc) return rc;
+  }
+  for (int t = 1; t <= nl; t++) {
+    if (!((want_f32_mask >> t) & 1u) || (skip_mask & (1u << (t - 1)))) continue;
+    int rc = ensure_f32(net, t, batch, false, st);
     if (rc) return rc;
   }
   return XTB_OK;
@@ -772,54 +987,42 @@ static int net_forward_impl(xtb_net* net, const float* params, const void* obs, 
 
 static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
                              const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads,
-                             unsigned bias_done_tensors = 0u);
+                             unsigned bias_done_tensors = 0u, unsigned heads_bp_mask = 0u);
 extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
                                 const int32_t* head_tensors, int n_heads, void* stream) {
   return net_backward_impl(net, obs, gather_idx, batch, head_tensors, n_heads, stream, 0u, true);
 }
-// head_tensors: tensors whose gradient buffers (fp32 AND planes) were filled by the caller / by a fp32 kernel
+// head_tensors: tensors whose gradient was filled by the caller: fp32 row-major, or (bit set in heads_bp_mask) planes
 static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
                              const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads,
-                             unsigned bias_done_tensors) {
+                             unsigned bias_done_tensors, unsigned heads_bp_mask) {
   if (!net || !net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_net_backward: net not bound (grads required)");
   if (batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "batch out of range");
   cudaStream_t st = S(stream);
   const int nl = (int)net->L.size();
   std::vector<char> has_grad(nl + 1, 0), written(nl + 1, 0);
+  for (int t = 1; t <= nl; t++) net->gf32_ok[t] = net->gbp_ok[t] = 0;
+  net->pending.clear();
   for (int h = 0; h < n_heads; h++) {
     int t = head_tensors[h];
     if (t < 1 || t > nl) return fail(XTB_ERR_ARG, "bad head tensor %d", t);
     has_grad[t] = 1; written[t] = 1;
-    // gradients written from outside (loss kernels, python) only touch the fp32 buffer: refresh the planes
-    // when a tensor-core kernel of this layer will read them
-    const LayerPlan& lp = net->L[t - 1];
-    if (!(skip_mask & (1u << (t - 1))) && ((lp.d.kind == XTB_CONV && (tc_conv_ok(net, lp) || tc_conv_dgrad_ok(lp))) || tc_dense_ok(lp)) &&
-        !net->gout_planes_fresh) {
-      Planes pg = gout_planes(net, t);
-      long long n = (long long)batch * net->tsize[t];
-      XLAUNCH(tc::split_planes_kernel, (unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st, (const float*)(net->ws + net->gout_off[t]), pg.hi, pg.lo_off, n);
-      LAUNCH_CHECK();
-    }
+    if ((heads_bp_mask >> t) & 1u) net->gbp_ok[t] = 1; else net->gf32_ok[t] = 1;
   }
   if (zero_grads) CUDA_TRY(cudaMemsetAsync(net->grads, 0, net->n_params * sizeof(float), st));
-  // bias-gradient fusion: the bias gradient of the layer producing tensor s is the column sum of gout(s); when
-  // every consumer of s writes its contribution through a tensor-core data-gradient epilogue, those epilogues
-  // accumulate the column sums and the separate colsum launch of that layer is dropped
+  // bias-gradient fusion: the bias gradient of the layer producing tensor s is the column sum of gout(s); when s has
+  // exactly one consumer and that consumer's tensor-core data-gradient tile spans exactly the bias vector, its
+  // epilogue accumulates the column sums (ordered partial sums, no atomics) and the separate pass is dropped
   std::vector<char> fuse_bias(nl + 1, 0);
   for (int s = 1; s <= nl; s++) {
     if (bias_done_tensors & (1u << s)) { fuse_bias[s] = 2; continue; }
     const LayerPlan& ps = net->L[s - 1];
-    bool all = true, any = false;
-    for (int j = 0; j < nl; j++) {
-      if (net->L[j].d.src != s) continue;
-      any = true;
-      const LayerPlan& c = net->L[j];
-      bool ok = !(skip_mask & (1u << j)) &&
-                ((c.d.kind == XTB_CONV && tc_conv_dgrad_ok(c) && ps.d.kind == XTB_CONV && c.g.C % 16 == 0) ||
-                 (c.d.kind == XTB_DENSE && tc_dense_ok(c) && ps.d.kind == XTB_DENSE && c.K % 16 == 0 && c.K <= 64));
-      if (!ok) all = false;
-    }
-    fuse_bias[s] = (any && all) ? 1 : 0;
+    int consumers = 0, cj = -1;
+    for (int j = 0; j < nl; j++) if (net->L[j].d.src == s && !(skip_mask & (1u << j))) { consumers++; cj = j; }
+    if (consumers != 1) continue;
+    const LayerPlan& c = net->L[cj];
+    if (!use_tc(c)) continue;
+    if (ps.d.kind == XTB_CONV ? c.n_dg == ps.N : (c.d.kind == XTB_DENSE && c.n_dg == ps.N && c.K == ps.N)) fuse_bias[s] = 1;
   }
   for (int i = nl - 1; i >= 0; i--) {
     if (skip_mask & (1u << i)) continue;
@@ -830,31 +1033,38 @@ static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gathe
     if (rc) return rc;
     if (lp.d.src != 0) {
       int s = lp.d.src;
-      float* db_src = fuse_bias[s] == 1 ? net->grads + net->L[s - 1].b_off : nullptr;
-      rc = op_dgrad(net, i, written[s] ? 1 : 0, batch, st, db_src);
+      rc = op_dgrad(net, i, written[s] ? 1 : 0, batch, st, fuse_bias[s] == 1);
       if (rc) return rc;
       written[s] = 1; has_grad[s] = 1;
     }
   }
-  return XTB_OK;
+  return flush_reductions(net, st);
 }
 
-// Launch ONE kernel of one layer (0 = forward, 1 = weight gradient, 2 = data gradient) on the tensors
-// currently in the workspace: lets bench.py time the dominant kernel alone with CUDA events.
+// Launch ONE kernel of one layer (0 = forward, 1 = weight gradient, 2 = data gradient, 3 = frame decode) on the
+// tensors currently in the workspace: lets bench.py time the dominant kernel alone with CUDA events.
 extern "C" int xtb_net_bench_layer(xtb_net* net, int layer, int which, const void* obs, const int32_t* gather_idx,
                                    int batch, void* stream) {
   if (!net || !net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_net_bench_layer: net not bound");
   if (layer < 0 || layer >= (int)net->L.size() || batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "bad layer/batch");
   cudaStream_t st = S(stream);
-  if (which == 0) return op_forward(net, layer, net->params, true, obs, gather_idx, batch, st);
-  if (which == 1) return op_wgrad(net, layer, obs, gather_idx, batch, st);
+  // tensors the caller filled through xtb_net_tensor / xtb_net_tensor_grad are fp32 row-major
+  for (int t = 1; t <= (int)net->L.size(); t++) {
+    if (!net->f32_ok[t] && !net->bp_ok[t]) net->f32_ok[t] = 1;
+    if (!net->gf32_ok[t] && !net->gbp_ok[t]) net->gf32_ok[t] = 1;
+  }
+  if (which == 0) return op_forward(net, layer, net->params, true, obs, gather_idx, batch, false, st);
+  if (which == 1) { int rc = op_wgrad(net, layer, obs, gather_idx, batch, st, true); net->pending.clear(); return rc; }
   if (which == 2) {
     if (net->L[layer].d.src == 0) return fail(XTB_ERR_ARG, "layer reads the observation: no data gradient");
-    return op_dgrad(net, layer, 0, batch, st);
+    int rc = op_dgrad(net, layer, 0, batch, st);
+    net->pending.clear();
+    return rc;
   }
-  if (which == 3) return op_decode(net, obs, gather_idx, batch, st);
+  if (which == 3) { net->obs_bp_ok = false; return op_decode(net, obs, gather_idx, batch, st); }
   return fail(XTB_ERR_ARG, "xtb_net_bench_layer: which must be 0..3");
 }
+
 
 // ------------------------------------------------------------------------------------------
 // heads, GAE, losses
@@ -949,7 +1159,7 @@ struct xtb_adam {
   int clip_mode = 0, n_seg = 0, n_blk = 0;
   float *m = nullptr, *v = nullptr;
   int* blk_seg = nullptr; long long* blk_beg = nullptr; int* blk_len = nullptr;
-  double* norm_sq = nullptr; float* seg_scale = nullptr; AdamState* st = nullptr;
+  double* norm_sq = nullptr; float* seg_scale = nullptr; AdamState* st = nullptr; AdamHyper* hyp = nullptr;
 };
 
 extern "C" int xtb_adam_create(long long count, float lr, float beta1, float beta2, float eps, int clip_mode,
@@ -982,12 +1192,15 @@ extern "C" int xtb_adam_create(long long count, float lr, float beta1, float bet
   chk(cudaMalloc(&o->norm_sq, o->n_seg * sizeof(double)));
   chk(cudaMalloc(&o->seg_scale, o->n_seg * sizeof(float)));
   chk(cudaMalloc(&o->st, sizeof(AdamState)));
+  chk(cudaMalloc(&o->hyp, sizeof(AdamHyper)));
   if (e == cudaSuccess) {
     chk(cudaMemcpy(o->blk_seg, bseg.data(), o->n_blk * sizeof(int), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(o->blk_beg, bbeg.data(), o->n_blk * sizeof(long long), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(o->blk_len, blen.data(), o->n_blk * sizeof(int), cudaMemcpyHostToDevice));
     chk(cudaMemset(o->norm_sq, 0, o->n_seg * sizeof(double)));
     chk(cudaMemcpy(o->st, &init, sizeof init, cudaMemcpyHostToDevice));
+    AdamHyper hy{lr, beta1, beta2, eps, clip};
+    chk(cudaMemcpy(o->hyp, &hy, sizeof hy, cudaMemcpyHostToDevice));
     chk(cudaMemset(m, 0, count * sizeof(float)));
     chk(cudaMemset(v, 0, count * sizeof(float)));
   }
@@ -1000,31 +1213,31 @@ extern "C" void xtb_adam_destroy(xtb_adam* o) {
   if (!o) return;
   drop_graphs_of(o);
   cudaFree(o->blk_seg); cudaFree(o->blk_beg); cudaFree(o->blk_len);
-  cudaFree(o->norm_sq); cudaFree(o->seg_scale); cudaFree(o->st);
+  cudaFree(o->norm_sq); cudaFree(o->seg_scale); cudaFree(o->st); cudaFree(o->hyp);
   delete o;
 }
 
-static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream, tc::bf16* w_hi, long long w_lo);
+static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream);
 extern "C" int xtb_adam_step(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream) {
-  return adam_step_impl(o, params, grads, grad_scale, stream, nullptr, 0);
+  return adam_step_impl(o, params, grads, grad_scale, stream);
 }
-// optimiser step on a network's bound parameters; the weights' bf16 planes are refreshed by the same kernel
+// optimiser step on a network's bound parameters, then the weight blobs of its tensor-core layers are refreshed
 extern "C" int xtb_adam_step_net(xtb_adam* o, xtb_net* net, float grad_scale, void* stream) {
   if (!net || !net->ws || !net->params || !net->grads) return fail(XTB_ERR_STATE, "xtb_adam_step_net: net not bound");
   if (!o || o->count != net->n_params) return fail(XTB_ERR_ARG, "xtb_adam_step_net: optimiser/net size mismatch");
-  Planes w = w_planes(net);
-  return adam_step_impl(o, net->params, net->grads, grad_scale, stream, w.hi, w.lo_off);
+  int rc = adam_step_impl(o, net->params, net->grads, grad_scale, stream);
+  if (rc) return rc;
+  return xtb_net_sync_weights(net, stream);
 }
-static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream, tc::bf16* w_hi, long long w_lo) {
+static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream) {
   if (!o || !params || !grads) return fail(XTB_ERR_ARG, "xtb_adam_step: null pointer");
   cudaStream_t st = S(stream);
   XLAUNCH(sqnorm_kernel, o->n_blk, OPT_THREADS, 0, st, grads, o->blk_seg, o->blk_beg, o->blk_len, o->norm_sq);
   LAUNCH_CHECK();
-  XLAUNCH(adam_prep_kernel, 1, 32, 0, st, o->st, o->norm_sq, o->seg_scale, o->n_seg, o->clip_mode, o->clip, grad_scale,
-                                     o->lr, o->beta1, o->beta2);
+  XLAUNCH(adam_prep_kernel, 1, 32, 0, st, o->st, (const AdamHyper*)o->hyp, o->norm_sq, o->seg_scale, o->n_seg, o->clip_mode, grad_scale);
   LAUNCH_CHECK();
   XLAUNCH(adam_kernel, o->n_blk, OPT_THREADS, 0, st, params, grads, o->m, o->v, o->blk_seg, o->blk_beg, o->blk_len,
-                                                o->seg_scale, o->st, o->beta1, o->beta2, o->eps, w_hi, w_lo);
+                                                o->seg_scale, o->st, (const AdamHyper*)o->hyp, (__nv_bfloat16*)nullptr, 0LL);
   LAUNCH_CHECK();
   return XTB_OK;
 }
@@ -1033,12 +1246,51 @@ extern "C" const float* xtb_adam_grad_norm(const xtb_adam* o) { return o ? &o->s
 extern "C" int xtb_adam_set_lr(xtb_adam* o, float lr) {
   if (!o) return fail(XTB_ERR_ARG, "null optimiser");
   o->lr = lr;
+  // device-resident: captured graphs read it at replay time.  Ordered after everything already submitted.
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(&o->hyp->lr, &lr, sizeof lr, cudaMemcpyHostToDevice));
   return XTB_OK;
 }
 
 // ------------------------------------------------------------------------------------------
 // fused PPO learner loop
 // ------------------------------------------------------------------------------------------
+// CUDA graphs cannot be captured on the legacy default stream, which is what a host that never creates streams
+// (stream == NULL) runs on.  Such calls are moved onto a private non-blocking stream of the current device, fenced
+// against the legacy stream with events on both sides, so the caller keeps default-stream ordering semantics.
+struct EngineStream { cudaStream_t st = nullptr; cudaEvent_t in = nullptr, out = nullptr; };
+static EngineStream g_engine_streams[64];
+struct StreamScope {
+  cudaStream_t st = nullptr;
+  EngineStream* es = nullptr;
+  int begin(void* stream, bool side_if_null) {
+    st = S(stream);
+    if (st || !side_if_null) return XTB_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(XTB_ERR_ARG, "device index %d out of range", dev);
+    EngineStream& e = g_engine_streams[dev];
+    if (!e.st) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&e.st, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&e.in, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&e.out, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(e.in, nullptr));
+    CUDA_TRY(cudaStreamWaitEvent(e.st, e.in, 0));
+    es = &e; st = e.st;
+    return XTB_OK;
+  }
+  int end() {
+    if (!es) return XTB_OK;
+    CUDA_TRY(cudaEventRecord(es->out, es->st));
+    CUDA_TRY(cudaStreamWaitEvent(nullptr, es->out, 0));
+    es = nullptr;
+    return XTB_OK;
+  }
+};
+static std::atomic<long long> g_graph_replays{0};
+extern "C" long long xtb_graph_replay_count(void) { return g_graph_replays.load(); }
+
 // A captured graph bakes every kernel argument: the key carries everything that can change them.
 struct GraphKey {
   const void* net; const void* opt; const void* obs; const void* perm; const void* loss; int n, b, e;
@@ -1077,15 +1329,21 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
     for (int s0 = 0; s0 < N; s0 += B, step++) {
       int mb = std::min(B, N - s0);
       const int32_t* idx = perm + (long long)e * N + s0;
-      int rc = net_forward_impl(net, nullptr, ro->obs, idx, mb, stream, skip);
+      // fp32 row-major copies: the hidden tensors the fused heads read, or the head outputs the loss kernel reads
+      unsigned want = fuse ? ((1u << lpi.d.src) | (1u << lv.d.src)) : ((1u << pi_t) | (1u << v_t));
+      int rc = net_forward_impl(net, nullptr, ro->obs, idx, mb, stream, skip, want);
       if (rc) return rc;
       if (fuse) {
         CUDA_TRY(cudaMemsetAsync(net->grads, 0, net->n_params * sizeof(float), S(stream)));
         PpoHeadsArgs a;
         a.h_pi = (const float*)(net->ws + net->out_off[lpi.d.src]); a.h_v = (const float*)(net->ws + net->out_off[lv.d.src]);
         a.g_pi = (float*)(net->ws + net->gout_off[lpi.d.src]); a.g_v = (float*)(net->ws + net->gout_off[lv.d.src]);
-        a.gp_hi = gout_planes(net, lpi.d.src).hi; a.gp_lo = gout_planes(net, lpi.d.src).lo_off;
-        a.gv_hi = gout_planes(net, lv.d.src).hi; a.gv_lo = gout_planes(net, lv.d.src).lo_off;
+        // hidden-layer gradients go straight into batch-planar planes when the hidden layer runs on tensor cores
+        const bool bp_pi = use_tc(net->L[lpi.d.src - 1]) && net->plane_elems[lpi.d.src] > 0;
+        const bool bp_v = use_tc(net->L[lv.d.src - 1]) && net->plane_elems[lv.d.src] > 0;
+        a.gp_hi = bp_pi ? gout_bp(net, lpi.d.src).hi : nullptr; a.gp_lo = net->plane_elems[lpi.d.src];
+        a.gv_hi = bp_v ? gout_bp(net, lv.d.src).hi : nullptr; a.gv_lo = net->plane_elems[lv.d.src];
+        a.pitch = net->pitch;
         a.w_pi = net->params + lpi.w_off; a.b_pi = net->params + lpi.b_off; a.w_v = net->params + lv.w_off; a.b_v = net->params + lv.b_off;
         a.dw_pi = net->grads + lpi.w_off; a.db_pi = net->grads + lpi.b_off; a.dw_v = net->grads + lv.w_off; a.db_v = net->grads + lv.b_off;
         // the hidden layers' bias gradients (column sums of g) when they are dense and only feed the heads
@@ -1106,9 +1364,8 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         else XLAUNCH((ppo_heads_kernel<16, 4>), blocks, 256, shb, S(stream), a);
         LAUNCH_CHECK();
         int srcs[2] = {lpi.d.src, lv.d.src};
-        net->gout_planes_fresh = true;    // the fused kernel wrote fp32 and planes
-        rc = net_backward_impl(net, ro->obs, idx, mb, srcs, a.shared ? 1 : 2, stream, skip, false, bias_done);
-        net->gout_planes_fresh = false;
+        unsigned hbp = (bp_pi ? (1u << lpi.d.src) : 0u) | (bp_v ? (1u << lv.d.src) : 0u);   // the fused kernel wrote planes there
+        rc = net_backward_impl(net, ro->obs, idx, mb, srcs, a.shared ? 1 : 2, stream, skip, false, bias_done, hbp);
         if (rc) return rc;
       } else {
         rc = xtb_ppo_loss_grad(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), idx, ro->action, ro->old_logp,
@@ -1146,8 +1403,11 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
     if (rc > 0) world = rc;
     inv_world = 1.f / world;
   }
-  if (!use_graph || !stream || g_grad_hook)
+  if (!use_graph || g_grad_hook)
     return ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, inv_world, stream);
+  StreamScope sc;
+  int src = sc.begin(stream, true);
+  if (src) return src;
   GraphKey key;
   memset(&key, 0, sizeof key);
   key.net = net; key.opt = opt; key.obs = ro->obs; key.perm = perm; key.loss = loss_per_step;
@@ -1157,10 +1417,10 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
   key.pi_t = pi_tensor; key.v_t = v_tensor; key.fuse = g_fuse_heads; key.tc = g_tc_mode; key.ws = net->ws;
   auto it = g_graphs.find(key);
   if (it == g_graphs.end()) {
-    cudaStream_t st = S(stream);
+    cudaStream_t st = sc.st;
     long long before = g_launches.load();
     CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, 1.f, stream);
+    int rc = ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, 1.f, (void*)st);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     long long captured = g_launches.load() - before;
@@ -1173,9 +1433,10 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
     if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
     it = g_graphs.emplace(key, GraphVal{exec, captured}).first;
   }
-  CUDA_TRY(cudaGraphLaunch(it->second.exec, S(stream)));
+  CUDA_TRY(cudaGraphLaunch(it->second.exec, sc.st));
   g_launches.fetch_add(it->second.kernels, std::memory_order_relaxed);
-  return XTB_OK;
+  g_graph_replays.fetch_add(1, std::memory_order_relaxed);
+  return sc.end();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1209,7 +1470,8 @@ static int rollout_infer_launch(xtb_net* net, const void* obs, const int32_t* st
               lpi.d.src != 0 && lv.d.src != 0 && lpi.K == lv.K && lpi.K % 32 == 0 && adim <= 8 && kpl <= 16;
   unsigned skip = fuse ? ((1u << (pi_t - 1)) | (1u << (v_t - 1))) : 0u;
   for (int t = 0; t < T; t++) {
-    int rc = net_forward_impl(net, nullptr, obs, step_idx ? step_idx + (long long)t * E : nullptr, E, stream, skip);
+    unsigned want = fuse ? ((1u << lpi.d.src) | (1u << lv.d.src)) : ((1u << pi_t) | (1u << v_t));
+    int rc = net_forward_impl(net, nullptr, obs, step_idx ? step_idx + (long long)t * E : nullptr, E, stream, skip, want);
     if (rc) return rc;
     int32_t* a_t = action + (long long)t * E; float* lp_t = logp + (long long)t * E; float* v_o = value + (long long)t * E;
     if (fuse) {
@@ -1239,18 +1501,21 @@ extern "C" int xtb_ppo_rollout_infer(xtb_net* net, const void* obs, const int32_
   if (n_env <= 0 || n_env > net->max_batch || n_step <= 0) return fail(XTB_ERR_ARG, "xtb_ppo_rollout_infer: bad sizes");
   if (pi_tensor < 1 || pi_tensor > nl || v_tensor < 1 || v_tensor > nl || net->tsize[v_tensor] != 1 || net->tsize[pi_tensor] > MAX_ADIM)
     return fail(XTB_ERR_ARG, "xtb_ppo_rollout_infer: bad head tensors");
-  if (!use_graph || !stream)
+  if (!use_graph)
     return rollout_infer_launch(net, obs, step_idx, n_env, n_step, pi_tensor, v_tensor, seed, offset_dev, action, logp, value, stream);
+  StreamScope sc;
+  int src = sc.begin(stream, true);
+  if (src) return src;
   InferKey key;
   memset(&key, 0, sizeof key);
   key.net = net; key.obs = obs; key.idx = step_idx; key.act = action; key.logp = logp; key.val = value; key.ctr = offset_dev;
   key.ws = net->ws; key.seed = seed; key.e = n_env; key.t = n_step; key.pi_t = pi_tensor; key.v_t = v_tensor; key.tc = g_tc_mode;
   auto it = g_infer_graphs.find(key);
   if (it == g_infer_graphs.end()) {
-    cudaStream_t st = S(stream);
+    cudaStream_t st = sc.st;
     long long before = g_launches.load();
     CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = rollout_infer_launch(net, obs, step_idx, n_env, n_step, pi_tensor, v_tensor, seed, offset_dev, action, logp, value, stream);
+    int rc = rollout_infer_launch(net, obs, step_idx, n_env, n_step, pi_tensor, v_tensor, seed, offset_dev, action, logp, value, (void*)st);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     long long captured = g_launches.load() - before;
@@ -1263,9 +1528,10 @@ extern "C" int xtb_ppo_rollout_infer(xtb_net* net, const void* obs, const int32_
     if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
     it = g_infer_graphs.emplace(key, GraphVal{exec, captured}).first;
   }
-  CUDA_TRY(cudaGraphLaunch(it->second.exec, S(stream)));
+  CUDA_TRY(cudaGraphLaunch(it->second.exec, sc.st));
   g_launches.fetch_add(it->second.kernels, std::memory_order_relaxed);
-  return XTB_OK;
+  g_graph_replays.fetch_add(1, std::memory_order_relaxed);
+  return sc.end();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1292,13 +1558,17 @@ extern "C" int xtb_ppo_predict_host(xtb_net* net, const void* obs_host, size_t o
                                     int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
                                     float* out_dev, float* out_host, int use_graph, void* stream) {
   if (!obs_host || !obs_dev || !out_dev || !out_host) return fail(XTB_ERR_ARG, "xtb_ppo_predict_host: null pointer");
-  CUDA_TRY(xtb::Stager::instance().stage_h2d(obs_dev, obs_host, obs_bytes, S(stream)));
+  StreamScope sc;
+  int src = sc.begin(stream, use_graph != 0);
+  if (src) return src;
+  void* st = (void*)sc.st;
+  CUDA_TRY(xtb::Stager::instance().stage_h2d(obs_dev, obs_host, obs_bytes, sc.st));
   int rc = xtb_ppo_rollout_infer(net, obs_dev, nullptr, n_env, 1, pi_tensor, v_tensor, seed, offset_dev,
-                                 reinterpret_cast<int32_t*>(out_dev), out_dev + n_env, out_dev + 2 * (size_t)n_env, use_graph, stream);
+                                 reinterpret_cast<int32_t*>(out_dev), out_dev + n_env, out_dev + 2 * (size_t)n_env, use_graph, st);
   if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(out_host, out_dev, sizeof(float) * 3 * (size_t)n_env, cudaMemcpyDeviceToHost, S(stream)));
-  CUDA_TRY(cudaStreamSynchronize(S(stream)));
-  return XTB_OK;
+  CUDA_TRY(cudaMemcpyAsync(out_host, out_dev, sizeof(float) * 3 * (size_t)n_env, cudaMemcpyDeviceToHost, sc.st));
+  CUDA_TRY(cudaStreamSynchronize(sc.st));
+  return sc.end();
 }
 extern "C" int xtb_copy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
   CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, S(stream)));

@@ -86,8 +86,9 @@ class Net(object):
         ws_bytes = int(self.lib.xtb_net_workspace_bytes(self.handle))
         self.ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=self.device)
         self._ws_base = (self.ws.data_ptr() + 255) // 256 * 256
-        check(self.lib.xtb_net_bind(self.handle, _ptr(self.params), _ptr(self.grads),
-                                    C.c_void_p(self._ws_base), ws_bytes))
+        with torch.cuda.device(self.device):
+            check(self.lib.xtb_net_bind_stream(self.handle, _ptr(self.params), _ptr(self.grads),
+                                               C.c_void_p(self._ws_base), ws_bytes, stream_ptr()))
 
     def params_changed(self):
         """Must follow every host-side write into `self.params`: refreshes the bf16 hi/lo planes the
