@@ -228,6 +228,20 @@ int xtb_ppo_predict_host(xtb_net* net, const void* obs_host, size_t obs_bytes, v
 typedef int (*xtb_grad_hook)(void* user, float* grads, long long count, void* stream);
 int xtb_set_grad_hook(xtb_grad_hook hook, void* user);
 
+/* Data-parallel communicator owned by the library (precedent zeus/trainer/trainer_tf.py:187-203): NCCL is
+ * resolved with dlopen (`nccl_path` NULL = "libnccl.so.2").  Rank 0 calls xtb_comm_unique_id and ships the 128 bytes to
+ * the other ranks (engine.py uses torch.distributed); every rank then calls xtb_comm_create.  With a communicator
+ * installed (xtb_set_grad_comm) the fused training loops all-reduce the flat gradient bucket themselves -- the large
+ * dense weight gradient as soon as it is final, on a side stream under the rest of the backward pass -- and stay inside
+ * the CUDA graph. */
+typedef struct xtb_comm xtb_comm;
+int xtb_comm_unique_id(const char* nccl_path, void* id128);
+int xtb_comm_create(const char* nccl_path, const void* id128, int rank, int world, xtb_comm** out);
+void xtb_comm_destroy(xtb_comm* comm);
+int xtb_comm_world(const xtb_comm* comm);
+int xtb_set_grad_comm(xtb_comm* comm);
+int xtb_comm_allreduce(xtb_comm* comm, float* buf, long long count, void* stream);
+
 /* Launch one kernel of one layer alone (which: 0 forward, 1 weight gradient) on the tensors
  * currently in the workspace -- measurement hook for bench.py's roofline object. */
 int xtb_net_bench_layer(xtb_net* net, int layer, int which, const void* obs, const int32_t* gather_idx,

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libxtb200.so")
+LIB_PATH = os.environ.get("XTB_LIB_PATH") or os.path.join(HERE, "lib", "libxtb200.so")   # override: experiment builds (scripts/)
 
 XTB_MAX_LAYERS = 16
 CONV, DENSE = 0, 1
@@ -78,6 +78,12 @@ _SIGS = {
     "xtb_ppo_rollout_infer": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, _P, C.c_int, _P]),
     "xtb_ppo_predict_host": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, C.c_int, _P]),
     "xtb_set_grad_hook": (C.c_int, [GRAD_HOOK, _P]),
+    "xtb_comm_unique_id": (C.c_int, [C.c_char_p, _P]),
+    "xtb_comm_create": (C.c_int, [C.c_char_p, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "xtb_comm_destroy": (None, [_P]),
+    "xtb_comm_world": (C.c_int, [_P]),
+    "xtb_set_grad_comm": (C.c_int, [_P]),
+    "xtb_comm_allreduce": (C.c_int, [_P, _P, C.c_longlong, _P]),
     "xtb_net_bench_layer": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "xtb_set_fuse_heads": (C.c_int, [C.c_int]),
     "xtb_set_tc_mode": (C.c_int, [C.c_int]),

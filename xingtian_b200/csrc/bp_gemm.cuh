@@ -34,6 +34,10 @@
 
 #include "gemm_f32.cuh"
 
+#ifndef XTB_BP_WAIT_HINT
+#define XTB_BP_WAIT_HINT 20000u   // suspend-time hint (ns) of mbarrier.try_wait
+#endif
+
 namespace xtb {
 namespace bp {
 
@@ -60,7 +64,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(20000u)
+      : "r"(bar), "r"(parity), "r"(XTB_BP_WAIT_HINT)
       : "memory");
   return ok;
 }
@@ -76,6 +80,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// one lane of a converged warp: the uniform-datapath instructions (UBLKCP, UTCHMMA, UTCBAR) are issued under it with
+// warp-uniform operands, so ptxas keeps addresses and descriptors in uniform registers instead of wrapping every
+// instruction in an ELECT / R2UR sequence
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -148,6 +160,22 @@ __device__ __forceinline__ void split8(const float v[8], uint4& hi, uint4& lo) {
   split2(v[6], v[7], hi.w, lo.w);
 }
 
+// Optional timeline trace (XTB_BP_TRACE builds only): %globaltimer stamps of one lane per role, kept in shared memory
+// while the kernel runs (a stamp is a timer read and one st.shared) and written out by the first CTAs at kernel exit.
+#ifdef XTB_BP_TRACE
+__device__ unsigned long long* g_bp_trace = nullptr;     // [cta < 4][role 0..2][BP_TR_N] ; slot 0 = count
+#define BP_TR_N 22
+#define BP_TRACE_DECL __shared__ unsigned long long bp_tr[3][BP_TR_N]; if (threadIdx.x < 3) bp_tr[threadIdx.x][0] = 0;
+#define BP_TRACE(role, code) do { if ((threadIdx.x & 31) == 0 && ((role) != 0 || threadIdx.x < 32) && ((role) != 1 || threadIdx.x < 32 * (RW_P_WARPS + 1))) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); \
+    unsigned long long i_ = bp_tr[role][0] + 1; if (i_ < BP_TR_N) { bp_tr[role][i_] = (t_ << 8) | (unsigned)(code); bp_tr[role][0] = i_; } } } while (0)
+#define BP_TRACE_DUMP do { __syncthreads(); if (g_bp_trace && blockIdx.x < 4) for (int i_ = threadIdx.x; i_ < 3 * BP_TR_N; i_ += blockDim.x) \
+    g_bp_trace[(size_t)blockIdx.x * 3 * BP_TR_N + i_] = bp_tr[i_ / BP_TR_N][i_ % BP_TR_N]; } while (0)
+#else
+#define BP_TRACE_DECL
+#define BP_TRACE(role, code) do {} while (0)
+#define BP_TRACE_DUMP do {} while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // batch-planar tensor handle
 // ------------------------------------------------------------------------------------------
@@ -165,19 +193,43 @@ __host__ __device__ inline long long bp_index(int pitch, int row, int f) { retur
 //   dense         : unit = (N tile, K split)                K stages walk a range of feature chunks
 // Weights ("blob"): batch-planar W^T, i.e. [n chunk][k row][8] with pitch = K rows.  Forward reads it MN-major (rows k,
 // chunks along n), the data gradient K-major (rows = output feature k, chunks along the reduction n): same bytes.
+//
+// The stage walk of a conv unit (which feature chunks, which weight rows) is a host-built table (StageEnt per stage,
+// UnitEnt per unit, built once per layer in xtb_net_create): the role loops are a table fetch, an mbarrier wait and a
+// handful of adds per stage.  (First version: the walk was computed in the loops; a stage cost ~0.85 us of dependent
+// integer code in the producer and MMA threads while its data arrived in 0.16 us -- profiles/r2_role_timeline.md.)
 // ------------------------------------------------------------------------------------------
-constexpr int RW_THREADS = 192;
-constexpr int RW_A_PLANE = 2048;              // 128 rows x 16 B
+// Warp roles.  A single warp needs ~0.3-0.6 us of dependent instructions per stage (table fetch, barrier wait, address
+// and descriptor arithmetic, issue) while the data of a stage arrives in ~0.16 us, so the issue roles are replicated:
+// producer warp p fills ring slot p (every slot has its own full/empty barrier pair), MMA warp m owns the tiles with
+// (tile count & 1) == m and with them TMEM accumulator buffer m (MMAs of one accumulator stay in one warp's program
+// order), two epilogue warps per TMEM lane quarter split the accumulator columns.
+constexpr int RW_P_WARPS = 4;
+constexpr int RW_M_WARPS = 2;
+constexpr int RW_EPI_WARPS = 8;
+constexpr int RW_E_WARP0 = RW_P_WARPS + RW_M_WARPS;      // 6: (warp & 3) of warps 6..13 covers every TMEM lane quarter twice
+constexpr int RW_E_TID0 = 32 * RW_E_WARP0;
+constexpr int RW_THREADS = 32 * (RW_E_WARP0 + RW_EPI_WARPS);
+constexpr int RW_A_PLANE = 2048;                 // 128 rows x 16 B
 constexpr int RW_STAGE_A = 2 * 8 * RW_A_PLANE;   // hi + lo, 8 chunks (64 K elements)
 constexpr int RW_STAGE_B = 16384;
 constexpr int RW_MAX_STAGES = 4;
+
+struct StageEnt {            // one K stage of a conv unit (8 bytes; the tables are copied to shared memory at kernel start)
+  uint32_t a_chunk;          // first operand feature chunk of the stage
+  uint16_t w_row;            // first weight-blob row of the stage (forward: k row; data gradient: tap * Cin)
+  uint16_t nch;              // feature chunks in this stage (even, <= 8)
+};
+typedef uint32_t UnitEnt;    // first stage index | stage count << 24
+struct StageDesc { uint32_t a_off, w_off, nch; };   // byte offsets inside a plane / blob plane
 
 struct RowsArgs {
   BpT a; int a_split;                               // operand rows (activations / gradients); a_split: lo plane is read
   const bf16* w_hi; const bf16* w_lo; int w_pitch;  // weight blob planes
   int w_res; int w_res_chunks;                      // blob resident in shared memory (conv): chunks to load per plane
   int mode;                                         // 0 conv forward, 1 conv data gradient, 2 dense
-  int H, W, C, OH, OW, Cout, KH, KW, S, padT, padL; // conv geometry: [H,W,C] -> [OH,OW,Cout]
+  const StageEnt* stages; const UnitEnt* units;     // conv stage walk (global; n_stage_ents / n_units entries)
+  int n_stage_ents;
   int kchunks, kc_split, n_ntiles;                  // dense: K chunks in total / per split, N tiles
   int n_units, n_btiles, B, N;                      // tiles = n_units * n_btiles; N = accumulator columns per plane
   // forward epilogue
@@ -187,92 +239,73 @@ struct RowsArgs {
   BpT src; int src_act; int accumulate; float* db_part;
 };
 
-struct StageDesc { int a_chunk0, nch, w_row, w_c0; };
-struct ItState { int y, x, ky, t, chunk, rem, wrow, end, ntile; };
-
-template <int KIND>
-__device__ __forceinline__ void it_init(const RowsArgs& a, int u, ItState& s) {
-  if (a.mode == 2) {
-    s.ntile = u % a.n_ntiles;
-    int z = u / a.n_ntiles;
-    s.chunk = z * a.kc_split;
-    s.end = min(a.kchunks, s.chunk + a.kc_split);
-  } else {
-    int wu = (KIND == 2) ? a.W : a.OW;
-    s.y = u / wu; s.x = u - s.y * wu;
-    s.ky = -1; s.rem = 0; s.t = -1;
-  }
-}
-template <int KIND>
-__device__ __forceinline__ bool it_next(const RowsArgs& a, ItState& s, StageDesc& d) {
-  if (a.mode == 2) {
-    if (s.chunk >= s.end) return false;
-    d.a_chunk0 = s.chunk; d.nch = min(8, s.end - s.chunk);
-    if (KIND == 2) { d.w_row = s.ntile * a.N; d.w_c0 = s.chunk; }
-    else { d.w_row = s.chunk * 8; d.w_c0 = s.ntile * (a.N >> 3); }
-    s.chunk += d.nch;
-    return true;
-  }
-  if (KIND != 2) {
-    // forward conv: per filter row the taps inside the image are one contiguous feature run
-    if (s.rem == 0) {
-      for (;;) {
-        if (++s.ky >= a.KH) return false;
-        int iy = s.y * a.S - a.padT + s.ky;
-        if (iy < 0 || iy >= a.H) continue;
-        int x0 = s.x * a.S - a.padL, xl = max(x0, 0), xh = min(x0 + a.KW, a.W);
-        if (xh <= xl) continue;
-        s.chunk = ((iy * a.W + xl) * a.C) >> 3;
-        s.rem = ((xh - xl) * a.C) >> 3;
-        s.wrow = (s.ky * a.KW + (xl - x0)) * a.C;
-        break;
-      }
+// per-tile stage source: conv = run of the shared-memory table, dense = arithmetic progression
+struct TileWalk {
+  const uint2* st; uint32_t a0, w0, da, dw, a_pstride; int ns, nch_last;
+  template <int KIND>
+  __device__ __forceinline__ void init(const RowsArgs& a, int u, const uint2* stages_sm, const uint32_t* units_sm) {
+    a_pstride = (uint32_t)a.a.pitch * 16u;
+    if (a.mode == 2) {
+      const int nt = u % a.n_ntiles, z = u / a.n_ntiles;
+      const int cbeg = z * a.kc_split, cend = min(a.kchunks, cbeg + a.kc_split);
+      ns = (cend - cbeg + 7) >> 3;
+      nch_last = cend - cbeg - 8 * (ns - 1);
+      a0 = (uint32_t)cbeg * a_pstride; da = 8u * a_pstride;
+      if (KIND == 2) { w0 = ((uint32_t)cbeg * a.w_pitch + (uint32_t)nt * a.N) * 16u; dw = 8u * (uint32_t)a.w_pitch * 16u; }
+      else { w0 = ((uint32_t)(nt * (a.N >> 3)) * a.w_pitch + (uint32_t)cbeg * 8u) * 16u; dw = 1024u; }
+      st = nullptr;
+    } else {
+      const uint32_t ue = units_sm[u];
+      st = stages_sm + (ue & 0xffffffu); ns = (int)(ue >> 24);
     }
-    d.a_chunk0 = s.chunk; d.nch = min(8, s.rem); d.w_row = s.wrow; d.w_c0 = 0;
-    s.chunk += d.nch; s.rem -= d.nch; s.wrow += d.nch * 8;
-    return true;
   }
-  // data gradient: one stage per filter tap whose output position exists
-  for (;;) {
-    if (++s.t >= a.KH * a.KW) return false;
-    int ky = s.t / a.KW, kx = s.t - ky * a.KW;
-    int ty = s.y + a.padT - ky, tx = s.x + a.padL - kx;
-    if (ty < 0 || tx < 0) continue;
-    int oy = ty / a.S, ox = tx / a.S;
-    if (oy * a.S != ty || ox * a.S != tx || oy >= a.OH || ox >= a.OW) continue;
-    d.a_chunk0 = ((oy * a.OW + ox) * a.Cout) >> 3;
-    d.nch = a.Cout >> 3;
-    d.w_row = s.t * a.C;
-    d.w_c0 = 0;
-    return true;
+  __device__ __forceinline__ StageDesc get(int s) const {
+    if (st) {
+      const uint2 v = st[s];
+      return StageDesc{v.x * a_pstride, (v.y & 0xffffu) * 16u, v.y >> 16};
+    }
+    return StageDesc{a0 + (uint32_t)s * da, w0 + (uint32_t)s * dw, (uint32_t)(s == ns - 1 ? nch_last : 8)};
   }
-}
+};
 
 template <int KIND>
 __global__ void __launch_bounds__(RW_THREADS, 1)
 bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes, int wres_bytes, int tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  __shared__ __align__(8) uint64_t bars[2 * RW_MAX_STAGES + 5];
+  // stage-walk tables live behind the stage ring: [stages : n_stage_ents x 8 B][units : n_units x 4 B]
+  uint2* stages_sm = reinterpret_cast<uint2*>(smem + wres_bytes + n_stages * stage_bytes);
+  uint32_t* units_sm = reinterpret_cast<uint32_t*>(stages_sm + a.n_stage_ents);
+  // full barriers exist once per MMA warp: a slot is consumed alternately by the two warps, and a waiter that saw only
+  // every other completion of one barrier could not tell its phase from the one two fills earlier
+  __shared__ __align__(8) uint64_t bars[3 * RW_MAX_STAGES + 5];
   __shared__ uint32_t tmem_slot;
   __shared__ float red_sh[4][64];
+  __shared__ float bias_sh[64];
+  BP_TRACE_DECL
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[RW_MAX_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * RW_MAX_STAGES]), tempty0 = smem_u32(&bars[2 * RW_MAX_STAGES + 2]);
-  const uint32_t wbar = smem_u32(&bars[2 * RW_MAX_STAGES + 4]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2 * RW_MAX_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[3 * RW_MAX_STAGES]), tempty0 = smem_u32(&bars[3 * RW_MAX_STAGES + 2]);
+  const uint32_t wbar = smem_u32(&bars[3 * RW_MAX_STAGES + 4]);
   if (tid == 0) {
-    for (int s = 0; s < RW_MAX_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
+    for (int s = 0; s < RW_MAX_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(full0 + 8 * (RW_MAX_STAGES + s), 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, RW_EPI_WARPS); }
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tmem_cols);
+  if (warp == RW_P_WARPS) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   pdl_wait();
   pdl_trigger();
+  if (a.mode != 2) {      // tables are static data uploaded at bind time; every thread helps, one barrier
+    const uint2* gs = reinterpret_cast<const uint2*>(a.stages);
+    for (int i = tid; i < a.n_stage_ents; i += RW_THREADS) stages_sm[i] = __ldg(gs + i);
+    for (int i = tid; i < a.n_units; i += RW_THREADS) units_sm[i] = __ldg(a.units + i);
+    __syncthreads();
+  }
   const uint32_t tmem_base = tmem_slot;
   const uint32_t wres = smem_u32(smem);                  // resident weights: hi plane chunks then lo plane chunks
   const uint32_t stage0 = wres + (uint32_t)wres_bytes;
@@ -280,144 +313,218 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
   const int N = a.N;
   constexpr bool CAT = (KIND != 2);                      // forward: one MMA over [W_hi | W_lo], accumulator 2N columns
   const int acc_cols = CAT ? 2 * N : N;
+  const int nbt = a.n_btiles;
+  // tile = blockIdx.x + i * gridDim.x  ->  (unit u, batch tile bt), advanced without divisions
+  const int du = (int)gridDim.x / nbt, dbt = (int)gridDim.x - du * nbt;
 
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (a.w_res && lane == 0) {
+  if (warp < RW_P_WARPS) {
+    // ================= TMA producers: warp p fills ring slot p; converged warp, one elected lane issues the copies ====
+    if (warp == 0 && a.w_res && elect_one()) {
       const uint32_t bytes = (uint32_t)a.w_res_chunks * a.w_pitch * 16;
       mbar_expect_tx(wbar, 2 * bytes);
       bulk_g2s(wres, a.w_hi, bytes, wbar);
       bulk_g2s(wres + bytes, a.w_lo, bytes, wbar);
     }
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int u = tile / a.n_btiles, bt = tile - u * a.n_btiles;
-      const int b0 = bt * 128, nr = min(128, a.B - b0);
-      ItState it; StageDesc d;
-      it_init<KIND>(a, u, it);
-      while (it_next<KIND>(a, it, d)) {
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        const int n_a = d.nch * (a.a_split ? 2 : 1);
-        const int n_bh = a.w_res ? 0 : (KIND == 2 ? d.nch : (N >> 3));
-        const uint32_t a_bytes = (uint32_t)nr * 16;
-        const uint32_t b_bytes = (KIND == 2) ? (uint32_t)N * 16 : (uint32_t)d.nch * 128;
-        if (lane == 0) mbar_expect_tx(full0 + 8 * stage, a_bytes * n_a + b_bytes * 2 * n_bh);
-        __syncwarp();
-        const uint32_t sA = stage0 + (uint32_t)stage * stage_bytes, sB = sA + RW_STAGE_A;
-        for (int i = lane; i < n_a + 2 * n_bh; i += 32) {
-          if (i < n_a) {
-            const int pl = i >= d.nch, c = i - pl * d.nch;
-            const bf16* src = a.a.hi + (pl ? a.a.lo_off : 0) + ((long long)(d.a_chunk0 + c) * a.a.pitch + b0) * 8;
-            bulk_g2s(sA + pl * (8 * RW_A_PLANE) + c * RW_A_PLANE, src, a_bytes, full0 + 8 * stage);
-          } else {
-            const int j = i - n_a, pl = j >= n_bh, c = j - pl * n_bh;
-            const bf16* src = (pl ? a.w_lo : a.w_hi) + ((long long)(d.w_c0 + c) * a.w_pitch + d.w_row) * 8;
-            const uint32_t dst = (KIND == 2) ? sB + pl * 8192 + c * (N * 16) : sB + (pl * (N >> 3) + c) * 1024;
-            bulk_g2s(dst, src, b_bytes, full0 + 8 * stage);
-          }
-        }
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    const uint32_t idesc_n = make_idesc(N, false, !(KIND == 2));
-    const uint32_t idesc_cat = make_idesc(2 * N, false, true);
-    if (a.w_res) mbar_wait(wbar, 0);
+    const bool a_split = a.a_split != 0, w_res = a.w_res != 0;
+    const uint32_t a_pstride = (uint32_t)a.a.pitch * 16u, w_pstride = (uint32_t)a.w_pitch * 16u;
+    const char* a_hi = reinterpret_cast<const char*>(a.a.hi);
+    const char* a_lo = a_hi + a.a.lo_off * 2;
+    const char* w_hi = reinterpret_cast<const char*>(a.w_hi);
+    const char* w_lo = reinterpret_cast<const char*>(a.w_lo);
+    const int n_bh_fwd = N >> 3;
     int stage = 0; uint32_t phase = 0; int cnt = 0;
+    int u = (int)blockIdx.x / nbt, bt = (int)blockIdx.x - u * nbt;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, cnt++) {
-      const int u = tile / a.n_btiles;
-      const int buf = cnt & 1;
-      const uint32_t acc = tmem_base + buf * acc_cols;
-      mbar_wait(tempty0 + 8 * buf, ((cnt >> 1) & 1) ^ 1);
-      tc_fence_after();
-      ItState it; StageDesc d;
-      it_init<KIND>(a, u, it);
-      uint32_t accum = 0;
-      while (it_next<KIND>(a, it, d)) {
-        mbar_wait(full0 + 8 * stage, phase);
-        tc_fence_after();
-        if (lane == 0) {
+      const int b0 = bt * 128, nr = min(128, a.B - b0);
+      const uint32_t a_bytes = (uint32_t)nr * 16u, row_off = (uint32_t)b0 * 16u;
+      TileWalk tw; tw.init<KIND>(a, u, stages_sm, units_sm);
+      for (int s = 0; s < tw.ns; s++) {
+        if (stage != warp) { if (++stage == n_stages) { stage = 0; phase ^= 1; } continue; }
+        const StageDesc d = tw.get(s);
+        BP_TRACE(0, 1);
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        BP_TRACE(0, 2);
+        const int nch = (int)d.nch;
+        const int n_bh = w_res ? 0 : (KIND == 2 ? nch : n_bh_fwd);
+        const uint32_t b_bytes = (KIND == 2) ? (uint32_t)N * 16u : (uint32_t)nch * 128u;
+        const uint32_t fb = full0 + 8 * ((cnt & 1) * RW_MAX_STAGES + stage);
+        if (elect_one()) {
+#ifdef XTB_EXP_NO_LOAD
+          mbar_arrive(fb);
+#else
+          mbar_expect_tx(fb, a_bytes * (a_split ? 2 * nch : nch) + b_bytes * 2 * n_bh);
           const uint32_t sA = stage0 + (uint32_t)stage * stage_bytes, sB = sA + RW_STAGE_A;
-          const uint32_t sA_lo = sA + 8 * RW_A_PLANE;
-          for (int j = 0; j < (d.nch >> 1); j++) {
-            const uint64_t ah = make_desc(sA + j * 2 * RW_A_PLANE, RW_A_PLANE, 128);
-            if (KIND != 2) {
-              // W MN-major: rows k (16 per step), chunks along n; [hi | lo] chunk planes are adjacent
-              const uint64_t bw = a.w_res ? make_desc(wres + (uint32_t)(d.w_row + 16 * j) * 16, 128, (uint32_t)a.w_pitch * 16)
-                                          : make_desc(sB + j * 256, 128, 1024);
-              umma_bf16(acc, ah, bw, idesc_cat, accum);
-              if (a.a_split) umma_bf16(acc, make_desc(sA_lo + j * 2 * RW_A_PLANE, RW_A_PLANE, 128), bw, idesc_n, 1u);
-            } else {
-              // W K-major: rows = output feature, chunks along the reduction (2 per step)
-              uint64_t bh, bl;
-              if (a.w_res) {
-                const uint32_t off = ((uint32_t)(d.w_c0 + 2 * j) * a.w_pitch + d.w_row) * 16;
-                const uint32_t plane = (uint32_t)a.w_res_chunks * a.w_pitch * 16;
-                bh = make_desc(wres + off, (uint32_t)a.w_pitch * 16, 128);
-                bl = make_desc(wres + plane + off, (uint32_t)a.w_pitch * 16, 128);
-              } else {
-                bh = make_desc(sB + j * 2 * (N * 16), (uint32_t)N * 16, 128);
-                bl = make_desc(sB + 8192 + j * 2 * (N * 16), (uint32_t)N * 16, 128);
-              }
-              umma_bf16(acc, ah, bh, idesc_n, accum);
-              umma_bf16(acc, ah, bl, idesc_n, 1u);
-              if (a.a_split) umma_bf16(acc, make_desc(sA_lo + j * 2 * RW_A_PLANE, RW_A_PLANE, 128), bh, idesc_n, 1u);
-            }
-            accum = 1u;
+          const char* ah = a_hi + d.a_off + row_off;
+          for (int c = 0; c < nch; c++) bulk_g2s(sA + c * RW_A_PLANE, ah + (uint32_t)c * a_pstride, a_bytes, fb);
+          if (a_split) {
+            const char* al = a_lo + d.a_off + row_off;
+            for (int c = 0; c < nch; c++) bulk_g2s(sA + 8 * RW_A_PLANE + c * RW_A_PLANE, al + (uint32_t)c * a_pstride, a_bytes, fb);
           }
-          umma_commit(empty0 + 8 * stage);
+          if (!w_res) {
+            const char* wh = w_hi + d.w_off; const char* wl = w_lo + d.w_off;
+            if (KIND == 2) {
+              for (int c = 0; c < n_bh; c++) {
+                bulk_g2s(sB + c * (N * 16), wh + (uint32_t)c * w_pstride, b_bytes, fb);
+                bulk_g2s(sB + 8192 + c * (N * 16), wl + (uint32_t)c * w_pstride, b_bytes, fb);
+              }
+            } else {
+              for (int c = 0; c < n_bh; c++) {
+                bulk_g2s(sB + c * 1024, wh + (uint32_t)c * w_pstride, b_bytes, fb);
+                bulk_g2s(sB + (n_bh_fwd + c) * 1024, wl + (uint32_t)c * w_pstride, b_bytes, fb);
+              }
+            }
+          }
+#endif
         }
         __syncwarp();
+        BP_TRACE(0, 3);
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) umma_commit(tfull0 + 8 * buf);
-      __syncwarp();
+      u += du; bt += dbt;
+      if (bt >= nbt) { bt -= nbt; u++; }
+    }
+  } else if (warp < RW_E_WARP0) {
+    // ================= MMA issuers: warp m owns every second tile; converged warp, one elected lane issues ==========
+    {
+      const int mw = warp - RW_P_WARPS;
+      const uint32_t idesc_n = make_idesc(N, false, !(KIND == 2));
+      const uint32_t idesc_cat = make_idesc(2 * N, false, true);
+      const bool a_split = a.a_split != 0, w_res = a.w_res != 0;
+      // descriptor constant parts; the low 14 bits hold (shared address >> 4) and are advanced by plain adds
+      const uint64_t adesc_hi = make_desc(0, RW_A_PLANE, 128);
+      const uint64_t bdesc_hi = (KIND == 2) ? make_desc(0, (uint32_t)N * 16, 128) : make_desc(0, 128, 1024);
+      const uint32_t a_lo_add = (8 * RW_A_PLANE) >> 4, a_step = (2 * RW_A_PLANE) >> 4;
+      const uint32_t w_pstride = (uint32_t)a.w_pitch * 16u;
+      // resident weights: forward MN-major (LBO 128, SBO = pitch rows), data gradient K-major (LBO = pitch rows, SBO 128)
+      const uint64_t wdesc_hi = (KIND == 2) ? make_desc(0, w_pstride, 128) : make_desc(0, 128, w_pstride);
+      const uint32_t w_lo_add = ((uint32_t)a.w_res_chunks * w_pstride) >> 4;
+      const uint32_t b_step = (KIND == 2) ? (w_res ? (2 * w_pstride) >> 4 : (2u * N * 16u) >> 4) : (256 >> 4);
+      const uint32_t b_lo_add = w_res ? w_lo_add : (8192 >> 4);
+      const uint64_t b_const = w_res ? wdesc_hi : bdesc_hi;
+      if (w_res) mbar_wait(wbar, 0);
+      const uint32_t myfull = full0 + 8 * (mw * RW_MAX_STAGES);
+      uint32_t fphase = 0;                 // bit s: parity of the next completion of this warp's full barrier of slot s
+      int stage = 0; int cnt = 0;
+      int u = (int)blockIdx.x / nbt, bt = (int)blockIdx.x - u * nbt;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, cnt++) {
+        const int buf = cnt & 1;
+        const uint32_t acc = tmem_base + buf * acc_cols;
+        TileWalk tw; tw.init<KIND>(a, u, stages_sm, units_sm);
+        if (buf != mw) {       // the other warp's tile: only step the ring position over its stages
+          stage = (stage + tw.ns) % n_stages;
+          u += du; bt += dbt;
+          if (bt >= nbt) { bt -= nbt; u++; }
+          continue;
+        }
+        BP_TRACE(1, 10);
+        mbar_wait(tempty0 + 8 * buf, ((cnt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        BP_TRACE(1, 11);
+        uint32_t accum = 0;
+        for (int s = 0; s < tw.ns; s++) {
+          const StageDesc d = tw.get(s);
+          mbar_wait(myfull + 8 * stage, (fphase >> stage) & 1u);
+          fphase ^= 1u << stage;
+          tc_fence_after();
+          BP_TRACE(1, 12);
+          const uint32_t sA = stage0 + (uint32_t)stage * stage_bytes;
+          uint32_t a_lo32 = sA >> 4;
+          uint32_t b_lo32 = w_res ? (wres + d.w_off) >> 4 : (sA + RW_STAGE_A) >> 4;
+          const int ksteps = (int)d.nch >> 1;
+          if (elect_one()) {
+#ifndef XTB_EXP_NO_MMA
+            for (int j = 0; j < ksteps; j++) {
+              const uint64_t ah = adesc_hi | a_lo32, bh = b_const | b_lo32;
+              if (KIND != 2) {
+                umma_bf16(acc, ah, bh, idesc_cat, accum);                                   // A_hi x [W_hi | W_lo]
+                if (a_split) umma_bf16(acc, adesc_hi | (a_lo32 + a_lo_add), bh, idesc_n, 1u);   // A_lo x W_hi
+              } else {
+                umma_bf16(acc, ah, bh, idesc_n, accum);
+                umma_bf16(acc, ah, b_const | (b_lo32 + b_lo_add), idesc_n, 1u);
+                if (a_split) umma_bf16(acc, adesc_hi | (a_lo32 + a_lo_add), bh, idesc_n, 1u);
+              }
+              accum = 1u;
+              a_lo32 += a_step; b_lo32 += b_step;
+            }
+#endif
+            umma_commit(empty0 + 8 * stage);
+          }
+          accum = 1u;
+          __syncwarp();
+          BP_TRACE(1, 13);
+          if (++stage == n_stages) stage = 0;
+        }
+        if (elect_one()) umma_commit(tfull0 + 8 * buf);
+        __syncwarp();
+        u += du; bt += dbt;
+        if (bt >= nbt) { bt -= nbt; u++; }
+      }
     }
   } else {
-    // ================= epilogue (warps 2..5; warp & 3 = TMEM lane quarter) =================
-    const int q = warp & 3;
-    float dbacc[64];
+    // ================= epilogue: warps 2..9; warp & 3 = TMEM lane quarter, two warps per quarter split the columns ====
+    const int q = warp & 3, half = (warp - RW_E_WARP0) >> 2;
+    if (KIND == 0 && a.mode != 2 && tid >= RW_E_TID0 && tid < RW_E_TID0 + N) bias_sh[tid - RW_E_TID0] = a.bias[tid - RW_E_TID0];
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * RW_EPI_WARPS) : "memory");
+    float dbacc[32];
     if (KIND == 2) {
 #pragma unroll
-      for (int j = 0; j < 64; j++) dbacc[j] = 0.f;
+      for (int j = 0; j < 32; j++) dbacc[j] = 0.f;
     }
     const int b_pad = (a.B + 15) & ~15;
+    // columns of this warp: 16-column groups g with (g & 1) == half when N >= 32; the single group of N = 16 goes to half 0
+    const int n_groups = N >> 4;
+    const long long out_pstride = (long long)a.out.pitch * 8;      // elements between feature chunks
     int cnt = 0;
+    int u = (int)blockIdx.x / nbt, bt = (int)blockIdx.x - u * nbt;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, cnt++) {
-      const int u = tile / a.n_btiles, bt = tile - u * a.n_btiles;
       const int buf = cnt & 1;
       const int b = bt * 128 + q * 32 + lane;
       int oc0, z = 0;                          // first output chunk of the unit
       if (a.mode == 2) { const int nt = u % a.n_ntiles; z = u / a.n_ntiles; oc0 = nt * (N >> 3); }
       else oc0 = u * (N >> 3);
+      if (warp == RW_E_WARP0) BP_TRACE(2, 20);
       mbar_wait(tfull0 + 8 * buf, (cnt >> 1) & 1);
       tc_fence_after();
+      if (warp == RW_E_WARP0) BP_TRACE(2, 21);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * acc_cols;
+      // all TMEM loads of this warp first, one wait
+      uint32_t r0[2][16], r1[2][16];
 #pragma unroll
-      for (int c = 0; c < 64; c += 16) {
-        if (c < N) {
-          uint32_t r0[16], r1[16];
-          tmem_ld16_nowait(taddr + c, r0);
-          if (CAT) tmem_ld16_nowait(taddr + N + c, r1);
-          tmem_wait_ld();
+      for (int gi = 0; gi < 2; gi++) {
+        const int g = 2 * gi + half;
+        if (g < n_groups) {
+          tmem_ld16_nowait(taddr + 16 * g, r0[gi]);
+          if (CAT) tmem_ld16_nowait(taddr + N + 16 * g, r1[gi]);
+        }
+      }
+      tmem_wait_ld();
+#ifndef XTB_EXP_NO_EPI
+#pragma unroll
+      for (int gi = 0; gi < 2; gi++) {
+        const int g = 2 * gi + half;
+        if (g < n_groups) {
+          const int c = 16 * g;
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r0[i]) + (CAT ? __uint_as_float(r1[i]) : 0.f);
+          for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r0[gi][i]) + (CAT ? __uint_as_float(r1[gi][i]) : 0.f);
           if (KIND == 0) {
             if (b < a.B) {
               const int f0 = oc0 * 8 + c;
-              const int bo = (a.mode == 2) ? f0 : c;        // conv: bias per channel; dense: per feature
+              if (a.mode == 2) {
 #pragma unroll
-              for (int i = 0; i < 16; i++) v[i] = act_apply(a.act, a.alpha * v[i] + a.bias[bo + i]);
+                for (int i = 0; i < 16; i++) v[i] = act_apply(a.act, a.alpha * v[i] + a.bias[f0 + i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = act_apply(a.act, a.alpha * v[i] + bias_sh[c + i]);
+              }
               if (a.out.hi) {
+                bf16* p = a.out.hi + (long long)(oc0 + 2 * g) * out_pstride + (long long)b * 8;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                   uint4 hi, lo;
                   split8(v + 8 * h, hi, lo);
-                  bf16* p = a.out.hi + ((long long)(oc0 + (c >> 3) + h) * a.out.pitch + b) * 8;
-                  *reinterpret_cast<uint4*>(p) = hi;
-                  *reinterpret_cast<uint4*>(p + a.out.lo_off) = lo;
+                  *reinterpret_cast<uint4*>(p + h * out_pstride) = hi;
+                  *reinterpret_cast<uint4*>(p + h * out_pstride + a.out.lo_off) = lo;
                 }
               }
               if (a.out_f32) {
@@ -433,76 +540,84 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
               for (int i = 0; i < 4; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
           } else {
+            bf16* p = a.out.hi + (long long)(oc0 + 2 * g) * out_pstride + (long long)b * 8;
             if (b < a.B) {
+              const bf16* sp = a.src.hi + (long long)(oc0 + 2 * g) * ((long long)a.src.pitch * 8) + (long long)b * 8;
 #pragma unroll
               for (int h = 0; h < 2; h++) {
-                const long long e = ((long long)(oc0 + (c >> 3) + h) * a.out.pitch + b) * 8;
                 float* vv = v + 8 * h;
                 if (a.src_act == 1) {
                   float s[8];
-                  unpack8(*reinterpret_cast<const uint4*>(a.src.hi + ((long long)(oc0 + (c >> 3) + h) * a.src.pitch + b) * 8), s);
+                  unpack8(*reinterpret_cast<const uint4*>(sp + h * (long long)a.src.pitch * 8), s);
 #pragma unroll
                   for (int i = 0; i < 8; i++) vv[i] = s[i] > 0.f ? vv[i] : 0.f;
                 } else if (a.src_act == 2) {
                   float s[8], t[8];
-                  const bf16* sp = a.src.hi + ((long long)(oc0 + (c >> 3) + h) * a.src.pitch + b) * 8;
-                  unpack8(*reinterpret_cast<const uint4*>(sp), s);
-                  unpack8(*reinterpret_cast<const uint4*>(sp + a.src.lo_off), t);
+                  unpack8(*reinterpret_cast<const uint4*>(sp + h * (long long)a.src.pitch * 8), s);
+                  unpack8(*reinterpret_cast<const uint4*>(sp + h * (long long)a.src.pitch * 8 + a.src.lo_off), t);
 #pragma unroll
                   for (int i = 0; i < 8; i++) { float y = s[i] + t[i]; vv[i] *= 1.f - y * y; }
                 }
 #pragma unroll
-                for (int i = 0; i < 8; i++) dbacc[c + 8 * h + i] += vv[i];
+                for (int i = 0; i < 8; i++) dbacc[16 * gi + 8 * h + i] += vv[i];
                 if (a.accumulate) {
                   float s[8], t[8];
-                  unpack8(*reinterpret_cast<const uint4*>(a.out.hi + e), s);
-                  unpack8(*reinterpret_cast<const uint4*>(a.out.hi + a.out.lo_off + e), t);
+                  unpack8(*reinterpret_cast<const uint4*>(p + h * out_pstride), s);
+                  unpack8(*reinterpret_cast<const uint4*>(p + h * out_pstride + a.out.lo_off), t);
 #pragma unroll
                   for (int i = 0; i < 8; i++) vv[i] += s[i] + t[i];
                 }
                 uint4 hi, lo;
                 split8(vv, hi, lo);
-                *reinterpret_cast<uint4*>(a.out.hi + e) = hi;
-                *reinterpret_cast<uint4*>(a.out.hi + a.out.lo_off + e) = lo;
+                *reinterpret_cast<uint4*>(p + h * out_pstride) = hi;
+                *reinterpret_cast<uint4*>(p + h * out_pstride + a.out.lo_off) = lo;
               }
             } else if (b < b_pad && !a.accumulate) {
               // gradient rows up to the next multiple of 16 are read by the weight-gradient K loop: keep them zero
 #pragma unroll
               for (int h = 0; h < 2; h++) {
-                const long long e = ((long long)(oc0 + (c >> 3) + h) * a.out.pitch + b) * 8;
-                *reinterpret_cast<uint4*>(a.out.hi + e) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(a.out.hi + a.out.lo_off + e) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(p + h * out_pstride) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(p + h * out_pstride + a.out.lo_off) = make_uint4(0, 0, 0, 0);
               }
             }
           }
         }
       }
+#endif
       tc_fence_before();
       __syncwarp();
+      if (warp == RW_E_WARP0) BP_TRACE(2, 22);
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      u += du; bt += dbt;
+      if (bt >= nbt) { bt -= nbt; u++; }
     }
     if (KIND == 2 && a.db_part) {
-      // column sums of this CTA: lanes -> warps -> one row of the partial table (added in order by grad_reduce_kernel)
+      // column sums of this CTA: lanes -> the four quarter warps of each column owner -> one row of the partial table
 #pragma unroll
-      for (int j = 0; j < 64; j++) {
-        if (j < N) {
-          float s = dbacc[j];
+      for (int gi = 0; gi < 2; gi++) {
+        const int g = 2 * gi + half;
+        if (g < n_groups) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane == 0) red_sh[q][j] = s;
+          for (int i = 0; i < 16; i++) {
+            float s = dbacc[16 * gi + i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) red_sh[q][16 * g + i] = s;
+          }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = tid - 64;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * RW_EPI_WARPS) : "memory");
+      const int t = tid - RW_E_TID0;
       if (t < N) a.db_part[(long long)blockIdx.x * N + t] = (red_sh[0][t] + red_sh[1][t]) + (red_sh[2][t] + red_sh[3][t]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == RW_P_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
   }
+  BP_TRACE_DUMP;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -511,7 +626,8 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
 //   conv  : the KW*C features of one filter row at one output pixel are contiguous ("run"); accumulator r =
 //           (filter row ky, M tile mt) holds dW rows (ky, kx, ci); a CTA walks a subset of (output pixel, 64 samples)
 //           chunks, adds every filter row of each into its own TMEM accumulator and finally writes its partial sums
-//           part[cta][r][128][N]; chunks that fall outside the image (SAME padding) are read from a zero buffer
+//           part[cta][r][128][N]; chunks that fall outside the image (SAME padding) are read from a zero buffer.
+//           The (pixel, accumulator) -> operand mapping is a host-built table (WgEnt).
 //   dense : accumulator = (M tile r of the input features, N tile); the CTA reduces over all samples and stores dW.
 // ------------------------------------------------------------------------------------------
 constexpr int WG_KB = 64;                        // samples per K chunk
@@ -520,166 +636,201 @@ constexpr int WG_STAGE_A = 2 * 16 * WG_PLANE;    // hi + lo, 16 chunks
 constexpr int WG_STAGE_B = 2 * 8 * WG_PLANE;     // hi + lo, up to 8 chunks (N <= 64)
 constexpr int WG_STAGE = WG_STAGE_A + WG_STAGE_B;
 constexpr int WG_STAGES = 4;
+constexpr int WG_P_WARPS = 4;                   // producer warp p fills ring slot p
+constexpr int WG_M_WARPS = 2;                   // MMA warp m owns the accumulators with (r & 1) == m
+constexpr int WG_E_WARP0 = WG_P_WARPS + WG_M_WARPS;
+constexpr int WG_THREADS = 32 * (WG_E_WARP0 + 4);
+
+struct WgEnt {               // conv: one (output pixel, accumulator) pair (8 bytes, copied to shared memory)
+  int32_t x_chunk;           // first X feature chunk of the M tile (may be negative at a padded border)
+  uint16_t okmask;           // bit c: chunk c of the tile lies inside the image and inside the filter row
+  uint16_t valid;            // the filter row exists for this pixel
+};
 
 struct WgradArgs {
   BpT x; int x_split; BpT g; const bf16* zeros;
   int mode;                                      // 0 conv, 1 dense
-  int H, W, C, OH, OW, KH, KW, S, padT, padL;
-  int run_chunks, mts, R;                        // conv: chunks per filter row, M tiles per row, accumulators
+  const WgEnt* tab;                              // conv: [n_opix][R]
+  int R;                                         // conv: accumulators
   int N, B, n_bsub, n_opix;
   int x_chunks, r_tiles, n_ntiles;               // dense: feature chunks of X, M tiles, N tiles
   float* part;                                   // conv: partial sums [cta][R][128][N]
   float* dw; int ldw; int k_rows;                // dense: dW[k_rows][ldw]
 };
 
-__global__ void __launch_bounds__(RW_THREADS, 1)
+// stage source of one (K chunk, accumulator) pair
+struct WgWalk {
+  __device__ __forceinline__ static WgEnt get(const WgradArgs& a, const uint2* tab_sm, int opix, int r, int rt) {
+    if (a.mode == 0) {
+      const uint2 v = tab_sm[opix * a.R + r];
+      return WgEnt{(int32_t)v.x, (uint16_t)(v.y & 0xffffu), (uint16_t)(v.y >> 16)};
+    }
+    const int c0 = rt * 16, left = a.x_chunks - c0;
+    return WgEnt{c0, (uint16_t)(left >= 16 ? 0xffffu : ((1u << left) - 1u)), (uint16_t)1};
+  }
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
 bp_wgrad_kernel(const __grid_constant__ WgradArgs a, int tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 2];
+  __shared__ __align__(8) uint64_t bars[3 * WG_STAGES + 2];      // full barriers once per MMA warp (see bp_rows_kernel)
   __shared__ uint32_t tmem_slot;
+  uint2* tab_sm = reinterpret_cast<uint2*>(smem + WG_STAGES * WG_STAGE);     // conv: [n_opix][R] entries behind the stage ring
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[WG_STAGES]);
-  const uint32_t tfull = smem_u32(&bars[2 * WG_STAGES]), tempty = smem_u32(&bars[2 * WG_STAGES + 1]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2 * WG_STAGES]);
+  const uint32_t tfull = smem_u32(&bars[3 * WG_STAGES]), tempty = smem_u32(&bars[3 * WG_STAGES + 1]);
   if (tid == 0) {
-    for (int s = 0; s < WG_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(tfull, 1); mbar_init(tempty, 4);
+    for (int s = 0; s < WG_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(full0 + 8 * (WG_STAGES + s), 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, WG_M_WARPS); mbar_init(tempty, 4);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tmem_cols);
+  if (warp == WG_P_WARPS) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   pdl_wait();
   pdl_trigger();
+  const bool conv = a.mode == 0;
+  if (conv) {
+    const uint2* gt = reinterpret_cast<const uint2*>(a.tab);
+    for (int i = tid; i < a.n_opix * a.R; i += WG_THREADS) tab_sm[i] = __ldg(gt + i);
+    __syncthreads();
+  }
   const uint32_t tmem_base = tmem_slot;
   const uint32_t stage0 = smem_u32(smem);
   const int N = a.N;
   // work: conv = one pass over this CTA's (pixel, sample chunk) list; dense = tiles (r, ntile), each over all samples
-  const int n_tiles = a.mode == 0 ? 1 : a.r_tiles * a.n_ntiles;
-  const int n_kc = a.mode == 0 ? a.n_opix * a.n_bsub : a.n_bsub;
+  const int n_tiles = conv ? 1 : a.r_tiles * a.n_ntiles;
+  const int n_kc = conv ? a.n_opix * a.n_bsub : a.n_bsub;
+  const int tile0 = conv ? 0 : (int)blockIdx.x, tile_step = conv ? 1 : (int)gridDim.x;
+  const int kc0 = conv ? (int)blockIdx.x : 0, kc_step = conv ? (int)gridDim.x : 1;
+  const int n_r = conv ? a.R : 1;
+  const int dop = kc_step / a.n_bsub, dbs = kc_step - dop * a.n_bsub;      // (pixel, sample chunk) advance of one kc step
 
-  if (warp == 0) {
-    // ================= TMA producer =================
+  if (warp < WG_P_WARPS) {
+    // ================= TMA producers: warp p fills ring slot p; converged warp, one elected lane issues the copies ====
+    const uint32_t pstride_x = (uint32_t)a.x.pitch * 16u, pstride_g = (uint32_t)a.g.pitch * 16u;
+    const char* x_hi = reinterpret_cast<const char*>(a.x.hi);
+    const char* x_lo = x_hi + a.x.lo_off * 2;
+    const char* g_hi = reinterpret_cast<const char*>(a.g.hi);
+    const char* g_lo = g_hi + a.g.lo_off * 2;
+    const char* zeros = reinterpret_cast<const char*>(a.zeros);
+    const bool x_split = a.x_split != 0;
+    const int n_bh = N >> 3;
     int stage = 0; uint32_t phase = 0;
-    for (int tile = (a.mode == 0 ? 0 : blockIdx.x); tile < n_tiles; tile += (a.mode == 0 ? 1 : gridDim.x)) {
-      for (int kc = (a.mode == 0 ? blockIdx.x : 0); kc < n_kc; kc += (a.mode == 0 ? gridDim.x : 1)) {
-        int opix = 0, bs = kc, rt = 0, nt = 0;
-        if (a.mode == 0) { opix = kc / a.n_bsub; bs = kc - opix * a.n_bsub; }
-        else { rt = tile / a.n_ntiles; nt = tile - rt * a.n_ntiles; }
+    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+      const int rt = tile / a.n_ntiles, nt = tile - rt * a.n_ntiles;
+      int opix = conv ? kc0 / a.n_bsub : 0, bs = conv ? kc0 - opix * a.n_bsub : 0;
+      for (int kc = kc0; kc < n_kc; kc += kc_step) {
         const int b0 = bs * WG_KB;
-        const int nr16 = (min(WG_KB, a.B - b0) + 15) & ~15;
-        const uint32_t bytes = (uint32_t)nr16 * 16;
-        const int oy = opix / a.OW, ox = opix - oy * a.OW;
-        const int n_r = a.mode == 0 ? a.R : 1;
+        const uint32_t bytes = (uint32_t)((min(WG_KB, a.B - b0) + 15) & ~15) * 16u, row_off = (uint32_t)b0 * 16u;
+        const uint32_t g_off = (uint32_t)((conv ? opix : nt) * n_bh) * pstride_g + row_off;
         for (int r = 0; r < n_r; r++) {
-          int chunk0, xc0 = 0, mt = 0;          // first X feature chunk of the 16-chunk M tile
-          if (a.mode == 0) {
-            const int ky = r / a.mts; mt = r - ky * a.mts;
-            const int iy = oy * a.S - a.padT + ky;
-            if (iy < 0 || iy >= a.H) continue;
-            xc0 = ox * a.S - a.padL;
-            chunk0 = ((iy * a.W + xc0) * a.C) / 8 + mt * 16;     // may be negative at a padded border: per-chunk test below
-          } else chunk0 = rt * 16;
+          const WgEnt e = WgWalk::get(a, tab_sm, opix, r, rt);
+          if (!e.valid) continue;
+          if (stage != warp) { if (++stage == WG_STAGES) { stage = 0; phase ^= 1; } continue; }
+          const long long x_off = (long long)e.x_chunk * (long long)pstride_x + row_off;
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const int n_a = 16 * (a.x_split ? 2 : 1), n_bh = N >> 3;
-          if (lane == 0) mbar_expect_tx(full0 + 8 * stage, bytes * (n_a + 2 * n_bh));
-          __syncwarp();
-          const uint32_t sA = stage0 + (uint32_t)stage * WG_STAGE, sB = sA + WG_STAGE_A;
-          for (int i = lane; i < n_a + 2 * n_bh; i += 32) {
-            if (i < n_a) {
-              const int pl = i >= 16, c = i - pl * 16;
-              bool ok;
-              if (a.mode == 0) {
-                const int cj = mt * 16 + c;                       // chunk within the filter-row run
-                const int px = xc0 + (cj * 8) / a.C;              // input column of that chunk
-                ok = cj < a.run_chunks && px >= 0 && px < a.W;
-              } else ok = chunk0 + c < a.x_chunks;
-              const bf16* src = ok ? a.x.hi + (pl ? a.x.lo_off : 0) + ((long long)(chunk0 + c) * a.x.pitch + b0) * 8 : a.zeros;
-              bulk_g2s(sA + pl * (16 * WG_PLANE) + c * WG_PLANE, src, bytes, full0 + 8 * stage);
-            } else {
-              const int j = i - n_a, pl = j >= n_bh, c = j - pl * n_bh;
-              const int gc = (a.mode == 0 ? opix * (N >> 3) : nt * (N >> 3)) + c;
-              const bf16* src = a.g.hi + (pl ? a.g.lo_off : 0) + ((long long)gc * a.g.pitch + b0) * 8;
-              bulk_g2s(sB + pl * (8 * WG_PLANE) + c * WG_PLANE, src, bytes, full0 + 8 * stage);
+          const uint32_t fb = full0 + 8 * ((r & 1) * WG_STAGES + stage);
+          if (elect_one()) {
+            mbar_expect_tx(fb, bytes * ((x_split ? 32 : 16) + 2 * n_bh));
+            const uint32_t sA = stage0 + (uint32_t)stage * WG_STAGE, sB = sA + WG_STAGE_A;
+            const uint32_t mask = e.okmask;
+#pragma unroll 4
+            for (int c = 0; c < 16; c++)
+              bulk_g2s(sA + c * WG_PLANE, ((mask >> c) & 1u) ? x_hi + x_off + (long long)((uint32_t)c * pstride_x) : zeros, bytes, fb);
+            if (x_split) {
+#pragma unroll 4
+              for (int c = 0; c < 16; c++)
+                bulk_g2s(sA + (16 + c) * WG_PLANE, ((mask >> c) & 1u) ? x_lo + x_off + (long long)((uint32_t)c * pstride_x) : zeros, bytes, fb);
+            }
+            for (int c = 0; c < n_bh; c++) {
+              bulk_g2s(sB + c * WG_PLANE, g_hi + g_off + (uint32_t)c * pstride_g, bytes, fb);
+              bulk_g2s(sB + (8 + c) * WG_PLANE, g_lo + g_off + (uint32_t)c * pstride_g, bytes, fb);
             }
           }
+          __syncwarp();
           if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
+        if (conv) { opix += dop; bs += dbs; if (bs >= a.n_bsub) { bs -= a.n_bsub; opix++; } } else bs++;
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    const uint32_t idesc = make_idesc(N, true, true);
-    int stage = 0; uint32_t phase = 0; int cnt = 0;
-    for (int tile = (a.mode == 0 ? 0 : blockIdx.x); tile < n_tiles; tile += (a.mode == 0 ? 1 : gridDim.x), cnt++) {
-      mbar_wait(tempty, (cnt & 1) ^ 1);
-      tc_fence_after();
-      uint32_t touched = 0;
-      for (int kc = (a.mode == 0 ? blockIdx.x : 0); kc < n_kc; kc += (a.mode == 0 ? gridDim.x : 1)) {
-        int opix = 0, bs = kc;
-        if (a.mode == 0) { opix = kc / a.n_bsub; bs = kc - opix * a.n_bsub; }
-        const int b0 = bs * WG_KB;
-        const int ksteps = ((min(WG_KB, a.B - b0) + 15) & ~15) >> 4;
-        const int oy = opix / a.OW;
-        const int n_r = a.mode == 0 ? a.R : 1;
-        for (int r = 0; r < n_r; r++) {
-          if (a.mode == 0) {
-            const int iy = oy * a.S - a.padT + r / a.mts;
-            if (iy < 0 || iy >= a.H) continue;
-          }
-          mbar_wait(full0 + 8 * stage, phase);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sA = stage0 + (uint32_t)stage * WG_STAGE, sB = sA + WG_STAGE_A;
+  } else if (warp < WG_E_WARP0) {
+    // ================= MMA issuers: warp m owns the accumulators with (r & 1) == m ====================================
+    {
+      const int mw = warp - WG_P_WARPS;
+      const uint32_t idesc = make_idesc(N, true, true);
+      const bool x_split = a.x_split != 0;
+      const uint64_t desc_hi = make_desc(0, 128, WG_PLANE);      // MN-major operands: LBO 128 B, SBO = chunk plane
+      const uint32_t myfull = full0 + 8 * (mw * WG_STAGES);
+      uint32_t fphase = 0;
+      int stage = 0; int cnt = 0;
+      for (int tile = tile0; tile < n_tiles; tile += tile_step, cnt++) {
+        const int rt = tile / a.n_ntiles;
+        mbar_wait(tempty, (cnt & 1) ^ 1);
+        tc_fence_after();
+        uint32_t touched = 0;
+        int opix = conv ? kc0 / a.n_bsub : 0, bs = conv ? kc0 - opix * a.n_bsub : 0;
+        for (int kc = kc0; kc < n_kc; kc += kc_step) {
+          const int b0 = bs * WG_KB;
+          const int ksteps = ((min(WG_KB, a.B - b0) + 15) & ~15) >> 4;
+          for (int r = 0; r < n_r; r++) {
+            const WgEnt e = WgWalk::get(a, tab_sm, opix, r, rt);
+            if (!e.valid) continue;
+            if ((r & 1) != mw) { if (++stage == WG_STAGES) stage = 0; continue; }
+            mbar_wait(myfull + 8 * stage, (fphase >> stage) & 1u);
+            fphase ^= 1u << stage;
+            tc_fence_after();
+            const uint32_t sA = stage0 + (uint32_t)stage * WG_STAGE;
+            uint32_t a32 = sA >> 4, g32 = (sA + WG_STAGE_A) >> 4;
             const uint32_t acc = tmem_base + r * N;
             uint32_t accum = (touched >> r) & 1u;
-            for (int j = 0; j < ksteps; j++) {
-              const uint64_t ah = make_desc(sA + j * 256, 128, WG_PLANE);
-              const uint64_t gh = make_desc(sB + j * 256, 128, WG_PLANE);
-              const uint64_t gl = make_desc(sB + 8 * WG_PLANE + j * 256, 128, WG_PLANE);
-              umma_bf16(acc, ah, gh, idesc, accum);
-              umma_bf16(acc, ah, gl, idesc, 1u);
-              if (a.x_split) umma_bf16(acc, make_desc(sA + 16 * WG_PLANE + j * 256, 128, WG_PLANE), gh, idesc, 1u);
-              accum = 1u;
+            if (elect_one()) {
+              for (int j = 0; j < ksteps; j++) {
+                const uint64_t ah = desc_hi | a32, gh = desc_hi | g32;
+                umma_bf16(acc, ah, gh, idesc, accum);
+                umma_bf16(acc, ah, desc_hi | (g32 + ((8 * WG_PLANE) >> 4)), idesc, 1u);
+                if (x_split) umma_bf16(acc, desc_hi | (a32 + ((16 * WG_PLANE) >> 4)), gh, idesc, 1u);
+                accum = 1u;
+                a32 += 256 >> 4; g32 += 256 >> 4;
+              }
+              umma_commit(empty0 + 8 * stage);
             }
-            umma_commit(empty0 + 8 * stage);
+            __syncwarp();
+            touched |= 1u << r;
+            if (++stage == WG_STAGES) stage = 0;
           }
-          touched |= 1u << r;
-          __syncwarp();
-          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+          if (conv) { opix += dop; bs += dbs; if (bs >= a.n_bsub) { bs -= a.n_bsub; opix++; } } else bs++;
         }
+        if (elect_one()) umma_commit(tfull);
+        __syncwarp();
       }
-      if (lane == 0) umma_commit(tfull);
-      __syncwarp();
     }
   } else {
     // ================= epilogue =================
     const int q = warp & 3;
     const int m = q * 32 + lane;                 // accumulator row = feature within the M tile
     int cnt = 0;
-    for (int tile = (a.mode == 0 ? 0 : blockIdx.x); tile < n_tiles; tile += (a.mode == 0 ? 1 : gridDim.x), cnt++) {
-      mbar_wait(tfull, cnt & 1);
-      tc_fence_after();
-      // accumulators this CTA's chunk list reached (same walk as the producer / MMA roles)
-      uint32_t touched = a.mode == 0 ? 0u : 1u;
-      if (a.mode == 0) {
-        for (int kc = blockIdx.x; kc < n_kc; kc += gridDim.x) {
-          const int oy = (kc / a.n_bsub) / a.OW;
-          for (int r = 0; r < a.R; r++) {
-            const int iy = oy * a.S - a.padT + r / a.mts;
-            if (iy >= 0 && iy < a.H) touched |= 1u << r;
-          }
+    for (int tile = tile0; tile < n_tiles; tile += tile_step, cnt++) {
+      // accumulators this CTA's chunk list reaches (same walk as the producer / MMA roles), found while the main loop runs
+      uint32_t touched = conv ? 0u : 1u;
+      if (conv) {
+        int opix = kc0 / a.n_bsub, bs = kc0 - opix * a.n_bsub;
+        for (int kc = kc0; kc < n_kc; kc += kc_step) {
+          for (int r = 0; r < a.R; r++) if (WgWalk::get(a, tab_sm, opix, r, 0).valid) touched |= 1u << r;
+          opix += dop; bs += dbs; if (bs >= a.n_bsub) { bs -= a.n_bsub; opix++; }
         }
       }
-      const int n_r = a.mode == 0 ? a.R : 1;
-      const bool have_work = a.mode != 0 || (int)blockIdx.x < a.n_opix * a.n_bsub;
+      mbar_wait(tfull, cnt & 1);
+      tc_fence_after();
+      const bool have_work = !conv || (int)blockIdx.x < n_kc;
       for (int r = 0; r < n_r; r++) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + r * N;
         float* dst;
         bool ok;
-        if (a.mode == 0) {
+        if (conv) {
           dst = a.part + (((long long)blockIdx.x * a.R + r) * 128 + m) * N;
           ok = have_work;
         } else {
@@ -689,18 +840,19 @@ bp_wgrad_kernel(const __grid_constant__ WgradArgs a, int tmem_cols) {
           ok = k < a.k_rows;
         }
         const bool live = (touched >> r) & 1u;
+        uint32_t rr[4][16];
 #pragma unroll
-        for (int c = 0; c < 64; c += 16) {
-          if (c < N) {
-            uint32_t rr[16];
-            tmem_ld16_nowait(taddr + c, rr);
-            tmem_wait_ld();
-            if (ok) {
-              float4* o = reinterpret_cast<float4*>(dst + c);
+        for (int g = 0; g < 4; g++) if (16 * g < N) tmem_ld16_nowait(taddr + 16 * g, rr[g]);
+        tmem_wait_ld();
+        if (ok) {
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            if (16 * g < N) {
+              float4* o = reinterpret_cast<float4*>(dst + 16 * g);
 #pragma unroll
               for (int i = 0; i < 4; i++)
-                o[i] = live ? make_float4(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1]), __uint_as_float(rr[4 * i + 2]),
-                                          __uint_as_float(rr[4 * i + 3]))
+                o[i] = live ? make_float4(__uint_as_float(rr[g][4 * i]), __uint_as_float(rr[g][4 * i + 1]), __uint_as_float(rr[g][4 * i + 2]),
+                                          __uint_as_float(rr[g][4 * i + 3]))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
@@ -713,7 +865,7 @@ bp_wgrad_kernel(const __grid_constant__ WgradArgs a, int tmem_cols) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == WG_P_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
   }

@@ -58,6 +58,9 @@ class Stager {
     if (done_.size() < n) done_ = std::vector<std::atomic<int>>(n);
     for (size_t c = 0; c < n; c++) done_[c].store(0, std::memory_order_relaxed);
     const uint64_t g = gen_.load(std::memory_order_relaxed) + 1;
+    // close the claim counter first (generation g, index beyond any chunk count): a worker still holding the previous
+    // generation can no longer win a CAS against the old counter value while the job fields below change
+    next_.store((g << 32) | 0xffffffffu, std::memory_order_release);
     job_src_.store(s, std::memory_order_relaxed); job_bytes_.store(bytes, std::memory_order_relaxed);
     job_chunks_.store(n, std::memory_order_relaxed); job_seq_.store(seq_, std::memory_order_relaxed);
     size_t allowed = 0;
@@ -116,14 +119,19 @@ class Stager {
   }
 
   cudaError_t init() {
-    if (ring_) return cudaSuccess;
-    cudaError_t e = cudaHostAlloc((void**)&ring_, CHUNK * SLOTS, cudaHostAllocDefault);
-    if (e != cudaSuccess) { ring_ = nullptr; return e; }
-    for (int i = 0; i < SLOTS; i++) {
-      e = cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming);
-      if (e != cudaSuccess) return e;
-      used_[i] = false; owner_[i] = i;
+    if (inited_) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    if (!ring_) {
+      e = cudaHostAlloc((void**)&ring_, CHUNK * SLOTS, cudaHostAllocDefault);
+      if (e != cudaSuccess) { ring_ = nullptr; return e; }
     }
+    for (int i = n_events_; i < SLOTS; i++) {
+      e = cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;              // a later call resumes here: nothing half-initialised is used
+      used_[i] = false; owner_[i] = i;
+      n_events_ = i + 1;
+    }
+    inited_ = true;
     int nt = 4;
     if (const char* env = getenv("XTB_STAGE_THREADS")) nt = atoi(env);
     unsigned hw = std::thread::hardware_concurrency();
@@ -210,6 +218,8 @@ class Stager {
   std::atomic<size_t> job_bytes_{0}, job_chunks_{0}, job_seq_{0};
   size_t seq_ = 0;
   char* ring_ = nullptr;
+  bool inited_ = false;
+  int n_events_ = 0;
   cudaEvent_t ev_[SLOTS];
   bool used_[SLOTS];
   int owner_[SLOTS];

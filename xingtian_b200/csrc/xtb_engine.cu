@@ -18,6 +18,7 @@
 #include "rl_kernels.cuh"
 #include "stager.cuh"
 #include "bp_gemm.cuh"
+#include "comm.cuh"
 #include <cstdlib>
 #include <type_traits>
 
@@ -59,6 +60,70 @@ extern "C" long long xtb_launch_count(void) { return g_launches.load(); }
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- data-parallel communicator ---------------------------------------------------------------
+static NcclApi g_nccl;
+static xtb_comm* g_comm = nullptr;          // installed communicator: gradients are all-reduced inside the training loops
+extern "C" int xtb_comm_unique_id(const char* nccl_path, void* id128) {
+  if (!id128) return fail(XTB_ERR_ARG, "xtb_comm_unique_id: null pointer");
+  if (const char* err = g_nccl.load(nccl_path)) return fail(XTB_ERR_STATE, "cannot load NCCL: %s", err);
+  NcclUniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc) return fail(XTB_ERR_CUDA, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+  memcpy(id128, &id, sizeof id);
+  return XTB_OK;
+}
+extern "C" int xtb_comm_create(const char* nccl_path, const void* id128, int rank, int world, xtb_comm** out) {
+  if (!id128 || !out || world < 1 || rank < 0 || rank >= world) return fail(XTB_ERR_ARG, "xtb_comm_create: bad argument");
+  if (const char* err = g_nccl.load(nccl_path)) return fail(XTB_ERR_STATE, "cannot load NCCL: %s", err);
+  auto* c = new xtb_comm();
+  c->rank = rank; c->world = world;
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  int rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
+  if (rc) { delete c; return fail(XTB_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc)); }
+  cudaError_t e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming);
+  if (e != cudaSuccess) { g_nccl.CommDestroy(c->comm); delete c; return fail(XTB_ERR_CUDA, "xtb_comm_create: %s", cudaGetErrorString(e)); }
+  *out = c;
+  return XTB_OK;
+}
+extern "C" void xtb_comm_destroy(xtb_comm* c) {
+  if (!c) return;
+  if (g_comm == c) g_comm = nullptr;
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->fork) cudaEventDestroy(c->fork);
+  if (c->join) cudaEventDestroy(c->join);
+  delete c;
+}
+extern "C" int xtb_comm_world(const xtb_comm* c) { return c ? c->world : 1; }
+// NULL uninstalls.  While installed, the fused training loops scale losses/gradients by 1/(world * B_local), sum the
+// gradient bucket over ranks before the optimiser step and stay inside the CUDA graph.
+extern "C" int xtb_set_grad_comm(xtb_comm* c) { g_comm = c; return XTB_OK; }
+// sum `count` floats in place over the ranks of `c`, on `stream`
+extern "C" int xtb_comm_allreduce(xtb_comm* c, float* buf, long long count, void* stream) {
+  if (!c || !buf || count < 0) return fail(XTB_ERR_ARG, "xtb_comm_allreduce: bad argument");
+  if (count == 0 || c->world == 1) return XTB_OK;
+  int rc = g_nccl.AllReduce(buf, buf, (size_t)count, kNcclFloat, kNcclSum, c->comm, S(stream));
+  if (rc) return fail(XTB_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(rc));
+  return XTB_OK;
+}
+// Early bucket [off, off+count): forked onto the communicator's side stream at the current point of `stream`, so the
+// exchange overlaps whatever is enqueued on `stream` afterwards; comm_join() makes `stream` wait for it.
+static int comm_fork_allreduce(xtb_comm* c, float* buf, long long count, cudaStream_t st) {
+  CUDA_TRY(cudaEventRecord(c->fork, st));
+  CUDA_TRY(cudaStreamWaitEvent(c->side, c->fork, 0));
+  int rc = g_nccl.AllReduce(buf, buf, (size_t)count, kNcclFloat, kNcclSum, c->comm, c->side);
+  if (rc) return fail(XTB_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(rc));
+  CUDA_TRY(cudaEventRecord(c->join, c->side));
+  return XTB_OK;
+}
+static int comm_join(xtb_comm* c, cudaStream_t st) {
+  CUDA_TRY(cudaStreamWaitEvent(st, c->join, 0));
+  return XTB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // network
 // ------------------------------------------------------------------------------------------
@@ -89,7 +154,68 @@ struct LayerPlan {
   int n_fwd = 0, n_dg = 0;  // accumulator columns: forward (Cout / dense N tile), data gradient (Cin / dense K tile)
   int run_chunks = 0, mts = 0, R = 0;   // conv weight gradient: chunks per filter row, M tiles per row, accumulators
   size_t part_off = 0, dbpart_off = 0;  // workspace offsets of the partial-sum areas
+  // host-built stage walks of the tensor-core kernels (conv layers) and their workspace offsets
+  std::vector<bp::StageEnt> fwd_st, dg_st; std::vector<bp::UnitEnt> fwd_un, dg_un; std::vector<bp::WgEnt> wg_tab;
+  size_t fwd_st_off = 0, fwd_un_off = 0, dg_st_off = 0, dg_un_off = 0, wg_off = 0;
 };
+
+// The K-stage walk of every unit of a conv layer (see bp_rows_kernel): forward = per filter row the taps inside the
+// image are one contiguous feature run, cut into stages of <= 64 elements; data gradient = one stage per filter tap
+// whose output position exists.  Weight gradient: per (output pixel, accumulator) the first X chunk and which of the
+// 16 chunks of the M tile are real.
+static void build_conv_tables(LayerPlan& lp) {
+  const ConvGeom& q = lp.q;
+  const int Cout = lp.N;
+  for (int oy = 0; oy < q.OH; oy++)
+    for (int ox = 0; ox < q.OW; ox++) {
+      uint32_t first = (uint32_t)lp.fwd_st.size(), count = 0;
+      for (int ky = 0; ky < q.KH; ky++) {
+        int iy = oy * q.S - q.padT + ky;
+        if (iy < 0 || iy >= q.H) continue;
+        int x0 = ox * q.S - q.padL, xl = std::max(x0, 0), xh = std::min(x0 + q.KW, q.W);
+        if (xh <= xl) continue;
+        int chunk = ((iy * q.W + xl) * q.C) >> 3, rem = ((xh - xl) * q.C) >> 3, wrow = (ky * q.KW + (xl - x0)) * q.C;
+        while (rem > 0) {
+          int nch = std::min(8, rem);
+          lp.fwd_st.push_back(bp::StageEnt{(uint32_t)chunk, (uint16_t)wrow, (uint16_t)nch});
+          chunk += nch; rem -= nch; wrow += nch * 8; count++;
+        }
+      }
+      lp.fwd_un.push_back(first | (count << 24));
+    }
+  for (int iy = 0; iy < q.H; iy++)
+    for (int ix = 0; ix < q.W; ix++) {
+      uint32_t first = (uint32_t)lp.dg_st.size(), count = 0;
+      for (int t = 0; t < q.KH * q.KW; t++) {
+        int ky = t / q.KW, kx = t - ky * q.KW;
+        int ty = iy + q.padT - ky, tx = ix + q.padL - kx;
+        if (ty < 0 || tx < 0) continue;
+        int oy = ty / q.S, ox = tx / q.S;
+        if (oy * q.S != ty || ox * q.S != tx || oy >= q.OH || ox >= q.OW) continue;
+        lp.dg_st.push_back(bp::StageEnt{(uint32_t)(((oy * q.OW + ox) * Cout) >> 3), (uint16_t)(t * q.C), (uint16_t)(Cout >> 3)});
+        count++;
+      }
+      lp.dg_un.push_back(first | (count << 24));
+    }
+  for (int oy = 0; oy < q.OH; oy++)
+    for (int ox = 0; ox < q.OW; ox++)
+      for (int r = 0; r < lp.R; r++) {
+        int ky = r / lp.mts, mt = r - ky * lp.mts;
+        int iy = oy * q.S - q.padT + ky;
+        bp::WgEnt e{0, 0, 0};
+        if (iy >= 0 && iy < q.H) {
+          int xc0 = ox * q.S - q.padL;
+          long long chunk0 = ((long long)(iy * q.W + xc0) * q.C) / 8 + mt * 16;
+          e.x_chunk = (int32_t)chunk0;
+          for (int c = 0; c < 16; c++) {
+            int cj = mt * 16 + c, px = xc0 + (cj * 8) / q.C;
+            if (cj < lp.run_chunks && px >= 0 && px < q.W) e.okmask |= (uint16_t)(1u << c);
+          }
+          e.valid = 1;
+        }
+        lp.wg_tab.push_back(e);
+      }
+}
 
 struct PendingRed { bp::RedSeg s; };
 
@@ -303,6 +429,13 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
     }
     lp.dbpart_off = w; w += align_up((size_t)kSMs * 64 * sizeof(float), 256);
   }
+  for (auto& lp : net->L) if (lp.tc && lp.d.kind == XTB_CONV) {
+    build_conv_tables(lp);
+    auto place = [&](size_t bytes) { size_t o = w; w += align_up(bytes, 256); return o; };
+    lp.fwd_st_off = place(lp.fwd_st.size() * sizeof(bp::StageEnt)); lp.fwd_un_off = place(lp.fwd_un.size() * sizeof(bp::UnitEnt));
+    lp.dg_st_off = place(lp.dg_st.size() * sizeof(bp::StageEnt)); lp.dg_un_off = place(lp.dg_un.size() * sizeof(bp::UnitEnt));
+    lp.wg_off = place(lp.wg_tab.size() * sizeof(bp::WgEnt));
+  }
   // split-K partial sums of a dense forward: n_z slabs of [round16(B)][N] with n_z <= 148 / (N tiles * batch tiles) + 1
   net->splitk_off = w;
   {
@@ -365,6 +498,14 @@ extern "C" int xtb_net_bind_stream(xtb_net* net, float* params, float* grads, vo
   if (!net->blob_segs.empty())
     CUDA_TRY(cudaMemcpyAsync(net->ws + net->segs_off, net->blob_segs.data(), net->blob_segs.size() * sizeof(bp::BlobSeg),
                              cudaMemcpyHostToDevice, st));
+  for (const auto& lp : net->L) if (lp.tc && lp.d.kind == XTB_CONV) {
+    auto up = [&](size_t off, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(net->ws + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+    CUDA_TRY(up(lp.fwd_st_off, lp.fwd_st.data(), lp.fwd_st.size() * sizeof(bp::StageEnt)));
+    CUDA_TRY(up(lp.fwd_un_off, lp.fwd_un.data(), lp.fwd_un.size() * sizeof(bp::UnitEnt)));
+    CUDA_TRY(up(lp.dg_st_off, lp.dg_st.data(), lp.dg_st.size() * sizeof(bp::StageEnt)));
+    CUDA_TRY(up(lp.dg_un_off, lp.dg_un.data(), lp.dg_un.size() * sizeof(bp::UnitEnt)));
+    CUDA_TRY(up(lp.wg_off, lp.wg_tab.data(), lp.wg_tab.size() * sizeof(bp::WgEnt)));
+  }
   std::fill(net->f32_ok.begin(), net->f32_ok.end(), 0); std::fill(net->bp_ok.begin(), net->bp_ok.end(), 0);
   std::fill(net->gf32_ok.begin(), net->gf32_ok.end(), 0); std::fill(net->gbp_ok.begin(), net->gbp_ok.end(), 0);
   net->obs_bp_ok = false;
@@ -448,9 +589,10 @@ static cudaError_t launch_rows(bp::RowsArgs& a, cudaStream_t st) {
   { cudaError_t e0 = ensure_kernel_attrs(); if (e0 != cudaSuccess) return e0; }
   const int wres_bytes = a.w_res ? (int)align_up((size_t)2 * a.w_res_chunks * a.w_pitch * 16, 128) : 0;
   const int stage_bytes = bp::RW_STAGE_A + (a.w_res ? 0 : bp::RW_STAGE_B);
-  int n_stages = std::min(bp::RW_MAX_STAGES, (kMaxDynSmem - 128 - wres_bytes) / stage_bytes);
+  const int tab_bytes = a.mode == 2 ? 0 : (int)align_up((size_t)a.n_stage_ents * sizeof(bp::StageEnt) + (size_t)a.n_units * sizeof(bp::UnitEnt), 128);
+  int n_stages = std::min(bp::RW_MAX_STAGES, (kMaxDynSmem - 128 - wres_bytes - tab_bytes) / stage_bytes);
   if (n_stages < 2) return cudaErrorInvalidConfiguration;
-  const int smem = 128 + wres_bytes + n_stages * stage_bytes;
+  const int smem = 128 + wres_bytes + n_stages * stage_bytes + tab_bytes;
   const int acc = (KIND == 2 ? a.N : 2 * a.N);
   const int total = a.n_units * a.n_btiles;
   const int grid = std::min(total, kSMs);
@@ -460,15 +602,10 @@ static cudaError_t launch_rows(bp::RowsArgs& a, cudaStream_t st) {
 
 static cudaError_t launch_wgrad(const bp::WgradArgs& a, int grid, cudaStream_t st) {
   { cudaError_t e0 = ensure_kernel_attrs(); if (e0 != cudaSuccess) return e0; }
-  const int smem = 128 + bp::WG_STAGES * bp::WG_STAGE;
+  const int smem = 128 + bp::WG_STAGES * bp::WG_STAGE + (a.mode == 0 ? (int)align_up((size_t)a.n_opix * a.R * sizeof(bp::WgEnt), 128) : 0);
   const int cols = (a.mode == 0 ? a.R : 1) * a.N;
-  XLAUNCH(bp::bp_wgrad_kernel, grid, bp::RW_THREADS, smem, st, a, tmem_cols_for(cols));
+  XLAUNCH(bp::bp_wgrad_kernel, grid, bp::WG_THREADS, smem, st, a, tmem_cols_for(cols));
   return cudaPeekAtLastError();
-}
-
-static void fill_conv_geom(bp::RowsArgs& a, const ConvGeom& q, int cout) {
-  a.H = q.H; a.W = q.W; a.C = q.C; a.OH = q.OH; a.OW = q.OW; a.Cout = cout; a.KH = q.KH; a.KW = q.KW; a.S = q.S;
-  a.padT = q.padT; a.padL = q.padL;
 }
 
 // forward of a tensor-core layer.  want_f32: also store the fp32 row-major copy; want_bp: store the planes
@@ -490,7 +627,8 @@ static cudaError_t tc_forward(xtb_net* net, int i, int B, bool want_f32, bool wa
   *launches = 1;
   if (lp.d.kind == XTB_CONV) {
     a.mode = 0;
-    fill_conv_geom(a, lp.q, lp.N);
+    a.stages = (const bp::StageEnt*)(net->ws + lp.fwd_st_off); a.units = (const bp::UnitEnt*)(net->ws + lp.fwd_un_off);
+    a.n_stage_ents = (int)lp.fwd_st.size();
     a.w_res = lp.w_res; a.w_res_chunks = lp.N / 8;
     a.n_units = lp.q.OH * lp.q.OW;
     return launch_rows<0>(a, st);
@@ -533,7 +671,8 @@ static cudaError_t tc_dgrad(xtb_net* net, int i, int B, int accumulate, float* d
   a.out = gout_bp(net, s); a.src = out_bp(net, s); a.src_act = lp.src_act; a.accumulate = accumulate; a.db_part = db_part;
   if (lp.d.kind == XTB_CONV) {
     a.mode = 1;
-    fill_conv_geom(a, lp.q, lp.N);
+    a.stages = (const bp::StageEnt*)(net->ws + lp.dg_st_off); a.units = (const bp::UnitEnt*)(net->ws + lp.dg_un_off);
+    a.n_stage_ents = (int)lp.dg_st.size();
     a.w_res = lp.w_res; a.w_res_chunks = lp.N / 8;
     a.n_units = lp.q.H * lp.q.W;
   } else {
@@ -558,8 +697,8 @@ static cudaError_t tc_wgrad(xtb_net* net, int i, int B, cudaStream_t st) {
   if (lp.d.kind == XTB_CONV) {
     const ConvGeom& q = lp.q;
     a.mode = 0;
-    a.H = q.H; a.W = q.W; a.C = q.C; a.OH = q.OH; a.OW = q.OW; a.KH = q.KH; a.KW = q.KW; a.S = q.S; a.padT = q.padT; a.padL = q.padL;
-    a.run_chunks = lp.run_chunks; a.mts = lp.mts; a.R = lp.R; a.N = lp.N; a.n_opix = q.OH * q.OW;
+    a.tab = (const bp::WgEnt*)(net->ws + lp.wg_off);
+    a.R = lp.R; a.N = lp.N; a.n_opix = q.OH * q.OW; a.n_ntiles = 1;
     a.part = (float*)(net->ws + lp.part_off);
     const int grid = std::min(kSMs, a.n_opix * a.n_bsub);
     bp::RedSeg r;
@@ -589,6 +728,13 @@ extern "C" int xtb_net_sync_weights(xtb_net* net, void* stream) {
   LAUNCH_CHECK();
   return XTB_OK;
 }
+
+#ifdef XTB_BP_TRACE
+extern "C" int xtb_bp_trace_set(unsigned long long* buf) {
+  CUDA_TRY(cudaMemcpyToSymbol(bp::g_bp_trace, &buf, sizeof buf));
+  return XTB_OK;
+}
+#endif
 
 // ---- representation changes ------------------------------------------------------------------
 static int ensure_bp(xtb_net* net, int t, int B, bool grad, cudaStream_t st) {
@@ -987,7 +1133,7 @@ static int net_forward_impl(xtb_net* net, const float* params, const void* obs, 
 
 static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
                              const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads,
-                             unsigned bias_done_tensors = 0u, unsigned heads_bp_mask = 0u);
+                             unsigned bias_done_tensors = 0u, unsigned heads_bp_mask = 0u, xtb_comm* comm = nullptr);
 extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
                                 const int32_t* head_tensors, int n_heads, void* stream) {
   return net_backward_impl(net, obs, gather_idx, batch, head_tensors, n_heads, stream, 0u, true);
@@ -995,12 +1141,13 @@ extern "C" int xtb_net_backward(xtb_net* net, const void* obs, const int32_t* ga
 // head_tensors: tensors whose gradient was filled by the caller: fp32 row-major, or (bit set in heads_bp_mask) planes
 static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gather_idx, int batch,
                              const int32_t* head_tensors, int n_heads, void* stream, unsigned skip_mask, bool zero_grads,
-                             unsigned bias_done_tensors, unsigned heads_bp_mask) {
+                             unsigned bias_done_tensors, unsigned heads_bp_mask, xtb_comm* comm) {
   if (!net || !net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_net_backward: net not bound (grads required)");
   if (batch <= 0 || batch > net->max_batch) return fail(XTB_ERR_ARG, "batch out of range");
   cudaStream_t st = S(stream);
   const int nl = (int)net->L.size();
   std::vector<char> has_grad(nl + 1, 0), written(nl + 1, 0);
+  long long early_off = 0, early_cnt = 0;
   for (int t = 1; t <= nl; t++) net->gf32_ok[t] = net->gbp_ok[t] = 0;
   net->pending.clear();
   for (int h = 0; h < n_heads; h++) {
@@ -1031,6 +1178,13 @@ static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gathe
     if (!has_grad[t]) continue;   // tensor does not influence the loss
     int rc = op_wgrad(net, i, obs, gather_idx, batch, st, fuse_bias[t] != 0);
     if (rc) return rc;
+    // data parallel: a large dense weight gradient is final here (direct store) -- start summing it over ranks now, on
+    // the communicator's side stream, while the rest of the backward pass runs
+    if (comm && comm->world > 1 && early_cnt == 0 && lp.d.kind == XTB_DENSE && use_tc(lp) && (long long)lp.K * lp.N >= (1 << 16)) {
+      early_off = lp.w_off; early_cnt = (long long)lp.K * lp.N;
+      rc = comm_fork_allreduce(comm, net->grads + early_off, early_cnt, st);
+      if (rc) return rc;
+    }
     if (lp.d.src != 0) {
       int s = lp.d.src;
       rc = op_dgrad(net, i, written[s] ? 1 : 0, batch, st, fuse_bias[s] == 1);
@@ -1038,7 +1192,18 @@ static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gathe
       written[s] = 1; has_grad[s] = 1;
     }
   }
-  return flush_reductions(net, st);
+  int rc = flush_reductions(net, st);
+  if (rc || !comm || comm->world == 1) return rc;
+  // the rest of the bucket: everything before and after the early range, as one NCCL group
+  if (early_cnt == 0) return xtb_comm_allreduce(comm, net->grads, net->n_params, stream);
+  int nrc = g_nccl.GroupStart();
+  if (!nrc && early_off > 0) nrc = g_nccl.AllReduce(net->grads, net->grads, (size_t)early_off, kNcclFloat, kNcclSum, comm->comm, st);
+  const long long tail = net->n_params - (early_off + early_cnt);
+  if (!nrc && tail > 0)
+    nrc = g_nccl.AllReduce(net->grads + early_off + early_cnt, net->grads + early_off + early_cnt, (size_t)tail, kNcclFloat, kNcclSum, comm->comm, st);
+  int erc = g_nccl.GroupEnd();
+  if (nrc || erc) return fail(XTB_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc ? nrc : erc));
+  return comm_join(comm, st);
 }
 
 // Launch ONE kernel of one layer (0 = forward, 1 = weight gradient, 2 = data gradient, 3 = frame decode) on the
@@ -1294,7 +1459,7 @@ extern "C" long long xtb_graph_replay_count(void) { return g_graph_replays.load(
 // A captured graph bakes every kernel argument: the key carries everything that can change them.
 struct GraphKey {
   const void* net; const void* opt; const void* obs; const void* perm; const void* loss; int n, b, e;
-  const void* ro[5]; float hp[4]; int pi_t, v_t, fuse, tc; const void* ws;
+  const void* ro[5]; float hp[4]; int pi_t, v_t, fuse, tc; const void* ws; const void* comm;
   bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
 };
 struct GraphVal { cudaGraphExec_t exec; long long kernels; };
@@ -1365,17 +1530,17 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         LAUNCH_CHECK();
         int srcs[2] = {lpi.d.src, lv.d.src};
         unsigned hbp = (bp_pi ? (1u << lpi.d.src) : 0u) | (bp_v ? (1u << lv.d.src) : 0u);   // the fused kernel wrote planes there
-        rc = net_backward_impl(net, ro->obs, idx, mb, srcs, a.shared ? 1 : 2, stream, skip, false, bias_done, hbp);
+        rc = net_backward_impl(net, ro->obs, idx, mb, srcs, a.shared ? 1 : 2, stream, skip, false, bias_done, hbp, g_comm);
         if (rc) return rc;
       } else {
         rc = xtb_ppo_loss_grad(xtb_net_tensor(net, pi_t), xtb_net_tensor(net, v_t), idx, ro->action, ro->old_logp,
                                ro->adv, ro->old_v, ro->target_v, mb, adim, hp, inv_world / mb,
                                xtb_net_tensor_grad(net, pi_t), xtb_net_tensor_grad(net, v_t), loss_per_step + step, stream);
         if (rc) return rc;
-        rc = xtb_net_backward(net, ro->obs, idx, mb, heads, 2, stream);
+        rc = net_backward_impl(net, ro->obs, idx, mb, heads, 2, stream, 0u, true, 0u, 0u, g_comm);
         if (rc) return rc;
       }
-      if (g_grad_hook) {
+      if (g_grad_hook && !g_comm) {
         rc = g_grad_hook(g_grad_hook_user, net->grads, net->n_params, stream);
         if (rc) return fail(XTB_ERR_STATE, "gradient hook failed with %d", rc);
       }
@@ -1397,13 +1562,14 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
   if (pi_tensor < 1 || pi_tensor > nl || v_tensor < 1 || v_tensor > nl || net->tsize[v_tensor] != 1)
     return fail(XTB_ERR_ARG, "xtb_ppo_train: bad head tensors");
   float inv_world = 1.f;
-  if (g_grad_hook) {   // data-parallel: the hook sums gradients over ranks; every rank holds B/world samples
+  if (g_comm) inv_world = 1.f / g_comm->world;
+  else if (g_grad_hook) {   // data-parallel: the hook sums gradients over ranks; every rank holds B/world samples
     int world = 1;
     int rc = g_grad_hook(g_grad_hook_user, nullptr, 0, nullptr);   // query: returns world size when grads == NULL
     if (rc > 0) world = rc;
     inv_world = 1.f / world;
   }
-  if (!use_graph || g_grad_hook)
+  if (!use_graph || (g_grad_hook && !g_comm))
     return ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, inv_world, stream);
   StreamScope sc;
   int src = sc.begin(stream, true);
@@ -1414,13 +1580,13 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
   key.n = n_sample; key.b = batch_size; key.e = n_epoch;
   key.ro[0] = ro->action; key.ro[1] = ro->old_logp; key.ro[2] = ro->adv; key.ro[3] = ro->old_v; key.ro[4] = ro->target_v;
   key.hp[0] = hp->clip_ratio; key.hp[1] = hp->ent_coef; key.hp[2] = hp->vf_clip; key.hp[3] = hp->critic_coef;
-  key.pi_t = pi_tensor; key.v_t = v_tensor; key.fuse = g_fuse_heads; key.tc = g_tc_mode; key.ws = net->ws;
+  key.pi_t = pi_tensor; key.v_t = v_tensor; key.fuse = g_fuse_heads; key.tc = g_tc_mode; key.ws = net->ws; key.comm = g_comm;
   auto it = g_graphs.find(key);
   if (it == g_graphs.end()) {
     cudaStream_t st = sc.st;
     long long before = g_launches.load();
     CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, 1.f, (void*)st);
+    int rc = ppo_train_launch(net, opt, ro, n_sample, batch_size, n_epoch, perm, hp, pi_tensor, v_tensor, loss_per_step, inv_world, (void*)st);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     long long captured = g_launches.load() - before;
