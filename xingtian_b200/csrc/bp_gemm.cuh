@@ -298,14 +298,24 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();
-  pdl_trigger();
-  if (a.mode != 2) {      // tables are static data uploaded at bind time; every thread helps, one barrier
+  // Static inputs are fetched BEFORE the dependency wait, i.e. under the tail of the preceding kernel: the stage-walk
+  // tables never change after bind, and the weight blob of a conv layer was written at least two kernels back (by the
+  // blob refresh of the previous optimiser step; the layer's own operand producer sits in between), so it is complete
+  // by the time the previous kernel has passed its own wait and released this one.
+  if (a.mode != 2) {      // every thread helps, one barrier
     const uint2* gs = reinterpret_cast<const uint2*>(a.stages);
     for (int i = tid; i < a.n_stage_ents; i += RW_THREADS) stages_sm[i] = __ldg(gs + i);
     for (int i = tid; i < a.n_units; i += RW_THREADS) units_sm[i] = __ldg(a.units + i);
-    __syncthreads();
   }
+  if (warp == 0 && a.w_res && elect_one()) {
+    const uint32_t bytes = (uint32_t)a.w_res_chunks * a.w_pitch * 16;
+    mbar_expect_tx(wbar, 2 * bytes);
+    bulk_g2s(smem_u32(smem), a.w_hi, bytes, wbar);
+    bulk_g2s(smem_u32(smem) + bytes, a.w_lo, bytes, wbar);
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_slot;
   const uint32_t wres = smem_u32(smem);                  // resident weights: hi plane chunks then lo plane chunks
   const uint32_t stage0 = wres + (uint32_t)wres_bytes;
@@ -319,12 +329,6 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
 
   if (warp < RW_P_WARPS) {
     // ================= TMA producers: warp p fills ring slot p; converged warp, one elected lane issues the copies ====
-    if (warp == 0 && a.w_res && elect_one()) {
-      const uint32_t bytes = (uint32_t)a.w_res_chunks * a.w_pitch * 16;
-      mbar_expect_tx(wbar, 2 * bytes);
-      bulk_g2s(wres, a.w_hi, bytes, wbar);
-      bulk_g2s(wres + bytes, a.w_lo, bytes, wbar);
-    }
     const bool a_split = a.a_split != 0, w_res = a.w_res != 0;
     const uint32_t a_pstride = (uint32_t)a.a.pitch * 16u, w_pstride = (uint32_t)a.w_pitch * 16u;
     const char* a_hi = reinterpret_cast<const char*>(a.a.hi);
@@ -510,12 +514,22 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
           if (KIND == 0) {
             if (b < a.B) {
               const int f0 = oc0 * 8 + c;
+              float bb[16];
               if (a.mode == 2) {
+                const float4* bp4 = reinterpret_cast<const float4*>(a.bias + f0);
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = act_apply(a.act, a.alpha * v[i] + a.bias[f0 + i]);
+                for (int i = 0; i < 4; i++) { const float4 t4 = __ldg(bp4 + i); bb[4 * i] = t4.x; bb[4 * i + 1] = t4.y; bb[4 * i + 2] = t4.z; bb[4 * i + 3] = t4.w; }
               } else {
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = act_apply(a.act, a.alpha * v[i] + bias_sh[c + i]);
+                for (int i = 0; i < 16; i++) bb[i] = bias_sh[c + i];
+              }
+              if (a.act == 2) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = tanhf(a.alpha * v[i] + bb[i]);
+              } else {          // relu / linear without a branch per element
+                const float lo = a.act == 1 ? 0.f : -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = fmaxf(fmaf(a.alpha, v[i], bb[i]), lo);
               }
               if (a.out.hi) {
                 bf16* p = a.out.hi + (long long)(oc0 + 2 * g) * out_pstride + (long long)b * 8;
@@ -687,17 +701,16 @@ bp_wgrad_kernel(const __grid_constant__ WgradArgs a, int tmem_cols) {
     fence_barrier_init();
   }
   if (warp == WG_P_WARPS) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tmem_cols);
+  const bool conv = a.mode == 0;
+  if (conv) {             // static table: fetched under the tail of the preceding kernel
+    const uint2* gt = reinterpret_cast<const uint2*>(a.tab);
+    for (int i = tid; i < a.n_opix * a.R; i += WG_THREADS) tab_sm[i] = __ldg(gt + i);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   pdl_wait();
   pdl_trigger();
-  const bool conv = a.mode == 0;
-  if (conv) {
-    const uint2* gt = reinterpret_cast<const uint2*>(a.tab);
-    for (int i = tid; i < a.n_opix * a.R; i += WG_THREADS) tab_sm[i] = __ldg(gt + i);
-    __syncthreads();
-  }
   const uint32_t tmem_base = tmem_slot;
   const uint32_t stage0 = smem_u32(smem);
   const int N = a.N;
@@ -1005,6 +1018,47 @@ __global__ void bp_splitk_finish_kernel(const float* __restrict__ part, int n_z,
 // Weight blobs: for every tensor-core layer the kernel matrix W[K, N] as batch-planar W^T planes
 // blob[((n >> 3) * K + k') * 8 + (n & 7)], k' = space-to-depth row order for a stride-4 first layer.
 struct BlobSeg { long long w_off, blob_off; int K, N, s2d_k4; };
+// inverse of s2d_real_row: real HWIO row -> row of the space-to-depth ordered blob
+__host__ __device__ inline int s2d_blob_row(int k, int k4) {
+  const int c = k & 3, pix = k >> 2, x = pix % (4 * k4), y = pix / (4 * k4);
+  return (((y >> 2) * k4 + (x >> 2)) << 6) + ((y & 3) << 4) + ((x & 3) << 2) + c;
+}
+// Blob planes of the parameters at flat index j .. j+cnt-1 (cnt <= 4, same weight row, n % 4 == 0 when cnt == 4):
+// used by the optimiser kernel so that the blobs are refreshed by the same pass that updates the parameters.
+__device__ __forceinline__ void blob_store1(const BlobSeg* __restrict__ segs, int n_segs, bf16* __restrict__ hi, long long lo_off,
+                                            long long j, float p) {
+  for (int q = 0; q < n_segs; q++) {
+    const long long w0 = segs[q].w_off;
+    const int K = segs[q].K, N = segs[q].N;
+    if (j < w0 || j >= w0 + (long long)K * N) continue;
+    const int rel = (int)(j - w0), k = rel / N, n = rel - k * N;
+    const int kp = segs[q].s2d_k4 ? s2d_blob_row(k, segs[q].s2d_k4) : k;
+    bf16* o = hi + segs[q].blob_off + ((long long)(n >> 3) * K + kp) * 8 + (n & 7);
+    const bf16 h = __float2bfloat16_rn(p);
+    o[0] = h; o[lo_off] = __float2bfloat16_rn(p - __bfloat162float(h));
+    return;
+  }
+}
+__device__ __forceinline__ void blob_store4(const BlobSeg* __restrict__ segs, int n_segs, bf16* __restrict__ hi, long long lo_off,
+                                            long long j, const float p[4]) {
+  for (int q = 0; q < n_segs; q++) {
+    const long long w0 = segs[q].w_off, w1 = w0 + (long long)segs[q].K * segs[q].N;
+    if (j + 3 < w0 || j >= w1) continue;
+    const int K = segs[q].K, N = segs[q].N;
+    const int rel = (int)(j - w0), k = rel / N, n = rel - k * N;
+    if (j >= w0 && j + 3 < w1 && (n & 3) == 0) {          // the common case: four parameters of one weight row
+      const int kp = segs[q].s2d_k4 ? s2d_blob_row(k, segs[q].s2d_k4) : k;
+      bf16* o = hi + segs[q].blob_off + ((long long)(n >> 3) * K + kp) * 8 + (n & 7);
+      uint32_t h0, l0, h1, l1;
+      split2(p[0], p[1], h0, l0); split2(p[2], p[3], h1, l1);
+      *reinterpret_cast<uint2*>(o) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(o + lo_off) = make_uint2(l0, l1);
+    } else {
+      for (int i = 0; i < 4; i++) blob_store1(segs, n_segs, hi, lo_off, j + i, p[i]);
+    }
+    return;
+  }
+}
 __global__ void bp_wprep_kernel(const float* __restrict__ params, const BlobSeg* __restrict__ segs, bf16* __restrict__ hi,
                                 long long lo_off) {
   pdl_wait(); pdl_trigger();

@@ -2,13 +2,15 @@
 //   tf.train.AdamOptimizer + tf.clip_by_global_norm : xt/model/ppo/ppo.py:97-102,
 //                                                     xt/model/impala/impala_cnn_opt.py:198-217
 //   keras Adam(clipnorm)                            : xt/model/dqn/dqn_cnn.py:60
-// Three launches per step: sqnorm (per-segment sum of squares, one atomic per block), prep
-// (1 thread: clip scales, lr_t, beta powers, re-zero accumulators), adam (elementwise update).
+// Two launches per step: sqnorm (per-segment sum of squares, one atomic per block; the last block to finish computes
+// the clip scales, lr_t and the beta powers and re-zeroes the accumulators), adam (elementwise update that also
+// refreshes the batch-planar weight blobs of the tensor-core layers, bp_gemm.cuh).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bp_gemm.cuh"
 #include "launch.cuh"
 
 namespace xtb {
@@ -23,32 +25,8 @@ struct AdamHyper {          // lives in device memory too: a captured CUDA graph
   float lr, beta1, beta2, eps, clip;
 };
 
-__global__ void __launch_bounds__(OPT_THREADS)
-sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ blk_seg,
-              const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
-              double* __restrict__ norm_sq) {
-  pdl_wait(); pdl_trigger();
-  const float* p = g + blk_beg[blockIdx.x];
-  int n = blk_len[blockIdx.x];
-  float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += OPT_THREADS) { float v = p[i]; s = fmaf(v, v, s); }
-  __shared__ float red[OPT_THREADS / 32];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float t = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (threadIdx.x == 0) atomicAdd(norm_sq + blk_seg[blockIdx.x], (double)t);
-  }
-}
-
-__global__ void adam_prep_kernel(AdamState* st, const AdamHyper* __restrict__ hyp, double* norm_sq, float* seg_scale, int n_seg,
-                                 int clip_mode, float grad_scale) {
-  pdl_wait(); pdl_trigger();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void adam_prep(AdamState* st, const AdamHyper* hyp, double* norm_sq, float* seg_scale, int n_seg,
+                                          int clip_mode, float grad_scale) {
   const float clip = hyp->clip, lr = hyp->lr, beta1 = hyp->beta1, beta2 = hyp->beta2;
   double tot = 0.0;
   for (int s = 0; s < n_seg; s++) tot += norm_sq[s];
@@ -72,12 +50,44 @@ __global__ void adam_prep_kernel(AdamState* st, const AdamHyper* __restrict__ hy
   st->lr_t = lr * sqrtf(1.f - b2p) / (1.f - b1p);
 }
 
+// `ticket`: zero-initialised counter; the block that draws the last ticket sees every block's contribution
+__global__ void __launch_bounds__(OPT_THREADS)
+sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ blk_seg,
+              const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
+              double* __restrict__ norm_sq, unsigned int* __restrict__ ticket, AdamState* st, const AdamHyper* __restrict__ hyp,
+              float* seg_scale, int n_seg, int clip_mode, float grad_scale) {
+  pdl_wait(); pdl_trigger();
+  const float* p = g + blk_beg[blockIdx.x];
+  int n = blk_len[blockIdx.x];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += OPT_THREADS) { float v = p[i]; s = fmaf(v, v, s); }
+  __shared__ float red[OPT_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) {
+      atomicAdd(norm_sq + blk_seg[blockIdx.x], (double)t);
+      __threadfence();
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        __threadfence();
+        *ticket = 0;
+        adam_prep(st, hyp, norm_sq, seg_scale, n_seg, clip_mode, grad_scale);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(OPT_THREADS)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, const int* __restrict__ blk_seg,
             const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
             const float* __restrict__ seg_scale, const AdamState* __restrict__ st, const AdamHyper* __restrict__ hyp,
-            __nv_bfloat16* __restrict__ w_hi, long long w_lo_off) {
+            const bp::BlobSeg* __restrict__ bsegs, int n_bsegs, __nv_bfloat16* __restrict__ w_hi, long long w_lo_off) {
   pdl_wait(); pdl_trigger();
   const float beta1 = hyp->beta1, beta2 = hyp->beta2, eps = hyp->eps;
   long long beg = blk_beg[blockIdx.x];
@@ -103,15 +113,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     *reinterpret_cast<float4*>(m + j) = make_float4(mm[0], mm[1], mm[2], mm[3]);
     *reinterpret_cast<float4*>(v + j) = make_float4(vv[0], vv[1], vv[2], vv[3]);
     *reinterpret_cast<float4*>(p + j) = make_float4(pp[0], pp[1], pp[2], pp[3]);
-    if (w_hi) {   // keep the bf16 hi/lo planes of the weights current (tensor-core operands)
-      __nv_bfloat162 h01 = __floats2bfloat162_rn(pp[0], pp[1]), h23 = __floats2bfloat162_rn(pp[2], pp[3]);
-      __nv_bfloat162 l01 = __floats2bfloat162_rn(pp[0] - __low2float(h01), pp[1] - __high2float(h01));
-      __nv_bfloat162 l23 = __floats2bfloat162_rn(pp[2] - __low2float(h23), pp[3] - __high2float(h23));
-      uint2 hu = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
-      uint2 lu = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
-      *reinterpret_cast<uint2*>(w_hi + j) = hu;
-      *reinterpret_cast<uint2*>(w_hi + w_lo_off + j) = lu;
-    }
+    if (w_hi) bp::blob_store4(bsegs, n_bsegs, w_hi, w_lo_off, j, pp);   // weight blobs of the tensor-core layers
   }
   for (int i = nv + threadIdx.x; i < n; i += OPT_THREADS) {
     long long j = beg + i;
@@ -121,11 +123,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     m[j] = mm; v[j] = vv;
     float pn = p[j] - lr_t * mm / (sqrtf(vv) + eps);
     p[j] = pn;
-    if (w_hi) {
-      __nv_bfloat16 h = __float2bfloat16_rn(pn);
-      w_hi[j] = h;
-      w_hi[w_lo_off + j] = __float2bfloat16_rn(pn - __bfloat162float(h));
-    }
+    if (w_hi) bp::blob_store1(bsegs, n_bsegs, w_hi, w_lo_off, j, pn);
   }
 }
 

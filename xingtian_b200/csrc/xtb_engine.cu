@@ -1324,7 +1324,7 @@ struct xtb_adam {
   int clip_mode = 0, n_seg = 0, n_blk = 0;
   float *m = nullptr, *v = nullptr;
   int* blk_seg = nullptr; long long* blk_beg = nullptr; int* blk_len = nullptr;
-  double* norm_sq = nullptr; float* seg_scale = nullptr; AdamState* st = nullptr; AdamHyper* hyp = nullptr;
+  double* norm_sq = nullptr; float* seg_scale = nullptr; AdamState* st = nullptr; AdamHyper* hyp = nullptr; unsigned int* ticket = nullptr;
 };
 
 extern "C" int xtb_adam_create(long long count, float lr, float beta1, float beta2, float eps, int clip_mode,
@@ -1358,12 +1358,14 @@ extern "C" int xtb_adam_create(long long count, float lr, float beta1, float bet
   chk(cudaMalloc(&o->seg_scale, o->n_seg * sizeof(float)));
   chk(cudaMalloc(&o->st, sizeof(AdamState)));
   chk(cudaMalloc(&o->hyp, sizeof(AdamHyper)));
+  chk(cudaMalloc(&o->ticket, sizeof(unsigned int)));
   if (e == cudaSuccess) {
     chk(cudaMemcpy(o->blk_seg, bseg.data(), o->n_blk * sizeof(int), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(o->blk_beg, bbeg.data(), o->n_blk * sizeof(long long), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(o->blk_len, blen.data(), o->n_blk * sizeof(int), cudaMemcpyHostToDevice));
     chk(cudaMemset(o->norm_sq, 0, o->n_seg * sizeof(double)));
     chk(cudaMemcpy(o->st, &init, sizeof init, cudaMemcpyHostToDevice));
+    chk(cudaMemset(o->ticket, 0, sizeof(unsigned int)));
     AdamHyper hy{lr, beta1, beta2, eps, clip};
     chk(cudaMemcpy(o->hyp, &hy, sizeof hy, cudaMemcpyHostToDevice));
     chk(cudaMemset(m, 0, count * sizeof(float)));
@@ -1378,31 +1380,30 @@ extern "C" void xtb_adam_destroy(xtb_adam* o) {
   if (!o) return;
   drop_graphs_of(o);
   cudaFree(o->blk_seg); cudaFree(o->blk_beg); cudaFree(o->blk_len);
-  cudaFree(o->norm_sq); cudaFree(o->seg_scale); cudaFree(o->st); cudaFree(o->hyp);
+  cudaFree(o->norm_sq); cudaFree(o->seg_scale); cudaFree(o->st); cudaFree(o->hyp); cudaFree(o->ticket);
   delete o;
 }
 
-static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream);
+static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream, xtb_net* net);
 extern "C" int xtb_adam_step(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream) {
-  return adam_step_impl(o, params, grads, grad_scale, stream);
+  return adam_step_impl(o, params, grads, grad_scale, stream, nullptr);
 }
-// optimiser step on a network's bound parameters, then the weight blobs of its tensor-core layers are refreshed
+// optimiser step on a network's bound parameters; the same kernel refreshes the weight blobs of its tensor-core layers
 extern "C" int xtb_adam_step_net(xtb_adam* o, xtb_net* net, float grad_scale, void* stream) {
   if (!net || !net->ws || !net->params || !net->grads) return fail(XTB_ERR_STATE, "xtb_adam_step_net: net not bound");
   if (!o || o->count != net->n_params) return fail(XTB_ERR_ARG, "xtb_adam_step_net: optimiser/net size mismatch");
-  int rc = adam_step_impl(o, net->params, net->grads, grad_scale, stream);
-  if (rc) return rc;
-  return xtb_net_sync_weights(net, stream);
+  return adam_step_impl(o, net->params, net->grads, grad_scale, stream, net);
 }
-static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream) {
+static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream, xtb_net* net) {
   if (!o || !params || !grads) return fail(XTB_ERR_ARG, "xtb_adam_step: null pointer");
   cudaStream_t st = S(stream);
-  XLAUNCH(sqnorm_kernel, o->n_blk, OPT_THREADS, 0, st, grads, o->blk_seg, o->blk_beg, o->blk_len, o->norm_sq);
+  XLAUNCH(sqnorm_kernel, o->n_blk, OPT_THREADS, 0, st, grads, o->blk_seg, o->blk_beg, o->blk_len, o->norm_sq, o->ticket, o->st,
+          (const AdamHyper*)o->hyp, o->seg_scale, o->n_seg, o->clip_mode, grad_scale);
   LAUNCH_CHECK();
-  XLAUNCH(adam_prep_kernel, 1, 32, 0, st, o->st, (const AdamHyper*)o->hyp, o->norm_sq, o->seg_scale, o->n_seg, o->clip_mode, grad_scale);
-  LAUNCH_CHECK();
+  const bool blobs = net && !net->blob_segs.empty();
   XLAUNCH(adam_kernel, o->n_blk, OPT_THREADS, 0, st, params, grads, o->m, o->v, o->blk_seg, o->blk_beg, o->blk_len,
-                                                o->seg_scale, o->st, (const AdamHyper*)o->hyp, (__nv_bfloat16*)nullptr, 0LL);
+          o->seg_scale, o->st, (const AdamHyper*)o->hyp, blobs ? (const bp::BlobSeg*)(net->ws + net->segs_off) : nullptr,
+          blobs ? (int)net->blob_segs.size() : 0, blobs ? (__nv_bfloat16*)(net->ws + net->blob_off) : nullptr, blobs ? net->blob_elems : 0LL);
   LAUNCH_CHECK();
   return XTB_OK;
 }
