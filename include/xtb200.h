@@ -161,6 +161,20 @@ int xtb_dqn_loss_grad(const float* q, const float* q_next_target, const float* q
                       int adim, float gamma, float inv_count, float* dq, float* y_out,
                       float* loss_out, void* stream);
 
+/* Same target/loss with the options BASELINE.json's north_star names (defaults = the reference): rows may be indexed
+ * through idx (minibatch rows of a replay ring); disc != NULL is a per-row bootstrap discount (gamma^n of an n-step
+ * return, 0 = the window hit a terminal step); huber_delta > 0 selects the Huber loss instead of the squared error. */
+int xtb_dqn_td_loss_grad(const float* q, const float* q_next_target, const float* q_next_online, const int32_t* idx,
+                         const int32_t* action, const float* reward, const uint8_t* done, const float* disc, int batch,
+                         int adim, float gamma, float huber_delta, float inv_count, float* dq, float* y_out,
+                         float* loss_out, void* stream);
+/* n-step returns over env-major trajectories [n_env][n_step] (north_star "n-step TD-target kernel"; the reference's
+ * DQN is 1-step, xt/algorithm/dqn/dqn.py:86-97): ret = sum_{k<m} gamma^k r_{t+k}, m = steps to the first terminal
+ * (inclusive), n, or the end of the segment; disc = gamma^m or 0 after a terminal; last = row whose next-state
+ * bootstraps; done_n = window contains a terminal. */
+int xtb_nstep_returns(const float* reward, const uint8_t* done, int n_env, int n_step, int n, float gamma, float* ret,
+                      float* disc, int32_t* last, uint8_t* done_n, void* stream);
+
 /* Keras model.train_on_batch(states, y) with loss='mse' (xt/model/model.py:77-82,
  * xt/model/dqn/dqn_cnn.py:60-61): loss = mean over B*A of (q-y)^2, dq = 2*(q-y)*inv_count. */
 int xtb_mse_loss_grad(const float* q, const float* y, int batch, int adim, float inv_count, float* dq,
@@ -202,6 +216,21 @@ typedef struct xtb_ppo_rollout {
 int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* ro, int n_sample,
                   int batch_size, int n_epoch, const int32_t* perm, const xtb_ppo_hyper* hp,
                   int pi_tensor, int v_tensor, float* loss_per_step, int use_graph, void* stream);
+
+/* ImpalaCnnOpt.train (xt/model/impala/impala_cnn_opt.py:251-265) as one captured step: forward over n_sample =
+ * k*step_len env-major rows (rows gather_idx[b] of obs when non-NULL), in-graph V-trace + summed losses, backward,
+ * clip_by_global_norm + Adam.  *loss_out += loss (device float). */
+int xtb_impala_train(xtb_net* net, xtb_adam* opt, const void* obs, const int32_t* gather_idx, const float* bp_logits,
+                     const int32_t* action, const uint8_t* done, const float* reward, int n_sample, int step_len,
+                     float gamma, int logit_tensor, int base_tensor, float* loss_out, int use_graph, void* stream);
+/* DQN.train (xt/algorithm/dqn/dqn.py:61-103) as one captured step over rows idx[0..n_sample) of a device replay ring:
+ * target forward on next_obs, optional double-DQN online forward (qn_o != NULL), online forward on obs, TD target +
+ * loss gradient (see xtb_dqn_td_loss_grad for disc / huber_delta), backward, per-tensor clip + Adam.
+ * qn_t, qn_o: scratch [n_sample, adim].  *loss_out += loss. */
+int xtb_dqn_train(xtb_net* net, xtb_net* target, xtb_adam* opt, const void* obs, const void* next_obs,
+                  const int32_t* idx, const int32_t* action, const float* reward, const uint8_t* done,
+                  const float* disc, int n_sample, float gamma, float huber_delta, int q_tensor, float* qn_t,
+                  float* qn_o, float* loss_out, int use_graph, void* stream);
 
 /* Rollout inference: for t in [0,n_step): forward over n_env observations (row e of step t is
  * obs[step_idx[t*n_env+e]], NULL = rows t*n_env..), sample actions with Philox(seed, *offset_dev + t), and

@@ -262,6 +262,143 @@ def test_dqn_train_matches_oracle():
     assert abs(l1 - 0.25) < 0.05
 
 
+def test_impala_c3_config_size_step_matches_oracle():
+    """C3 shapes through the plugin: E=64 envs deliver T=128-step trajectories, BATCH_SIZE=512 = 4 trajectories per SGD
+    step (T' = 127 after drop_last inside the V-trace); two captured steps vs the oracle learner."""
+    import xingtian_b200 as xb
+    S, k = 128, 8
+    info = {"actor": {"model_name": "ImpalaCnnOpt", "state_dim": [84, 84, 4], "input_dtype": "uint8", "state_mean": 0.0,
+                      "state_std": 255.0, "action_dim": 4, "max_batch": 512,
+                      "model_config": {"LR": 0.0005, "sample_batch_step": S, "grad_norm_clip": 40.0, "init_seed": 3}}}
+    alg = xb.alg_builder("IMPALAOpt", info, alg_cfg(instance_num=64, prepare_times_per_train=1, train_per_checkpoint=1, BATCH_SIZE=512))
+    w0 = alg.get_weights()
+    arch = orc.impala_cnn_arch()
+    ref = orc.ImpalaLearner(arch, w0, lr=0.0005, grad_norm_clip=40.0, sample_batch_step=S)
+    ro = orc.synth_ppo_rollout(21, k, S)
+    for i in range(k):
+        sl = slice(i * S, (i + 1) * S)
+        alg.prepare_data(dict(cur_state=ro["obs"][sl], logit=ro["logits"][sl], action=ro["action"][sl], reward=ro["reward"][sl], done=ro["done"][sl]))
+    loss = alg.train()
+    ref_losses = []
+    for s0 in range(0, k * S, 512):
+        sl = slice(s0, s0 + 512)
+        ref_losses.append(ref.train(ro["obs"][sl], [ro["logits"][sl], ro["action"][sl], ro["done"][sl], ro["reward"][sl]]))
+    print("impala C3 loss", loss, np.mean(ref_losses))
+    assert abs(loss - np.mean(ref_losses)) < 5e-3 * max(1.0, abs(np.mean(ref_losses)))
+    w1, r1 = alg.get_weights(), ref.weights()
+    upd = np.concatenate([(w1[k_] - w0[k_]).ravel() for k_ in w0]); rupd = np.concatenate([(r1[k_] - w0[k_]).ravel() for k_ in w0])
+    print("impala C3 update l2 rel", l2_rel(upd, rupd))
+    assert l2_rel(upd, rupd) < 5e-2
+
+
+def test_dqn_c4_config_size_step_matches_oracle():
+    """C4 shapes through the plugin: batch 512 out of a device replay ring, two captured steps vs the oracle learner."""
+    import random
+    import xingtian_b200 as xb
+    info = {"actor": {"model_name": "DqnCnn", "state_dim": [84, 84, 4], "action_dim": 4, "max_batch": 512,
+                      "model_config": {"LR": 0.00015, "init_seed": 5}}}
+    alg = xb.alg_builder("DQN", info, alg_cfg(instance_num=2, prepare_times_per_train=4, learning_starts=40, BUFFER_SIZE=1024,
+                                              BATCH_SIZE=512, TARGET_UPDATE_FREQ=1000))
+    w0 = alg.get_weights()
+    arch = orc.dqn_cnn_arch()
+    ref = orc.DqnLearner(arch, w0, lr=0.00015, clipnorm=10.0, target_update_freq=1000)
+    rng = np.random.default_rng(0)
+    n = 768
+    s = rng.integers(0, 256, (n, 84, 84, 4), dtype=np.uint8); s2 = rng.integers(0, 256, (n, 84, 84, 4), dtype=np.uint8)
+    a = rng.integers(0, 4, n); r = np.sign(rng.standard_normal(n)); d = rng.random(n) < 0.1
+    alg.prepare_data(dict(cur_state=s, action=a, reward=r, next_state=s2, done=d))
+    for step in range(2):
+        random.seed(step)
+        loss = alg.train()
+        random.seed(step)
+        picks = random.sample(range(n), 512)
+        ref_loss = ref.train(s[picks], a[picks], r[picks], s2[picks], d[picks])
+        print("dqn C4 step", step, loss, ref_loss)
+        assert abs(loss - ref_loss) < 5e-3 * max(1.0, abs(ref_loss)), step
+    w1, r1 = alg.get_weights(), ref.weights()
+    upd = np.concatenate([(w1[k] - w0[k]).ravel() for k in w0]); rupd = np.concatenate([(r1[k] - w0[k]).ravel() for k in w0])
+    print("dqn C4 update l2 rel", l2_rel(upd, rupd))
+    assert l2_rel(upd, rupd) < 5e-2
+
+
+def _nstep_ref(reward, done, n, gamma):
+    """numpy restatement of the n-step return (north_star extension; not in the reference): window stops at the first
+    terminal step (inclusive), after n steps, or at the end of the segment."""
+    T = len(reward)
+    ret = np.zeros(T, np.float64); disc = np.zeros(T, np.float64); last = np.zeros(T, np.int64); dn = np.zeros(T, bool)
+    for t in range(T):
+        acc, g, k, term = 0.0, 1.0, 0, False
+        while k < n and t + k < T:
+            acc += g * reward[t + k]; g *= gamma
+            if done[t + k]:
+                term = True; k += 1; break
+            k += 1
+        ret[t], disc[t], last[t], dn[t] = acc, (0.0 if term else g), t + k - 1, term
+    return ret, disc, last, dn
+
+
+@pytest.mark.parametrize("E,T,n", [(1, 64, 3), (5, 33, 1), (3, 40, 5)])
+def test_nstep_returns_kernel(E, T, n):
+    from xingtian_b200 import capi
+    from xingtian_b200.engine import _ptr, stream_ptr
+    rng = np.random.default_rng(E * 100 + T + n)
+    rew = rng.normal(0, 1, (E, T)).astype(np.float32); done = rng.random((E, T)) < 0.1
+    rd, dd = torch.from_numpy(rew).cuda(), torch.from_numpy(done.view(np.uint8)).cuda()
+    ret = torch.empty(E, T, device="cuda"); disc = torch.empty(E, T, device="cuda")
+    last = torch.empty(E, T, dtype=torch.int32, device="cuda"); dn = torch.empty(E, T, dtype=torch.uint8, device="cuda")
+    capi.check(capi.lib().xtb_nstep_returns(_ptr(rd), _ptr(dd), E, T, n, 0.99, _ptr(ret), _ptr(disc), _ptr(last), _ptr(dn), stream_ptr()))
+    for e in range(E):
+        r_ret, r_disc, r_last, r_dn = _nstep_ref(rew[e], done[e], n, 0.99)
+        assert rel_err(ret[e].cpu().numpy(), r_ret) < 1e-5 and rel_err(disc[e].cpu().numpy(), r_disc, floor=1.0) < 1e-6
+        np.testing.assert_array_equal(last[e].cpu().numpy() - e * T, r_last)
+        np.testing.assert_array_equal(dn[e].cpu().numpy().astype(bool), r_dn)
+
+
+def test_dqn_nstep_huber_step_matches_numpy():
+    """north_star extension (ns1): N_STEP=3 replay + Huber loss, one SGD step vs a torch-CPU restatement built on the
+    oracle's network; the default configuration (1-step, mse) is covered by test_dqn_train_matches_oracle."""
+    import random
+    import xingtian_b200 as xb
+    info = {"actor": {"model_name": "DqnCnn", "state_dim": [84, 84, 4], "action_dim": 4, "model_config": {"LR": 0.00015, "init_seed": 5}}}
+    alg = xb.alg_builder("DQN", info, alg_cfg(instance_num=1, prepare_times_per_train=4, learning_starts=8, BUFFER_SIZE=256,
+                                              BATCH_SIZE=32, TARGET_UPDATE_FREQ=1000, N_STEP=3, HUBER_DELTA=1.0))
+    assert alg.n_step == 3 and alg.huber_delta == 1.0
+    w0 = alg.get_weights()
+    arch = orc.dqn_cnn_arch()
+    rng = np.random.default_rng(1)
+    T = 64
+    s = rng.integers(0, 256, (T, 84, 84, 4), dtype=np.uint8); s2 = rng.integers(0, 256, (T, 84, 84, 4), dtype=np.uint8)
+    a = rng.integers(0, 4, T); r = rng.normal(0, 2, T).astype(np.float32); d = rng.random(T) < 0.1
+    alg.prepare_data(dict(cur_state=s, action=a, reward=r, next_state=s2, done=d))
+    ret, disc, last, dn = _nstep_ref(r, d, 3, 0.99)
+    random.seed(0)
+    loss = alg.train()
+    random.seed(0)
+    picks = random.sample(range(T), 32)
+    params = {k: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in w0.items()}
+    with torch.no_grad():
+        tq = orc.forward(arch, {k: torch.from_numpy(v) for k, v in w0.items()}, s2[last[picks]])[0].numpy()
+    y = np.where(dn[picks], ret[picks], ret[picks] + disc[picks] * tq.max(1)).astype(np.float32)
+    q = orc.forward(arch, params, s[picks])[0]
+    qa = q[torch.arange(32), torch.from_numpy(a[picks])]
+    diff = qa - torch.from_numpy(y)
+    hub = torch.where(diff.abs() <= 1.0, 0.5 * diff * diff, diff.abs() - 0.5)
+    ref_loss = hub.sum() / (32 * 4)
+    assert abs(loss - float(ref_loss)) < 5e-3 * max(1.0, abs(float(ref_loss))), (loss, float(ref_loss))
+    ref_loss.backward()
+    ref_p = [p.detach().clone() for p in params.values()]
+    opt = orc.TFAdam(ref_p, 0.00015, eps=1e-7)
+    grads = []
+    for p in params.values():
+        g = p.grad; nn = float(g.norm())
+        grads.append(g * (10.0 / nn) if nn > 10.0 else g)
+    opt.step(grads)
+    w1 = alg.get_weights()
+    upd = np.concatenate([(w1[k] - w0[k]).ravel() for k in w0])
+    rupd = np.concatenate([(rp.numpy() - w0[k]).ravel() for rp, k in zip(ref_p, w0)])
+    assert l2_rel(upd, rupd) < 5e-2, l2_rel(upd, rupd)
+
+
 def test_rollout_infer_graph_matches_per_step_predict():
     """The T-step graph-captured rollout inference equals T separate predict calls under the same Philox
     stream, and replays draw fresh noise (device-side offset counter)."""

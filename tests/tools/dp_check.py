@@ -37,8 +37,9 @@ def fill(alg, shards):
 
 perms = [np.stack([np.random.default_rng(1000 * r + e).permutation(N) for e in range(EPOCHS)]).astype(np.int32) for r in range(world)]
 # ---- data-parallel run
+dp_first = None
 alg = make_alg(BL)
-dp = engine.GradAllReduce(alg.actor.net)
+dp = engine.GradAllReduce(alg.actor.net) if os.environ.get("XTB_DP") == "hook" else engine.GradComm()
 fill(alg, [rank])
 loss_dp = alg.actor.train_device(N, perm=perms[rank])
 trace_dp = torch.tensor(alg.actor.last_losses, device="cuda")

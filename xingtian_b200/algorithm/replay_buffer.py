@@ -37,7 +37,8 @@ class DeviceReplayBuffer(object):
         self._alloc = 0
         self.count = 0      # valid entries
         self.head = 0       # next write slot
-        self.obs = self.next_obs = self.action = self.reward = self.done = None
+        self.obs = self.next_obs = self.action = self.reward = self.done = self.disc = None
+        self.keep_disc = False   # n-step replay: per-transition bootstrap discount
 
     def _grow(self, need):
         if need <= self._alloc:
@@ -53,19 +54,28 @@ class DeviceReplayBuffer(object):
         self.action = mk((new,), torch.int32, self.action)
         self.reward = mk((new,), torch.float32, self.reward)
         self.done = mk((new,), torch.uint8, self.done)
+        if self.keep_disc:
+            self.disc = mk((new,), torch.float32, self.disc)
         self._alloc = new
 
     def size(self):
         return self.count
 
-    def add_batch(self, obs, action, reward, next_obs, done):
+    def add_batch(self, obs, action, reward, next_obs, done, disc=None):
+        """Arrays may be numpy (host) or torch tensors already on the device."""
         n = len(action)
         np_dt = np.uint8 if self.obs_dtype == torch.uint8 else np.float32
-        obs = torch.from_numpy(np.ascontiguousarray(obs, np_dt)).to(self.device, non_blocking=True)
-        nxt = torch.from_numpy(np.ascontiguousarray(next_obs, np_dt)).to(self.device, non_blocking=True)
-        act = torch.from_numpy(np.ascontiguousarray(action, np.int32).reshape(-1)).to(self.device)
-        rew = torch.from_numpy(np.ascontiguousarray(reward, np.float32).reshape(-1)).to(self.device)
-        don = torch.from_numpy(np.ascontiguousarray(done, np.bool_).reshape(-1).view(np.uint8)).to(self.device)
+        def up(x, dt, flat=True):
+            if torch.is_tensor(x):
+                return x.to(self.device).reshape(-1) if flat else x.to(self.device)
+            a = np.ascontiguousarray(x, dt)
+            return torch.from_numpy(a.reshape(-1) if flat else a).to(self.device, non_blocking=not flat)
+        obs = up(obs, np_dt, flat=False)
+        nxt = up(next_obs, np_dt, flat=False)
+        act = up(action, np.int32)
+        rew = up(reward, np.float32)
+        don = done.reshape(-1) if torch.is_tensor(done) else torch.from_numpy(np.ascontiguousarray(done, np.bool_).reshape(-1).view(np.uint8)).to(self.device)
+        dsc = up(disc, np.float32) if disc is not None else None
         done_n = 0
         while done_n < n:
             self._grow(min(self.capacity, self.head + (n - done_n)))
@@ -74,6 +84,8 @@ class DeviceReplayBuffer(object):
             src = slice(done_n, done_n + k)
             self.obs[sl].copy_(obs[src]); self.next_obs[sl].copy_(nxt[src])
             self.action[sl].copy_(act[src]); self.reward[sl].copy_(rew[src]); self.done[sl].copy_(don[src])
+            if self.keep_disc and dsc is not None:
+                self.disc[sl].copy_(dsc[src])
             self.head = (self.head + k) % self.capacity
             self.count = min(self.capacity, self.count + k)
             done_n += k

@@ -358,17 +358,24 @@ __global__ void vtrace_kernel(const float* __restrict__ tp_logits, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
-// DQN 1-step TD target + Keras 'mse' (mean over B*A) gradient
+// DQN TD target + loss gradient.  Reference semantics (xt/algorithm/dqn/dqn.py:79-97 + Keras 'mse', mean over B*A):
+// y = r (+ gamma * max_a' Q_target(s') unless done), loss = mean (Q - y)^2 over B*A with only the taken action non-zero.
+// Extensions named by BASELINE.json's north_star, off by default:
+//   disc != NULL : per-sample bootstrap discount (gamma^n of an n-step return built by nstep_kernel; 0 = terminated)
+//   huber > 0    : Huber loss with that delta instead of the squared error (gradient clip(diff, -delta, delta))
+//   idx != NULL  : action / reward / done / disc are indexed through idx (minibatch rows of a replay ring)
 // ------------------------------------------------------------------------------------------
 __global__ void dqn_loss_kernel(const float* __restrict__ q, const float* __restrict__ qn_t,
-                                const float* __restrict__ qn_o, const int32_t* __restrict__ action,
-                                const float* __restrict__ reward, const uint8_t* __restrict__ done,
-                                int B, int A, float gamma, float inv_count, float* __restrict__ dq,
+                                const float* __restrict__ qn_o, const int32_t* __restrict__ idx,
+                                const int32_t* __restrict__ action, const float* __restrict__ reward,
+                                const uint8_t* __restrict__ done, const float* __restrict__ disc,
+                                int B, int A, float gamma, float huber, float inv_count, float* __restrict__ dq,
                                 float* __restrict__ y_out, float* __restrict__ loss_out) {
   pdl_wait(); pdl_trigger();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float lsum = 0.f;
   if (b < B) {
+    const int r = idx ? idx[b] : b;
     const float* t = qn_t + (long long)b * A;
     float mq;
     if (qn_o) {
@@ -380,14 +387,44 @@ __global__ void dqn_loss_kernel(const float* __restrict__ q, const float* __rest
       mq = t[0];
       for (int i = 1; i < A; i++) mq = fmaxf(mq, t[i]);
     }
-    float y = done[b] ? reward[b] : reward[b] + gamma * mq;
-    int a = action[b];
+    const float g = disc ? disc[r] : gamma;
+    float y = done[r] ? reward[r] : reward[r] + g * mq;
+    int a = action[r];
     float diff = q[(long long)b * A + a] - y;
-    for (int i = 0; i < A; i++) dq[(long long)b * A + i] = (i == a) ? 2.f * diff * inv_count : 0.f;
+    float grad, l;
+    if (huber > 0.f) {
+      const float ad = fabsf(diff);
+      l = ad <= huber ? 0.5f * diff * diff : huber * (ad - 0.5f * huber);
+      grad = fminf(fmaxf(diff, -huber), huber);
+    } else { l = diff * diff; grad = 2.f * diff; }
+    for (int i = 0; i < A; i++) dq[(long long)b * A + i] = (i == a) ? grad * inv_count : 0.f;
     if (y_out) y_out[b] = y;
-    lsum = diff * diff * inv_count;
+    lsum = l * inv_count;
   }
   block_atomic_add(lsum, loss_out);
+}
+
+// n-step returns over env-major trajectories [E][T] (north_star: "n-step TD-target kernel over a device-resident rollout
+// buffer"): R_t = sum_{k<m} gamma^k r_{t+k}, m = steps until the first done (inclusive) or n or the end of the segment;
+// disc_t = gamma^m, or 0 when the window ended in a terminal step; last_t = t + m - 1 (row whose next-state bootstraps);
+// done_n_t = 1 when the window contains a terminal step.  One thread per (env, t); rows of a warp are consecutive t.
+__global__ void nstep_kernel(const float* __restrict__ reward, const uint8_t* __restrict__ done, int E, int T, int n, float gamma,
+                             float* __restrict__ ret, float* __restrict__ disc, int32_t* __restrict__ last, uint8_t* __restrict__ done_n) {
+  pdl_wait(); pdl_trigger();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E * T) return;
+  const int e = i / T, t = i - e * T;
+  float acc = 0.f, g = 1.f;
+  int k = 0; bool term = false;
+  for (; k < n && t + k < T; k++) {
+    acc = fmaf(g, reward[e * T + t + k], acc);
+    g *= gamma;
+    if (done[e * T + t + k]) { term = true; k++; break; }
+  }
+  ret[i] = acc;
+  disc[i] = term ? 0.f : g;
+  last[i] = i + k - 1;
+  done_n[i] = term ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------

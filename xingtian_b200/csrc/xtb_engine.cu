@@ -455,6 +455,7 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
 }
 
 static void drop_graphs_of(const void* obj);
+static void drop_step_graphs_of(const void* obj);
 extern "C" void xtb_net_destroy(xtb_net* net) {
   if (!net) return;
   drop_graphs_of(net);
@@ -1294,14 +1295,29 @@ extern "C" int xtb_vtrace_loss_grad(const float* tp_logits, const float* baselin
   return XTB_OK;
 }
 
+extern "C" int xtb_dqn_td_loss_grad(const float* q, const float* q_next_target, const float* q_next_online, const int32_t* idx,
+                                    const int32_t* action, const float* reward, const uint8_t* done, const float* disc, int batch,
+                                    int adim, float gamma, float huber_delta, float inv_count, float* dq, float* y_out,
+                                    float* loss_out, void* stream) {
+  if (!q || !q_next_target || !action || !reward || !done || !dq || !loss_out) return fail(XTB_ERR_ARG, "xtb_dqn_td_loss_grad: null pointer");
+  if (batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_dqn_td_loss_grad: bad sizes");
+  XLAUNCH(dqn_loss_kernel, (batch + 127) / 128, 128, 0, S(stream), q, q_next_target, q_next_online, idx, action, reward, done, disc,
+          batch, adim, gamma, huber_delta, inv_count, dq, y_out, loss_out);
+  LAUNCH_CHECK();
+  return XTB_OK;
+}
 extern "C" int xtb_dqn_loss_grad(const float* q, const float* q_next_target, const float* q_next_online,
                                  const int32_t* action, const float* reward, const uint8_t* done, int batch,
                                  int adim, float gamma, float inv_count, float* dq, float* y_out,
                                  float* loss_out, void* stream) {
-  if (!q || !q_next_target || !action || !reward || !done || !dq || !loss_out) return fail(XTB_ERR_ARG, "xtb_dqn_loss_grad: null pointer");
-  if (batch <= 0 || adim <= 0) return fail(XTB_ERR_ARG, "xtb_dqn_loss_grad: bad sizes");
-  XLAUNCH(dqn_loss_kernel, (batch + 127) / 128, 128, 0, S(stream), q, q_next_target, q_next_online, action, reward, done,
-                                                              batch, adim, gamma, inv_count, dq, y_out, loss_out);
+  return xtb_dqn_td_loss_grad(q, q_next_target, q_next_online, nullptr, action, reward, done, nullptr, batch, adim, gamma, 0.f,
+                              inv_count, dq, y_out, loss_out, stream);
+}
+extern "C" int xtb_nstep_returns(const float* reward, const uint8_t* done, int n_env, int n_step, int n, float gamma, float* ret,
+                                 float* disc, int32_t* last, uint8_t* done_n, void* stream) {
+  if (!reward || !done || !ret || !disc || !last || !done_n) return fail(XTB_ERR_ARG, "xtb_nstep_returns: null pointer");
+  if (n_env <= 0 || n_step <= 0 || n <= 0) return fail(XTB_ERR_ARG, "xtb_nstep_returns: bad sizes");
+  XLAUNCH(nstep_kernel, (n_env * n_step + 127) / 128, 128, 0, S(stream), reward, done, n_env, n_step, n, gamma, ret, disc, last, done_n);
   LAUNCH_CHECK();
   return XTB_OK;
 }
@@ -1607,6 +1623,129 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
 }
 
 // ------------------------------------------------------------------------------------------
+// fused IMPALA / DQN learner steps (graph-captured like xtb_ppo_train; gradients all-reduced when a communicator is set)
+// ------------------------------------------------------------------------------------------
+struct StepKey {
+  const void* p[12]; int i[8]; float f[4];
+  bool operator<(const StepKey& o) const { return memcmp(this, &o, sizeof(StepKey)) < 0; }
+};
+static std::map<StepKey, GraphVal> g_step_graphs;
+
+static void drop_step_graphs_of(const void* obj) {
+  for (auto it = g_step_graphs.begin(); it != g_step_graphs.end();) {
+    if (it->first.p[0] == obj || it->first.p[1] == obj || it->first.p[11] == obj) { cudaGraphExecDestroy(it->second.exec); it = g_step_graphs.erase(it); } else ++it;
+  }
+}
+
+template <class F>
+static int run_step_graph(const StepKey& key, int use_graph, void* stream, F&& launch) {
+  if (!use_graph) return launch(stream);
+  StreamScope sc;
+  int src = sc.begin(stream, true);
+  if (src) return src;
+  auto it = g_step_graphs.find(key);
+  if (it == g_step_graphs.end()) {
+    cudaStream_t st = sc.st;
+    long long before = g_launches.load();
+    CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = launch((void*)st);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    long long captured = g_launches.load() - before;
+    g_launches.store(before);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    it = g_step_graphs.emplace(key, GraphVal{exec, captured}).first;
+  }
+  CUDA_TRY(cudaGraphLaunch(it->second.exec, sc.st));
+  g_launches.fetch_add(it->second.kernels, std::memory_order_relaxed);
+  g_graph_replays.fetch_add(1, std::memory_order_relaxed);
+  return sc.end();
+}
+
+// ImpalaCnnOpt.train (xt/model/impala/impala_cnn_opt.py:251-265): forward over n = k * step_len env-major samples,
+// V-trace + summed losses (vtrace_kernel), backward, clip + Adam.  With a communicator the losses are sums over the
+// GLOBAL batch, so no rescaling: gradients are summed over ranks.  loss_out: device float, accumulated (+=).
+extern "C" int xtb_impala_train(xtb_net* net, xtb_adam* opt, const void* obs, const int32_t* gather_idx, const float* bp_logits,
+                                const int32_t* action, const uint8_t* done, const float* reward, int n_sample, int step_len,
+                                float gamma, int logit_tensor, int base_tensor, float* loss_out, int use_graph, void* stream) {
+  if (!net || !opt || !obs || !bp_logits || !action || !done || !reward || !loss_out) return fail(XTB_ERR_ARG, "xtb_impala_train: null pointer");
+  if (!net->ws || !net->grads) return fail(XTB_ERR_STATE, "xtb_impala_train: net not bound");
+  const int nl = (int)net->L.size();
+  if (logit_tensor < 1 || logit_tensor > nl || base_tensor < 1 || base_tensor > nl || net->tsize[base_tensor] != 1)
+    return fail(XTB_ERR_ARG, "xtb_impala_train: bad head tensors");
+  if (n_sample <= 0 || n_sample > net->max_batch || step_len < 2 || n_sample % step_len) return fail(XTB_ERR_ARG, "xtb_impala_train: bad sizes");
+  const int adim = net->tsize[logit_tensor];
+  if (adim > MAX_ADIM) return fail(XTB_ERR_ARG, "xtb_impala_train: action dim too large");
+  StepKey key;
+  memset(&key, 0, sizeof key);
+  key.p[0] = net; key.p[1] = opt; key.p[2] = obs; key.p[3] = gather_idx; key.p[4] = bp_logits; key.p[5] = action; key.p[6] = done;
+  key.p[7] = reward; key.p[8] = loss_out; key.p[9] = net->ws; key.p[10] = g_comm;
+  key.i[0] = n_sample; key.i[1] = step_len; key.i[2] = logit_tensor; key.i[3] = base_tensor; key.i[4] = g_tc_mode; key.i[5] = 1;
+  key.f[0] = gamma;
+  return run_step_graph(key, use_graph, stream, [&](void* st) -> int {
+    int rc = net_forward_impl(net, nullptr, obs, gather_idx, n_sample, st, 0u, (1u << logit_tensor) | (1u << base_tensor));
+    if (rc) return rc;
+    rc = xtb_vtrace_loss_grad(xtb_net_tensor(net, logit_tensor), xtb_net_tensor(net, base_tensor), bp_logits, action, done, reward,
+                              n_sample / step_len, step_len, adim, gamma, xtb_net_tensor_grad(net, logit_tensor),
+                              xtb_net_tensor_grad(net, base_tensor), nullptr, nullptr, loss_out, st);
+    if (rc) return rc;
+    int heads[2] = {logit_tensor, base_tensor};
+    rc = net_backward_impl(net, obs, gather_idx, n_sample, heads, 2, st, 0u, true, 0u, 0u, g_comm);
+    if (rc) return rc;
+    return xtb_adam_step_net(opt, net, 1.f, st);
+  });
+}
+
+// DQN.train (xt/algorithm/dqn/dqn.py:61-103) on a device replay ring: rows idx[0..n) of (obs, next_obs, action, reward,
+// done[, disc]); target-network forward on s', optional double-DQN online forward on s', online forward on s, TD target +
+// loss gradient, backward, clip + Adam.  qn_t / qn_o: scratch [n, adim] (qn_o NULL = plain DQN).  Reference mode:
+// disc = NULL, huber_delta = 0.  With a communicator every rank holds n of world*n samples: inv_count = 1/(world*n*adim).
+extern "C" int xtb_dqn_train(xtb_net* net, xtb_net* target, xtb_adam* opt, const void* obs, const void* next_obs,
+                             const int32_t* idx, const int32_t* action, const float* reward, const uint8_t* done,
+                             const float* disc, int n_sample, float gamma, float huber_delta, int q_tensor, float* qn_t,
+                             float* qn_o, float* loss_out, int use_graph, void* stream) {
+  if (!net || !target || !opt || !obs || !next_obs || !action || !reward || !done || !qn_t || !loss_out)
+    return fail(XTB_ERR_ARG, "xtb_dqn_train: null pointer");
+  if (!net->ws || !net->grads || !target->ws) return fail(XTB_ERR_STATE, "xtb_dqn_train: nets not bound");
+  const int nl = (int)net->L.size();
+  if (q_tensor < 1 || q_tensor > nl || (int)target->L.size() != nl) return fail(XTB_ERR_ARG, "xtb_dqn_train: bad head tensor");
+  if (n_sample <= 0 || n_sample > net->max_batch || n_sample > target->max_batch) return fail(XTB_ERR_ARG, "xtb_dqn_train: bad batch");
+  const int adim = net->tsize[q_tensor];
+  StepKey key;
+  memset(&key, 0, sizeof key);
+  key.p[0] = net; key.p[1] = opt; key.p[2] = obs; key.p[3] = next_obs; key.p[4] = idx; key.p[5] = action; key.p[6] = reward;
+  key.p[7] = done; key.p[8] = loss_out; key.p[9] = net->ws; key.p[10] = g_comm; key.p[11] = target;
+  key.i[0] = n_sample; key.i[1] = q_tensor; key.i[2] = qn_o ? 1 : 0; key.i[3] = disc ? 1 : 0; key.i[4] = g_tc_mode; key.i[5] = 2;
+  key.f[0] = gamma; key.f[1] = huber_delta;
+  const float inv_world = g_comm ? 1.f / g_comm->world : 1.f;
+  return run_step_graph(key, use_graph, stream, [&](void* st) -> int {
+    const size_t qbytes = (size_t)n_sample * adim * sizeof(float);
+    int rc = net_forward_impl(target, nullptr, next_obs, idx, n_sample, st, 0u, 1u << q_tensor);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(qn_t, xtb_net_tensor(target, q_tensor), qbytes, cudaMemcpyDeviceToDevice, S(st)));
+    if (qn_o) {
+      rc = net_forward_impl(net, nullptr, next_obs, idx, n_sample, st, 0u, 1u << q_tensor);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemcpyAsync(qn_o, xtb_net_tensor(net, q_tensor), qbytes, cudaMemcpyDeviceToDevice, S(st)));
+    }
+    rc = net_forward_impl(net, nullptr, obs, idx, n_sample, st, 0u, 1u << q_tensor);
+    if (rc) return rc;
+    rc = xtb_dqn_td_loss_grad(xtb_net_tensor(net, q_tensor), qn_t, qn_o, idx, action, reward, done, disc, n_sample, adim, gamma,
+                              huber_delta, inv_world / ((float)n_sample * adim), xtb_net_tensor_grad(net, q_tensor), nullptr, loss_out, st);
+    if (rc) return rc;
+    int heads[1] = {q_tensor};
+    rc = net_backward_impl(net, obs, idx, n_sample, heads, 1, st, 0u, true, 0u, 0u, g_comm);
+    if (rc) return rc;
+    return xtb_adam_step_net(opt, net, 1.f, st);
+  });
+}
+
+// ------------------------------------------------------------------------------------------
 // rollout inference: T batched policy evaluations over the E stacked observations
 // ------------------------------------------------------------------------------------------
 struct InferKey {
@@ -1624,6 +1763,7 @@ static void drop_graphs_of(const void* obj) {
   for (auto it = g_infer_graphs.begin(); it != g_infer_graphs.end();) {
     if (it->first.net == obj) { cudaGraphExecDestroy(it->second.exec); it = g_infer_graphs.erase(it); } else ++it;
   }
+  drop_step_graphs_of(obj);
 }
 
 static int rollout_infer_launch(xtb_net* net, const void* obs, const int32_t* step_idx, int E, int T, int pi_t, int v_t,

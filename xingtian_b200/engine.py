@@ -223,6 +223,56 @@ class Adam(object):
         return float(out[0])
 
 
+def _nccl_path():
+    """libnccl of the running PyTorch (nvidia-nccl wheel); None lets the library try the loader path."""
+    import os
+    try:
+        import nvidia.nccl as pkg
+        for base in list(getattr(pkg, "__path__", [])):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
+class GradComm(object):
+    """Data-parallel learner with the library's own NCCL communicator: the gradient all-reduce is issued
+    by the fused training loops themselves, inside their CUDA graph, the big dense bucket under the conv backward.
+    torch.distributed is only the out-of-band channel that ships the NCCL unique id from rank 0."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        self.lib = capi.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        path = _nccl_path()
+        cpath = path.encode() if path else None
+        buf = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            check(self.lib.xtb_comm_unique_id(cpath, buf))
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        backend = dist.get_backend(group)
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev if backend == "nccl" else "cpu")
+        dist.broadcast(t, src=0, group=group)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self.handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            check(self.lib.xtb_comm_create(cpath, ident, self.rank, self.world, C.byref(self.handle)))
+        check(self.lib.xtb_set_grad_comm(self.handle))
+
+    def all_reduce_(self, tensor):
+        """In-place sum of a float32 device tensor over the ranks (utility; the training loops do their own)."""
+        check(self.lib.xtb_comm_allreduce(self.handle, _ptr(tensor), tensor.numel(), stream_ptr()))
+        return tensor
+
+    def close(self):
+        if self.handle.value:
+            check(self.lib.xtb_set_grad_comm(None))
+            self.lib.xtb_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
 class GradAllReduce(object):
     """Data-parallel learner: one process per GPU, every rank holds the rollouts of its
     own envs, gradients of the flat bucket are summed over ranks with NCCL between backward and the

@@ -26,6 +26,7 @@ class _DqnBase(XTModel):
         self.learning_rate = LR
         self.dueling = model_config.get("dueling", False)
         self._init_seed = model_config.get("init_seed")
+        self.use_graph = bool(model_config.get("use_cuda_graph", True))
         if self.dueling:
             raise NotImplementedError("dueling head (dqn_cnn.py:55-58) is not on the benchmarked path")
         super().__init__(model_info)
@@ -87,22 +88,26 @@ class _DqnBase(XTModel):
         self.opt.step()
         return float(b["loss"].cpu()[0])
 
-    def train_td_device(self, target_model, obs, action, reward, next_obs, done, n, gamma, loss_buf, double_dqn=False):
+    def train_td_device(self, target_model, obs, action, reward, next_obs, done, n, gamma, loss_buf, double_dqn=False,
+                        idx=None, disc=None, huber_delta=0.0):
         """Fused DQN.train (xt/algorithm/dqn/dqn.py:61-97) on device-resident transitions: target forward,
-        (double-DQN online forward on s'), online forward on s, TD target + mse gradient, backward, Adam."""
+        (double-DQN online forward on s'), online forward on s, TD target + loss gradient, backward, Adam -- one native
+        call replayed as a CUDA graph.  `idx` (int32 device tensor): the step uses rows idx[0..n) of the given buffers
+        (a replay ring) without copying them; `disc`: per-row n-step bootstrap discount; huber_delta > 0: Huber loss."""
         net = self.net
-        qn_t = target_model.forward_device(next_obs, n)
-        qn_o = None
-        if double_dqn:
-            qn_o_view = self.forward_device(next_obs, n)
-            qn_o = qn_o_view.clone()
-        q = self.forward_device(obs, n)
+        net.ensure_batch(n)
+        target_model.net.ensure_batch(n)
+        key = ("td", n)
+        sc = self._bufs.get(key)
+        if sc is None:
+            sc = dict(qn_t=torch.empty(n, self.action_dim, dtype=torch.float32, device=self.device),
+                      qn_o=torch.empty(n, self.action_dim, dtype=torch.float32, device=self.device))
+            self._bufs[key] = sc
         loss_buf.zero_()
-        check(net.lib.xtb_dqn_loss_grad(_ptr(q), _ptr(qn_t), _ptr(qn_o), _ptr(action), _ptr(reward), _ptr(done), n,
-                                        self.action_dim, float(gamma), 1.0 / (n * self.action_dim),
-                                        _ptr(net.tensor_grad(self.q_name)), None, _ptr(loss_buf), stream_ptr()))
-        net.backward(obs, n, [self.q_name])
-        self.opt.step()
+        check(net.lib.xtb_dqn_train(net.handle, target_model.net.handle, self.opt.handle, _ptr(obs), _ptr(next_obs), _ptr(idx),
+                                    _ptr(action), _ptr(reward), _ptr(done), _ptr(disc), int(n), float(gamma), float(huber_delta),
+                                    net.tid[self.q_name], _ptr(sc["qn_t"]), _ptr(sc["qn_o"]) if double_dqn else None,
+                                    _ptr(loss_buf), 1 if self.use_graph else 0, stream_ptr()))
         return loss_buf
 
 

@@ -33,6 +33,7 @@ class ImpalaCnnOpt(XTModel):
         self.grad_norm_clip = model_config.get("grad_norm_clip", 40.0)
         self.sample_batch_steps = model_config.get("sample_batch_step", 50)
         self._init_seed = model_config.get("init_seed")
+        self.use_graph = bool(model_config.get("use_cuda_graph", True))
         if self.opt_type != "adam":
             # rmsprop(decay .99, eps .1, centered) exists in the reference (impala_cnn_opt.py:205-206) but
             # no shipped YAML selects it
@@ -86,15 +87,11 @@ class ImpalaCnnOpt(XTModel):
         if n % s != 0 or n < s:
             raise ValueError("batch of %d samples is not a whole number of %d-step trajectories" % (n, s))
         net.ensure_batch(n)
-        net.forward(obs, n)
         loss_buf.zero_()
-        check(net.lib.xtb_vtrace_loss_grad(_ptr(net.tensor(self.logit_name)), _ptr(net.tensor(self.base_name)),
-                                           _ptr(bp_logits), _ptr(actions), _ptr(dones), _ptr(rewards), n // s, s,
-                                           self.action_dim, float(GAMMA), _ptr(net.tensor_grad(self.logit_name)),
-                                           _ptr(net.tensor_grad(self.base_name)), None, None, _ptr(loss_buf),
-                                           stream_ptr()))
-        net.backward(obs, n, [self.logit_name, self.base_name])
-        self.opt.step()
+        # forward, in-graph V-trace + losses, backward, clip + Adam: one native call, replayed as a CUDA graph
+        check(net.lib.xtb_impala_train(net.handle, self.opt.handle, _ptr(obs), None, _ptr(bp_logits), _ptr(actions), _ptr(dones),
+                                       _ptr(rewards), int(n), s, float(GAMMA), net.tid[self.logit_name], net.tid[self.base_name],
+                                       _ptr(loss_buf), 1 if self.use_graph else 0, stream_ptr()))
         return loss_buf
 
     def train(self, state, label):
