@@ -202,12 +202,13 @@ __host__ __device__ inline long long bp_index(int pitch, int row, int f) { retur
 // Warp roles.  A single warp needs ~0.3-0.6 us of dependent instructions per stage (table fetch, barrier wait, address
 // and descriptor arithmetic, issue) while the data of a stage arrives in ~0.16 us, so the issue roles are replicated:
 // producer warp p fills ring slot p (every slot has its own full/empty barrier pair), MMA warp m owns the tiles with
-// (tile count & 1) == m and with them TMEM accumulator buffer m (MMAs of one accumulator stay in one warp's program
-// order), two epilogue warps per TMEM lane quarter split the accumulator columns.
+// (tile count & 3) == m and with them TMEM accumulator buffer m (MMAs of one accumulator stay in one warp's program
+// order; the four warps work on the four in-flight ring slots like a systolic wave), two epilogue warps per TMEM lane
+// quarter split the accumulator columns.
 constexpr int RW_P_WARPS = 4;
-constexpr int RW_M_WARPS = 2;
+constexpr int RW_M_WARPS = 4;
 constexpr int RW_EPI_WARPS = 8;
-constexpr int RW_E_WARP0 = RW_P_WARPS + RW_M_WARPS;      // 6: (warp & 3) of warps 6..13 covers every TMEM lane quarter twice
+constexpr int RW_E_WARP0 = RW_P_WARPS + RW_M_WARPS;      // 8: (warp & 3) of warps 8..15 covers every TMEM lane quarter twice
 constexpr int RW_E_TID0 = 32 * RW_E_WARP0;
 constexpr int RW_THREADS = 32 * (RW_E_WARP0 + RW_EPI_WARPS);
 constexpr int RW_A_PLANE = 2048;                 // 128 rows x 16 B
@@ -239,20 +240,27 @@ struct RowsArgs {
   BpT src; int src_act; int accumulate; float* db_part;
 };
 
-// per-tile stage source: conv = run of the shared-memory table, dense = arithmetic progression
+// per-tile stage source: conv = run of the shared-memory table, dense = arithmetic progression.  setup() copies the
+// kernel parameters it needs into registers once per role (see the epilogue note on constant-bank reloads).
 struct TileWalk {
-  const uint2* st; uint32_t a0, w0, da, dw, a_pstride; int ns, nch_last;
+  const uint2* stages_sm; const uint32_t* units_sm;
+  uint32_t a_pstride, w_pitch; int mode, n_ntiles, kc_split, kchunks, N;
+  const uint2* st; uint32_t a0, w0, da, dw; int ns, nch_last;
+  __device__ __forceinline__ void setup(const RowsArgs& a, const uint2* s_sm, const uint32_t* u_sm) {
+    stages_sm = s_sm; units_sm = u_sm;
+    a_pstride = (uint32_t)a.a.pitch * 16u; w_pitch = (uint32_t)a.w_pitch;
+    mode = a.mode; n_ntiles = a.n_ntiles; kc_split = a.kc_split; kchunks = a.kchunks; N = a.N;
+  }
   template <int KIND>
-  __device__ __forceinline__ void init(const RowsArgs& a, int u, const uint2* stages_sm, const uint32_t* units_sm) {
-    a_pstride = (uint32_t)a.a.pitch * 16u;
-    if (a.mode == 2) {
-      const int nt = u % a.n_ntiles, z = u / a.n_ntiles;
-      const int cbeg = z * a.kc_split, cend = min(a.kchunks, cbeg + a.kc_split);
+  __device__ __forceinline__ void init(int u) {
+    if (mode == 2) {
+      const int nt = u % n_ntiles, z = u / n_ntiles;
+      const int cbeg = z * kc_split, cend = min(kchunks, cbeg + kc_split);
       ns = (cend - cbeg + 7) >> 3;
       nch_last = cend - cbeg - 8 * (ns - 1);
       a0 = (uint32_t)cbeg * a_pstride; da = 8u * a_pstride;
-      if (KIND == 2) { w0 = ((uint32_t)cbeg * a.w_pitch + (uint32_t)nt * a.N) * 16u; dw = 8u * (uint32_t)a.w_pitch * 16u; }
-      else { w0 = ((uint32_t)(nt * (a.N >> 3)) * a.w_pitch + (uint32_t)cbeg * 8u) * 16u; dw = 1024u; }
+      if (KIND == 2) { w0 = ((uint32_t)cbeg * w_pitch + (uint32_t)nt * N) * 16u; dw = 8u * w_pitch * 16u; }
+      else { w0 = ((uint32_t)(nt * (N >> 3)) * w_pitch + (uint32_t)cbeg * 8u) * 16u; dw = 1024u; }
       st = nullptr;
     } else {
       const uint32_t ue = units_sm[u];
@@ -278,19 +286,20 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
   uint32_t* units_sm = reinterpret_cast<uint32_t*>(stages_sm + a.n_stage_ents);
   // full barriers exist once per MMA warp: a slot is consumed alternately by the two warps, and a waiter that saw only
   // every other completion of one barrier could not tell its phase from the one two fills earlier
-  __shared__ __align__(8) uint64_t bars[3 * RW_MAX_STAGES + 5];
+  __shared__ __align__(8) uint64_t bars[(RW_M_WARPS + 1) * RW_MAX_STAGES + 2 * RW_M_WARPS + 1];
   __shared__ uint32_t tmem_slot;
   __shared__ float red_sh[4][64];
   __shared__ float bias_sh[64];
   BP_TRACE_DECL
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2 * RW_MAX_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[3 * RW_MAX_STAGES]), tempty0 = smem_u32(&bars[3 * RW_MAX_STAGES + 2]);
-  const uint32_t wbar = smem_u32(&bars[3 * RW_MAX_STAGES + 4]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[RW_M_WARPS * RW_MAX_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[(RW_M_WARPS + 1) * RW_MAX_STAGES]), tempty0 = tfull0 + 8 * RW_M_WARPS;
+  const uint32_t wbar = tempty0 + 8 * RW_M_WARPS;
   if (tid == 0) {
-    for (int s = 0; s < RW_MAX_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(full0 + 8 * (RW_MAX_STAGES + s), 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, RW_EPI_WARPS); }
+    for (int s = 0; s < RW_M_WARPS * RW_MAX_STAGES; s++) mbar_init(full0 + 8 * s, 1);
+    for (int s = 0; s < RW_MAX_STAGES; s++) mbar_init(empty0 + 8 * s, 1);
+    for (int b = 0; b < RW_M_WARPS; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, RW_EPI_WARPS); }
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
@@ -338,10 +347,12 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
     const int n_bh_fwd = N >> 3;
     int stage = 0; uint32_t phase = 0; int cnt = 0;
     int u = (int)blockIdx.x / nbt, bt = (int)blockIdx.x - u * nbt;
+    const int Bsz = a.B;
+    TileWalk tw; tw.setup(a, stages_sm, units_sm);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, cnt++) {
-      const int b0 = bt * 128, nr = min(128, a.B - b0);
+      const int b0 = bt * 128, nr = min(128, Bsz - b0);
       const uint32_t a_bytes = (uint32_t)nr * 16u, row_off = (uint32_t)b0 * 16u;
-      TileWalk tw; tw.init<KIND>(a, u, stages_sm, units_sm);
+      tw.init<KIND>(u);
       for (int s = 0; s < tw.ns; s++) {
         if (stage != warp) { if (++stage == n_stages) { stage = 0; phase ^= 1; } continue; }
         const StageDesc d = tw.get(s);
@@ -351,7 +362,7 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
         const int nch = (int)d.nch;
         const int n_bh = w_res ? 0 : (KIND == 2 ? nch : n_bh_fwd);
         const uint32_t b_bytes = (KIND == 2) ? (uint32_t)N * 16u : (uint32_t)nch * 128u;
-        const uint32_t fb = full0 + 8 * ((cnt & 1) * RW_MAX_STAGES + stage);
+        const uint32_t fb = full0 + 8 * ((cnt & (RW_M_WARPS - 1)) * RW_MAX_STAGES + stage);
         if (elect_one()) {
 #ifdef XTB_EXP_NO_LOAD
           mbar_arrive(fb);
@@ -410,18 +421,19 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
       uint32_t fphase = 0;                 // bit s: parity of the next completion of this warp's full barrier of slot s
       int stage = 0; int cnt = 0;
       int u = (int)blockIdx.x / nbt, bt = (int)blockIdx.x - u * nbt;
+      TileWalk tw; tw.setup(a, stages_sm, units_sm);
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, cnt++) {
-        const int buf = cnt & 1;
+        const int buf = cnt & (RW_M_WARPS - 1);
         const uint32_t acc = tmem_base + buf * acc_cols;
-        TileWalk tw; tw.init<KIND>(a, u, stages_sm, units_sm);
-        if (buf != mw) {       // the other warp's tile: only step the ring position over its stages
+        tw.init<KIND>(u);
+        if (buf != mw) {       // another warp's tile: only step the ring position over its stages
           stage = (stage + tw.ns) % n_stages;
           u += du; bt += dbt;
           if (bt >= nbt) { bt -= nbt; u++; }
           continue;
         }
         BP_TRACE(1, 10);
-        mbar_wait(tempty0 + 8 * buf, ((cnt >> 1) & 1) ^ 1);
+        mbar_wait(tempty0 + 8 * buf, ((cnt / RW_M_WARPS) & 1) ^ 1);
         tc_fence_after();
         BP_TRACE(1, 11);
         uint32_t accum = 0;
@@ -466,28 +478,37 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
     }
   } else {
     // ================= epilogue: warps 2..9; warp & 3 = TMEM lane quarter, two warps per quarter split the columns ====
+    // kernel parameters used per tile live in registers: the barrier waits are asm volatile with a memory clobber, after
+    // which the compiler re-reads the constant bank (a chain of dependent ~50-cycle loads per tile otherwise)
+    const int act = a.act, mode = a.mode, Bsz = a.B, n_nt = a.n_ntiles, ld_f32 = a.ld_f32, src_act = a.src_act, accumulate = a.accumulate;
+    const int ld_part = a.ld_part;
+    const float alpha = a.alpha;
+    bf16* const out_hi = a.out.hi; const long long out_lo = a.out.lo_off;
+    float* const out_f32 = a.out_f32; const float* const bias_g = a.bias;
+    float* const part = a.part; const long long part_z = a.part_z;
+    const bf16* const src_hi = a.src.hi; const long long src_lo = a.src.lo_off, src_pstride = (long long)a.src.pitch * 8;
     const int q = warp & 3, half = (warp - RW_E_WARP0) >> 2;
-    if (KIND == 0 && a.mode != 2 && tid >= RW_E_TID0 && tid < RW_E_TID0 + N) bias_sh[tid - RW_E_TID0] = a.bias[tid - RW_E_TID0];
+    if (KIND == 0 && mode != 2 && tid >= RW_E_TID0 && tid < RW_E_TID0 + N) bias_sh[tid - RW_E_TID0] = bias_g[tid - RW_E_TID0];
     asm volatile("bar.sync 1, %0;" ::"n"(32 * RW_EPI_WARPS) : "memory");
     float dbacc[32];
     if (KIND == 2) {
 #pragma unroll
       for (int j = 0; j < 32; j++) dbacc[j] = 0.f;
     }
-    const int b_pad = (a.B + 15) & ~15;
+    const int b_pad = (Bsz + 15) & ~15;
     // columns of this warp: 16-column groups g with (g & 1) == half when N >= 32; the single group of N = 16 goes to half 0
     const int n_groups = N >> 4;
     const long long out_pstride = (long long)a.out.pitch * 8;      // elements between feature chunks
     int cnt = 0;
     int u = (int)blockIdx.x / nbt, bt = (int)blockIdx.x - u * nbt;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, cnt++) {
-      const int buf = cnt & 1;
+      const int buf = cnt & (RW_M_WARPS - 1);
       const int b = bt * 128 + q * 32 + lane;
       int oc0, z = 0;                          // first output chunk of the unit
-      if (a.mode == 2) { const int nt = u % a.n_ntiles; z = u / a.n_ntiles; oc0 = nt * (N >> 3); }
+      if (mode == 2) { const int nt = u % n_nt; z = u / n_nt; oc0 = nt * (N >> 3); }
       else oc0 = u * (N >> 3);
       if (warp == RW_E_WARP0) BP_TRACE(2, 20);
-      mbar_wait(tfull0 + 8 * buf, (cnt >> 1) & 1);
+      mbar_wait(tfull0 + 8 * buf, (cnt / RW_M_WARPS) & 1);
       tc_fence_after();
       if (warp == RW_E_WARP0) BP_TRACE(2, 21);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * acc_cols;
@@ -512,86 +533,86 @@ bp_rows_kernel(const __grid_constant__ RowsArgs a, int n_stages, int stage_bytes
 #pragma unroll
           for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r0[gi][i]) + (CAT ? __uint_as_float(r1[gi][i]) : 0.f);
           if (KIND == 0) {
-            if (b < a.B) {
+            if (b < Bsz) {
               const int f0 = oc0 * 8 + c;
               float bb[16];
-              if (a.mode == 2) {
-                const float4* bp4 = reinterpret_cast<const float4*>(a.bias + f0);
+              if (mode == 2) {
+                const float4* bp4 = reinterpret_cast<const float4*>(bias_g + f0);
 #pragma unroll
                 for (int i = 0; i < 4; i++) { const float4 t4 = __ldg(bp4 + i); bb[4 * i] = t4.x; bb[4 * i + 1] = t4.y; bb[4 * i + 2] = t4.z; bb[4 * i + 3] = t4.w; }
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; i++) bb[i] = bias_sh[c + i];
               }
-              if (a.act == 2) {
+              if (act == 2) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = tanhf(a.alpha * v[i] + bb[i]);
+                for (int i = 0; i < 16; i++) v[i] = tanhf(alpha * v[i] + bb[i]);
               } else {          // relu / linear without a branch per element
-                const float lo = a.act == 1 ? 0.f : -INFINITY;
+                const float lo = act == 1 ? 0.f : -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = fmaxf(fmaf(a.alpha, v[i], bb[i]), lo);
+                for (int i = 0; i < 16; i++) v[i] = fmaxf(fmaf(alpha, v[i], bb[i]), lo);
               }
-              if (a.out.hi) {
-                bf16* p = a.out.hi + (long long)(oc0 + 2 * g) * out_pstride + (long long)b * 8;
+              if (out_hi) {
+                bf16* p = out_hi + (long long)(oc0 + 2 * g) * out_pstride + (long long)b * 8;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                   uint4 hi, lo;
                   split8(v + 8 * h, hi, lo);
                   *reinterpret_cast<uint4*>(p + h * out_pstride) = hi;
-                  *reinterpret_cast<uint4*>(p + h * out_pstride + a.out.lo_off) = lo;
+                  *reinterpret_cast<uint4*>(p + h * out_pstride + out_lo) = lo;
                 }
               }
-              if (a.out_f32) {
-                float4* o = reinterpret_cast<float4*>(a.out_f32 + (long long)b * a.ld_f32 + f0);
+              if (out_f32) {
+                float4* o = reinterpret_cast<float4*>(out_f32 + (long long)b * ld_f32 + f0);
 #pragma unroll
                 for (int i = 0; i < 4; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
               }
             }
           } else if (KIND == 1) {
-            if (b < a.B) {
-              float4* o = reinterpret_cast<float4*>(a.part + (long long)z * a.part_z + (long long)b * a.ld_part + oc0 * 8 + c);
+            if (b < Bsz) {
+              float4* o = reinterpret_cast<float4*>(part + (long long)z * part_z + (long long)b * ld_part + oc0 * 8 + c);
 #pragma unroll
               for (int i = 0; i < 4; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
           } else {
-            bf16* p = a.out.hi + (long long)(oc0 + 2 * g) * out_pstride + (long long)b * 8;
-            if (b < a.B) {
-              const bf16* sp = a.src.hi + (long long)(oc0 + 2 * g) * ((long long)a.src.pitch * 8) + (long long)b * 8;
+            bf16* p = out_hi + (long long)(oc0 + 2 * g) * out_pstride + (long long)b * 8;
+            if (b < Bsz) {
+              const bf16* sp = src_hi + (long long)(oc0 + 2 * g) * src_pstride + (long long)b * 8;
 #pragma unroll
               for (int h = 0; h < 2; h++) {
                 float* vv = v + 8 * h;
-                if (a.src_act == 1) {
+                if (src_act == 1) {
                   float s[8];
-                  unpack8(*reinterpret_cast<const uint4*>(sp + h * (long long)a.src.pitch * 8), s);
+                  unpack8(*reinterpret_cast<const uint4*>(sp + h * src_pstride), s);
 #pragma unroll
                   for (int i = 0; i < 8; i++) vv[i] = s[i] > 0.f ? vv[i] : 0.f;
-                } else if (a.src_act == 2) {
+                } else if (src_act == 2) {
                   float s[8], t[8];
-                  unpack8(*reinterpret_cast<const uint4*>(sp + h * (long long)a.src.pitch * 8), s);
-                  unpack8(*reinterpret_cast<const uint4*>(sp + h * (long long)a.src.pitch * 8 + a.src.lo_off), t);
+                  unpack8(*reinterpret_cast<const uint4*>(sp + h * src_pstride), s);
+                  unpack8(*reinterpret_cast<const uint4*>(sp + h * src_pstride + src_lo), t);
 #pragma unroll
                   for (int i = 0; i < 8; i++) { float y = s[i] + t[i]; vv[i] *= 1.f - y * y; }
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++) dbacc[16 * gi + 8 * h + i] += vv[i];
-                if (a.accumulate) {
+                if (accumulate) {
                   float s[8], t[8];
                   unpack8(*reinterpret_cast<const uint4*>(p + h * out_pstride), s);
-                  unpack8(*reinterpret_cast<const uint4*>(p + h * out_pstride + a.out.lo_off), t);
+                  unpack8(*reinterpret_cast<const uint4*>(p + h * out_pstride + out_lo), t);
 #pragma unroll
                   for (int i = 0; i < 8; i++) vv[i] += s[i] + t[i];
                 }
                 uint4 hi, lo;
                 split8(vv, hi, lo);
                 *reinterpret_cast<uint4*>(p + h * out_pstride) = hi;
-                *reinterpret_cast<uint4*>(p + h * out_pstride + a.out.lo_off) = lo;
+                *reinterpret_cast<uint4*>(p + h * out_pstride + out_lo) = lo;
               }
-            } else if (b < b_pad && !a.accumulate) {
+            } else if (b < b_pad && !accumulate) {
               // gradient rows up to the next multiple of 16 are read by the weight-gradient K loop: keep them zero
 #pragma unroll
               for (int h = 0; h < 2; h++) {
                 *reinterpret_cast<uint4*>(p + h * out_pstride) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(p + h * out_pstride + a.out.lo_off) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(p + h * out_pstride + out_lo) = make_uint4(0, 0, 0, 0);
               }
             }
           }
@@ -651,7 +672,7 @@ constexpr int WG_STAGE_B = 2 * 8 * WG_PLANE;     // hi + lo, up to 8 chunks (N <
 constexpr int WG_STAGE = WG_STAGE_A + WG_STAGE_B;
 constexpr int WG_STAGES = 4;
 constexpr int WG_P_WARPS = 4;                   // producer warp p fills ring slot p
-constexpr int WG_M_WARPS = 2;                   // MMA warp m owns the accumulators with (r & 1) == m
+constexpr int WG_M_WARPS = 4;                   // MMA warp m owns the accumulators with (r & 3) == m
 constexpr int WG_E_WARP0 = WG_P_WARPS + WG_M_WARPS;
 constexpr int WG_THREADS = 32 * (WG_E_WARP0 + 4);
 
@@ -688,15 +709,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 bp_wgrad_kernel(const __grid_constant__ WgradArgs a, int tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  __shared__ __align__(8) uint64_t bars[3 * WG_STAGES + 2];      // full barriers once per MMA warp (see bp_rows_kernel)
+  __shared__ __align__(8) uint64_t bars[(WG_M_WARPS + 1) * WG_STAGES + 2];      // full barriers once per MMA warp (see bp_rows_kernel)
   __shared__ uint32_t tmem_slot;
   uint2* tab_sm = reinterpret_cast<uint2*>(smem + WG_STAGES * WG_STAGE);     // conv: [n_opix][R] entries behind the stage ring
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2 * WG_STAGES]);
-  const uint32_t tfull = smem_u32(&bars[3 * WG_STAGES]), tempty = smem_u32(&bars[3 * WG_STAGES + 1]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[WG_M_WARPS * WG_STAGES]);
+  const uint32_t tfull = smem_u32(&bars[(WG_M_WARPS + 1) * WG_STAGES]), tempty = tfull + 8;
   if (tid == 0) {
-    for (int s = 0; s < WG_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(full0 + 8 * (WG_STAGES + s), 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < WG_M_WARPS * WG_STAGES; s++) mbar_init(full0 + 8 * s, 1);
+    for (int s = 0; s < WG_STAGES; s++) mbar_init(empty0 + 8 * s, 1);
     mbar_init(tfull, WG_M_WARPS); mbar_init(tempty, 4);
     fence_barrier_init();
   }
@@ -746,7 +768,7 @@ bp_wgrad_kernel(const __grid_constant__ WgradArgs a, int tmem_cols) {
           if (stage != warp) { if (++stage == WG_STAGES) { stage = 0; phase ^= 1; } continue; }
           const long long x_off = (long long)e.x_chunk * (long long)pstride_x + row_off;
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t fb = full0 + 8 * ((r & 1) * WG_STAGES + stage);
+          const uint32_t fb = full0 + 8 * ((r & (WG_M_WARPS - 1)) * WG_STAGES + stage);
           if (elect_one()) {
             mbar_expect_tx(fb, bytes * ((x_split ? 32 : 16) + 2 * n_bh));
             const uint32_t sA = stage0 + (uint32_t)stage * WG_STAGE, sB = sA + WG_STAGE_A;
@@ -792,7 +814,7 @@ bp_wgrad_kernel(const __grid_constant__ WgradArgs a, int tmem_cols) {
           for (int r = 0; r < n_r; r++) {
             const WgEnt e = WgWalk::get(a, tab_sm, opix, r, rt);
             if (!e.valid) continue;
-            if ((r & 1) != mw) { if (++stage == WG_STAGES) stage = 0; continue; }
+            if ((r & (WG_M_WARPS - 1)) != mw) { if (++stage == WG_STAGES) stage = 0; continue; }
             mbar_wait(myfull + 8 * stage, (fphase >> stage) & 1u);
             fphase ^= 1u << stage;
             tc_fence_after();

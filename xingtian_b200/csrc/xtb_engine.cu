@@ -597,7 +597,7 @@ static cudaError_t launch_rows(bp::RowsArgs& a, cudaStream_t st) {
   const int acc = (KIND == 2 ? a.N : 2 * a.N);
   const int total = a.n_units * a.n_btiles;
   const int grid = std::min(total, kSMs);
-  XLAUNCH(kern, grid, bp::RW_THREADS, smem, st, a, n_stages, stage_bytes, wres_bytes, tmem_cols_for(2 * acc));
+  XLAUNCH(kern, grid, bp::RW_THREADS, smem, st, a, n_stages, stage_bytes, wres_bytes, tmem_cols_for(bp::RW_M_WARPS * acc));
   return cudaPeekAtLastError();
 }
 
