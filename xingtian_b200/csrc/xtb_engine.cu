@@ -88,9 +88,13 @@ extern "C" int xtb_comm_create(const char* nccl_path, const void* id128, int ran
   *out = c;
   return XTB_OK;
 }
+static void drop_graphs_of(const void* obj);
 extern "C" void xtb_comm_destroy(xtb_comm* c) {
   if (!c) return;
   if (g_comm == c) g_comm = nullptr;
+  // captured training graphs hold NCCL kernels of this communicator: they go first, and nothing may be in flight
+  drop_graphs_of(c);
+  cudaDeviceSynchronize();
   if (c->comm) g_nccl.CommDestroy(c->comm);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->fork) cudaEventDestroy(c->fork);
@@ -1633,7 +1637,7 @@ static std::map<StepKey, GraphVal> g_step_graphs;
 
 static void drop_step_graphs_of(const void* obj) {
   for (auto it = g_step_graphs.begin(); it != g_step_graphs.end();) {
-    if (it->first.p[0] == obj || it->first.p[1] == obj || it->first.p[11] == obj) { cudaGraphExecDestroy(it->second.exec); it = g_step_graphs.erase(it); } else ++it;
+    if (it->first.p[0] == obj || it->first.p[1] == obj || it->first.p[10] == obj || it->first.p[11] == obj) { cudaGraphExecDestroy(it->second.exec); it = g_step_graphs.erase(it); } else ++it;
   }
 }
 
@@ -1758,7 +1762,7 @@ static std::map<InferKey, GraphVal> g_infer_graphs;
 // be allocated at the same address)
 static void drop_graphs_of(const void* obj) {
   for (auto it = g_graphs.begin(); it != g_graphs.end();) {
-    if (it->first.net == obj || it->first.opt == obj) { cudaGraphExecDestroy(it->second.exec); it = g_graphs.erase(it); } else ++it;
+    if (it->first.net == obj || it->first.opt == obj || it->first.comm == obj) { cudaGraphExecDestroy(it->second.exec); it = g_graphs.erase(it); } else ++it;
   }
   for (auto it = g_infer_graphs.begin(); it != g_infer_graphs.end();) {
     if (it->first.net == obj) { cudaGraphExecDestroy(it->second.exec); it = g_infer_graphs.erase(it); } else ++it;

@@ -266,7 +266,15 @@ class GradComm(object):
         check(self.lib.xtb_comm_allreduce(self.handle, _ptr(tensor), tensor.numel(), stream_ptr()))
         return tensor
 
+    def detach(self):
+        """Stop all-reducing (single-rank work on this process), keep the communicator alive."""
+        check(self.lib.xtb_set_grad_comm(None))
+
+    def attach(self):
+        check(self.lib.xtb_set_grad_comm(self.handle))
+
     def close(self):
+        """Collective: every rank must call it (the graphs that captured this communicator are destroyed first)."""
         if self.handle.value:
             check(self.lib.xtb_set_grad_comm(None))
             self.lib.xtb_comm_destroy(self.handle)
