@@ -308,14 +308,18 @@ class PpoBench(object):
         E, T, ro = self.E, self.T, self.ro
         self.host_obs = [np.ascontiguousarray(ro["obs"][np.arange(E) * T + t]) for t in range(T)]
         self.traj = []
+        # the frames reach the device once, inside predict(): trajectories refer to them by (env, first step, steps)
+        self.model.keep_predict_obs(E, T)
         for e in range(E):
             sl = slice(e * T, (e + 1) * T)
-            self.traj.append(dict(cur_state=ro["obs"][sl], action=ro["action"][sl], logp=ro["logp"][sl],
+            self.traj.append(dict(ring_rows=(e, 0, T), action=ro["action"][sl], logp=ro["logp"][sl],
                                   value=ro["value"][e], reward=ro["reward"][sl], done=ro["done"][sl]))
+        self.h2d -= self.n * int(np.prod(STATE))
 
     def e2e_iteration(self):
+        self.model._obs_ring["t"] = 0
         for t in range(self.T):
-            self.model.predict(self.host_obs[t])           # H2D obs, D2H (action, logp, value)
+            self.model.predict(self.host_obs[t])           # H2D obs (kept in the device ring), D2H (action, logp, value)
         for e in range(self.E):
             self.alg.prepare_data(self.traj[e])            # H2D trajectory (pinned ring), device GAE
         return self.alg.train()                            # D2H loss trace

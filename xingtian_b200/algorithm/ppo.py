@@ -48,14 +48,23 @@ class PPO(Algorithm):
         check(self.actor.net.lib.xtb_copy_h2d_staged(_ptr(dst), a.ctypes.data, a.nbytes, stream_ptr()))
 
     def prepare_data(self, train_data, **kwargs):
+        """`ring_rows` = (env_index, first_step, n_steps) instead of `cur_state`: the trajectory's frames are the ones the
+        learner-side batched predict() already uploaded (model.keep_predict_obs); they are copied device to device."""
         ro = self.actor.rollout
-        obs = train_data["cur_state"]
-        n = len(obs)
+        ring_rows = train_data.get("ring_rows")
+        n = int(ring_rows[2]) if ring_rows is not None else len(train_data["cur_state"])
         ro.n = self._count
         ro.reserve(self._count + n)
         sl = slice(self._count, self._count + n)
         obs_np = np.uint8 if self.actor.input_dtype == "uint8" else np.float32
-        self._stage(ro.obs[sl], np.asarray(obs), obs_np)
+        if ring_rows is not None:
+            ring = self.actor._obs_ring
+            e, t0 = int(ring_rows[0]), int(ring_rows[1]) % ring["T"]
+            if t0 + n > ring["T"]:
+                raise ValueError("trajectory wraps around the observation ring")
+            ro.obs[sl].copy_(ring["obs"][t0:t0 + n, e], non_blocking=True)
+        else:
+            self._stage(ro.obs[sl], np.asarray(train_data["cur_state"]), obs_np)
         self._stage(ro.action[sl], train_data["action"], np.int32)
         self._stage(ro.old_logp[sl], train_data["logp"], np.float32)
         if "adv" in train_data:

@@ -119,6 +119,7 @@ class PPO(XTModel):
         self._perm_host = None
         self._loss_dev = None
         self._pred_bufs = {}
+        self._obs_ring = None
         self._sample_seed = int(np.random.randint(0, 2 ** 31 - 1))
         self._sample_offset = 0
         self.pi_t = self.net.tid["pi_latent"]
@@ -204,12 +205,24 @@ class PPO(XTModel):
         if getattr(self, "_offset_dev", None) is None:
             self._offset_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.net.ensure_batch(batch)
+        ring = self._obs_ring
         # staged H2D -> graphed forward + sampling -> packed D2H -> stream sync, in one native call
         check(self.net.lib.xtb_ppo_predict_host(self.net.handle, state.ctypes.data, state.nbytes, io["obs_ptr"], batch,
                                                 self.pi_t, self.v_t, C.c_uint64(self._sample_seed), _ptr(self._offset_dev),
                                                 io["out_dev_ptr"], io["pin_out_ptr"], 1 if self.use_graph else 0, stream_ptr()))
+        if ring is not None and batch == ring["E"]:
+            # learner-side batched inference: the frames just uploaded ARE the rollout's cur_state -- keep them on the
+            # device (time-major ring) so prepare_data can take them from here instead of a second H2D copy
+            ring["obs"][ring["t"] % ring["T"]].copy_(io["obs"], non_blocking=True)
+            ring["t"] += 1
         out = io["pin_out_np"]
         return (out[0].view(np.int32).copy(), out[1].reshape(batch, 1).copy(), out[2].reshape(batch, 1).copy())
+
+    def keep_predict_obs(self, env_num, steps):
+        """Enable the device observation ring [steps][env_num][...] filled by predict() (see Algorithm.prepare_data's
+        `ring_rows` form).  Replaces the second upload of every frame (xt/framework/learner.py:382-437 data path)."""
+        self._obs_ring = dict(E=int(env_num), T=int(steps), t=0,
+                              obs=torch.empty((int(steps), int(env_num)) + tuple(self.state_dim), dtype=self._obs_dt, device=self.device))
 
     # -- training ----------------------------------------------------------------------------
     def make_perm(self, nbatch):

@@ -45,7 +45,18 @@ class _Inbox(object):
             if timeout is None or q.poll(timeout):
                 return q.recv()
             return None
-        return q.recv() if timeout is None else None       # blocking-only transport: no opportunistic batching
+        if timeout is None:
+            return q.recv()
+        # UniComm-like transport (zeus/common/ipc/uni_comm.py:37-41): poll its non-blocking recv up to the timeout
+        end = time.time() + timeout
+        while True:
+            try:
+                got = q.recv(block=False)
+            except TypeError:
+                return None                                  # blocking-only transport: no opportunistic batching
+            if got is not None or time.time() >= end:
+                return got
+            time.sleep(0.0002)
 
 
 def _unpack(item):
