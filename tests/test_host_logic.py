@@ -152,7 +152,7 @@ def test_stager_thread_pool_with_mock_dma(repo_root, tmp_path):
 
 def test_space_to_depth_identity_of_the_first_conv_layer():
     """The tensor-core path runs the 8x8 stride-4 conv over [84,84,4] as a 2x2 stride-1 conv over the space-to-depth
-    plane [21,21,64] (csrc/gemm_tc.cuh: decode_u8_s2d_kernel, s2d_row).  Restated in numpy: plane layout, weight-row
+    plane [21,21,64] (csrc/bp_gemm.cuh: bp_decode_s2d_kernel, s2d_real_row).  Restated in numpy: plane layout, weight-row
     map and the resulting GEMM equal the oracle's conv (xt/model/model_utils.py:141-160 Conv2D 32 x 8x8 / 4)."""
     import torch
     import torch.nn.functional as F

@@ -925,24 +925,57 @@ __host__ __device__ inline int s2d_real_row(int m, int k4) {
 }
 constexpr int RED_MAX = 24;
 struct RedSegs { RedSeg s[RED_MAX]; };
-__global__ void grad_reduce_kernel(const __grid_constant__ RedSegs segs, float* __restrict__ grads) {
+// One block = 128 consecutive elements of one segment: warp w sums slabs w, w + 8, ... with float4 loads (512 B per
+// warp and slab), then warp 0 adds the eight partial sums in warp order -- a fixed tree, bitwise reproducible.
+__global__ void __launch_bounds__(256) grad_reduce_kernel(const __grid_constant__ RedSegs segs, float* __restrict__ grads) {
   pdl_wait(); pdl_trigger();
+  __shared__ float4 sh[8][32];
   const RedSeg& s = segs.s[blockIdx.y];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= s.count) return;
-  long long dst;
-  if (s.kind == 0) {
-    const int n = i % s.N, mm = (i / s.N) & 127, r = i / (s.N * 128);
-    const int ky = r / s.mts, mt = r - ky * s.mts;
-    const int feat = mt * 128 + mm;
-    if (feat >= s.KW * s.C) return;
-    int row = ky * s.KW * s.C + feat;
-    if (s.s2d_k4) row = s2d_real_row(row, s.s2d_k4);
-    dst = s.dst_off + (long long)row * s.N + n;
-  } else dst = s.dst_off + i;
-  float acc = 0.f;
-  for (int k = 0; k < s.n_slabs; k++) acc += s.part[(long long)k * s.slab + i];
-  grads[dst] = s.alpha * acc;
+  if ((int)blockIdx.x * 128 >= s.count) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = ((int)blockIdx.x * 32 + lane) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < s.count) {
+    const bool vec = ((s.count | (int)(s.slab & 3)) & 3) == 0 && (reinterpret_cast<unsigned long long>(s.part) & 15ull) == 0;
+    if (vec) {
+#pragma unroll 5
+      for (int k = w; k < s.n_slabs; k += 8) {
+        const float4 x = *reinterpret_cast<const float4*>(s.part + (long long)k * s.slab + i);
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+      }
+    } else {
+      for (int k = w; k < s.n_slabs; k += 8) {
+        const float* p = s.part + (long long)k * s.slab + i;
+        acc.x += p[0];
+        if (i + 1 < s.count) acc.y += p[1];
+        if (i + 2 < s.count) acc.z += p[2];
+        if (i + 3 < s.count) acc.w += p[3];
+      }
+    }
+  }
+  sh[w][lane] = acc;
+  __syncthreads();
+  if (w != 0 || i >= s.count) return;
+  float4 t = sh[0][lane];
+#pragma unroll
+  for (int q = 1; q < 8; q++) { const float4 x = sh[q][lane]; t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w; }
+  const float v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int ie = i + e;
+    if (ie >= s.count) break;
+    long long dst;
+    if (s.kind == 0) {
+      const int n = ie % s.N, mm = (ie / s.N) & 127, r = ie / (s.N * 128);
+      const int ky = r / s.mts, mt = r - ky * s.mts;
+      const int feat = mt * 128 + mm;
+      if (feat >= s.KW * s.C) continue;
+      int row = ky * s.KW * s.C + feat;
+      if (s.s2d_k4) row = s2d_real_row(row, s.s2d_k4);
+      dst = s.dst_off + (long long)row * s.N + n;
+    } else dst = s.dst_off + ie;
+    grads[dst] = s.alpha * v[e];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1005,22 +1038,35 @@ __global__ void bp_colsum_kernel(BpT g, int B, int F, int period, float* __restr
     if (lane == 0) atomicAdd(db + (c * 8 + i) % period, v);
   }
 }
-// split-K partial sums part[z][b][N] -> act(sum_z + bias): fp32 row-major and/or batch-planar planes (fixed order)
+// split-K partial sums part[z][b][N] -> act(sum_z + bias): fp32 row-major and/or batch-planar planes.  FIN_ZL lanes share
+// one 8-feature piece: lane zl sums slabs zl, zl + FIN_ZL, ... and a fixed xor tree combines them (bitwise reproducible).
+constexpr int FIN_ZL = 8;
 __global__ void bp_splitk_finish_kernel(const float* __restrict__ part, int n_z, long long part_z, int B, int N,
                                         const float* __restrict__ bias, int act, float* __restrict__ out_f32, BpT out) {
   pdl_wait(); pdl_trigger();
   const int b_pad = (B + 15) & ~15;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t / FIN_ZL;
+  const int zl = (int)(t - i * FIN_ZL);
   const int chunks = N >> 3;
-  if (i >= (long long)chunks * b_pad) return;
   const int c = (int)(i / b_pad), b = (int)(i - (long long)c * b_pad);
-  if (b >= B) return;
+  const bool valid = i < (long long)chunks * b_pad && b < B;
   float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int z = 0; z < n_z; z++) {
-    const float4* p = reinterpret_cast<const float4*>(part + (long long)z * part_z + (long long)b * N + c * 8);
-    float4 x = p[0], y = p[1];
-    v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+  if (valid) {
+    const float* p0 = part + (long long)b * N + c * 8;
+#pragma unroll 4
+    for (int z = zl; z < n_z; z += FIN_ZL) {
+      const float4* p = reinterpret_cast<const float4*>(p0 + (long long)z * part_z);
+      float4 x = p[0], y = p[1];
+      v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+    }
   }
+#pragma unroll
+  for (int o = FIN_ZL / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  if (!valid || zl != 0) return;
 #pragma unroll
   for (int k = 0; k < 8; k++) v[k] = act_apply(act, v[k] + bias[c * 8 + k]);
   if (out_f32) {

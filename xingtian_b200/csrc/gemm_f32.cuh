@@ -4,7 +4,7 @@
 // loader functors (im2col gather with fused uint8 decode + minibatch gather, transposed-conv
 // gather, transposed im2col for weight gradients, plain / transposed dense) and whose result is
 // consumed by an epilogue functor (bias+activation, activation-gradient mask, split-K atomic
-// accumulation).  The tcgen05 kernels in gemm_tc.cuh implement the same contracts on the
+// accumulation).  The tcgen05 kernels in bp_gemm.cuh implement the same contracts on the
 // tensor cores; this file is the numerically straightforward fp32 version they are checked
 // against on the device, and the fallback for shapes the tensor-core path does not cover.
 #pragma once

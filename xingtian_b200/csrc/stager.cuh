@@ -26,8 +26,11 @@ namespace xtb {
 
 class Stager {
  public:
-  static constexpr size_t CHUNK = 256u << 10;   // bytes per pinned slot
-  static constexpr int SLOTS = 48;              // 12 MiB ring
+  // Slot size: XTB_STAGE_CHUNK_KB (default 256).  Measured on the C2 inference upload (0.9 MB, profiles/r2_results.md):
+  // 256 KiB slots / 4 threads 76 us, 64 KiB slots 96 us (every DMA issue costs the calling thread several us), pinned
+  // memory floor 40 us.
+  static constexpr size_t RING_BYTES = 12u << 20;
+  static constexpr int MAX_SLOTS = 192;
 
   static Stager& instance() {
     static Stager* s = new Stager();            // leaked on purpose: workers may outlive static destructors
@@ -40,15 +43,15 @@ class Stager {
     std::lock_guard<std::mutex> call_lock(call_mu_);       // one staged copy at a time
     cudaError_t err = init();
     if (err != cudaSuccess) return err;
-    const size_t n = (bytes + CHUNK - 1) / CHUNK;
+    const size_t n = (bytes + chunk_ - 1) / chunk_;
     const char* s = static_cast<const char*>(src);
     char* d = static_cast<char*>(dst);
     if (n == 1 || workers_.empty()) {                        // small copy: stage on the calling thread
       for (size_t c = 0; c < n; c++) {
-        int slot = (int)((seq_ + c) % SLOTS);
+        int slot = (int)((seq_ + c) % slots_);
         if ((err = wait_slot(slot)) != cudaSuccess) return err;
-        size_t off = c * CHUNK, len = bytes - off < CHUNK ? bytes - off : CHUNK;
-        memcpy(ring_ + (size_t)slot * CHUNK, s + off, len);
+        size_t off = c * chunk_, len = bytes - off < chunk_ ? bytes - off : chunk_;
+        memcpy(ring_ + (size_t)slot * chunk_, s + off, len);
         if ((err = issue(slot, 1, d + off, len, stream)) != cudaSuccess) return err;
       }
       seq_ += n;
@@ -64,8 +67,8 @@ class Stager {
     job_src_.store(s, std::memory_order_relaxed); job_bytes_.store(bytes, std::memory_order_relaxed);
     job_chunks_.store(n, std::memory_order_relaxed); job_seq_.store(seq_, std::memory_order_relaxed);
     size_t allowed = 0;
-    while (allowed < n && allowed < (size_t)SLOTS) {         // slots last used by earlier calls
-      if ((err = wait_slot((int)((seq_ + allowed) % SLOTS))) != cudaSuccess) return err;
+    while (allowed < n && allowed < (size_t)slots_) {         // slots last used by earlier calls
+      if ((err = wait_slot((int)((seq_ + allowed) % slots_))) != cudaSuccess) return err;
       allowed++;
     }
     allowed_.store(allowed, std::memory_order_release);
@@ -82,20 +85,20 @@ class Stager {
         const size_t claimed = (size_t)(next_.load(std::memory_order_acquire) & 0xffffffffu);
         const bool help = sleepers_.load(std::memory_order_acquire) > 0 || n - std::min(claimed, n) > nw;
         if (!(help && work_one(g))) cpu_relax();
-        if (allowed < n && allowed < c + SLOTS) {            // hand out slots whose previous DMA (issued: chunk < c) finished
-          int slot = (int)((seq_ + allowed) % SLOTS);
+        if (allowed < n && allowed < c + slots_) {            // hand out slots whose previous DMA (issued: chunk < c) finished
+          int slot = (int)((seq_ + allowed) % slots_);
           if (query_slot(slot) == cudaSuccess) allowed_.store(++allowed, std::memory_order_release);
         }
       }
       // one DMA for the run of finished chunks that is contiguous in the ring: c .. e
       size_t e = c;
-      while (e + 1 < n && (int)((seq_ + e + 1) % SLOTS) != 0 && done_[e + 1].load(std::memory_order_acquire)) e++;
-      const int slot0 = (int)((seq_ + c) % SLOTS);
-      const size_t off = c * CHUNK, end = std::min(bytes, (e + 1) * CHUNK);
+      while (e + 1 < n && (int)((seq_ + e + 1) % slots_) != 0 && done_[e + 1].load(std::memory_order_acquire)) e++;
+      const int slot0 = (int)((seq_ + c) % slots_);
+      const size_t off = c * chunk_, end = std::min(bytes, (e + 1) * chunk_);
       if (first == cudaSuccess) first = issue(slot0, (int)(e - c + 1), d + off, end - off, stream);
       c = e + 1;
       if (allowed < n && allowed <= c) {                     // nothing else can be staged: block on the oldest DMA
-        int s2 = (int)((seq_ + allowed) % SLOTS);
+        int s2 = (int)((seq_ + allowed) % slots_);
         cudaError_t e2 = wait_slot(s2);
         if (first == cudaSuccess) first = e2;
         allowed_.store(++allowed, std::memory_order_release);
@@ -121,11 +124,18 @@ class Stager {
   cudaError_t init() {
     if (inited_) return cudaSuccess;
     cudaError_t e = cudaSuccess;
+    if (n_events_ == 0) {
+      if (const char* env = getenv("XTB_STAGE_CHUNK_KB")) {
+        long kb = atol(env);
+        if (kb >= 64 && kb <= 1024 && (kb & (kb - 1)) == 0) chunk_ = (size_t)kb << 10;
+      }
+      slots_ = (int)(RING_BYTES / chunk_);
+    }
     if (!ring_) {
-      e = cudaHostAlloc((void**)&ring_, CHUNK * SLOTS, cudaHostAllocDefault);
+      e = cudaHostAlloc((void**)&ring_, RING_BYTES, cudaHostAllocDefault);
       if (e != cudaSuccess) { ring_ = nullptr; return e; }
     }
-    for (int i = n_events_; i < SLOTS; i++) {
+    for (int i = n_events_; i < slots_; i++) {
       e = cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming);
       if (e != cudaSuccess) return e;              // a later call resumes here: nothing half-initialised is used
       used_[i] = false; owner_[i] = i;
@@ -155,7 +165,7 @@ class Stager {
 
   // one async copy out of `count` consecutive ring slots starting at `slot`
   cudaError_t issue(int slot, int count, void* dst, size_t len, cudaStream_t stream) {
-    cudaError_t e = cudaMemcpyAsync(dst, ring_ + (size_t)slot * CHUNK, len, cudaMemcpyHostToDevice, stream);
+    cudaError_t e = cudaMemcpyAsync(dst, ring_ + (size_t)slot * chunk_, len, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     const int last = slot + count - 1;
     for (int i = slot; i <= last; i++) { used_[i] = true; owner_[i] = last; }
@@ -170,10 +180,10 @@ class Stager {
     size_t c = (size_t)(cur & 0xffffffffu);
     if (c >= job_chunks_.load(std::memory_order_relaxed) || c >= allowed_.load(std::memory_order_acquire)) return false;
     if (!next_.compare_exchange_strong(cur, cur + 1, std::memory_order_acq_rel)) return true;   // lost a race: retry
-    int slot = (int)((job_seq_.load(std::memory_order_relaxed) + c) % SLOTS);
+    int slot = (int)((job_seq_.load(std::memory_order_relaxed) + c) % slots_);
     size_t bytes = job_bytes_.load(std::memory_order_relaxed);
-    size_t off = c * CHUNK, len = bytes - off < CHUNK ? bytes - off : CHUNK;
-    memcpy(ring_ + (size_t)slot * CHUNK, job_src_.load(std::memory_order_relaxed) + off, len);
+    size_t off = c * chunk_, len = bytes - off < chunk_ ? bytes - off : chunk_;
+    memcpy(ring_ + (size_t)slot * chunk_, job_src_.load(std::memory_order_relaxed) + off, len);
     done_[c].store(1, std::memory_order_release);
     return true;
   }
@@ -220,9 +230,11 @@ class Stager {
   char* ring_ = nullptr;
   bool inited_ = false;
   int n_events_ = 0;
-  cudaEvent_t ev_[SLOTS];
-  bool used_[SLOTS];
-  int owner_[SLOTS];
+  size_t chunk_ = 256u << 10;   // bytes per pinned slot
+  int slots_ = 48;              // RING_BYTES / chunk_
+  cudaEvent_t ev_[MAX_SLOTS];
+  bool used_[MAX_SLOTS];
+  int owner_[MAX_SLOTS];
   std::vector<std::thread> workers_;
 };
 

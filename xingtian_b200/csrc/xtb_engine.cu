@@ -657,7 +657,7 @@ static cudaError_t tc_forward(xtb_net* net, int i, int B, bool want_f32, bool wa
   a.part_z = (long long)b_pad * lp.N; a.ld_part = lp.N;
   cudaError_t e = launch_rows<1>(a, st);
   if (e != cudaSuccess) return e;
-  long long pieces = (long long)(lp.N / 8) * b_pad;
+  long long pieces = (long long)(lp.N / 8) * b_pad * bp::FIN_ZL;
   XLAUNCH(bp::bp_splitk_finish_kernel, (unsigned)((pieces + 127) / 128), 128, 0, st, (const float*)a.part, nz, a.part_z, B, lp.N,
           a.bias, lp.d.act, a.out_f32, a.out);
   *launches = 2;
@@ -824,7 +824,7 @@ extern "C" int xtb_tc_gemm_test(int mode, const float* a, const float* b, float*
         CUDA_TRY(cudaMalloc(&part, (size_t)nz * M * N * sizeof(float)));
         r.part = part; r.part_z = (long long)M * N; r.ld_part = N;
         e = launch_rows<1>(r, st);
-        long long pieces = (long long)(N / 8) * ((M + 15) & ~15);
+        long long pieces = (long long)(N / 8) * ((M + 15) & ~15) * bp::FIN_ZL;
         XLAUNCH(bp::bp_splitk_finish_kernel, (unsigned)((pieces + 127) / 128), 128, 0, st, (const float*)part, nz, r.part_z, M, N,
                 (const float*)bias, 0, c, no_bp());
       } else {
@@ -1087,7 +1087,7 @@ static int flush_reductions(xtb_net* net, cudaStream_t st) {
   int mx = 0;
   if (net->pending.size() > bp::RED_MAX) return fail(XTB_ERR_STATE, "too many pending reductions");
   for (size_t k = 0; k < net->pending.size(); k++) { segs.s[k] = net->pending[k]; mx = std::max(mx, net->pending[k].count); }
-  dim3 grid((mx + 255) / 256, (unsigned)net->pending.size());
+  dim3 grid((mx + 127) / 128, (unsigned)net->pending.size());
   XLAUNCH(bp::grad_reduce_kernel, grid, 256, 0, st, segs, net->grads);
   LAUNCH_CHECK();
   net->pending.clear();
@@ -1543,9 +1543,10 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         a.logits_out = xtb_net_tensor(net, pi_t); a.v_out = xtb_net_tensor(net, v_t); a.loss_out = loss_per_step + step;
         a.B = mb; a.K = lpi.K; a.A = adim; a.act_pi = lpi.src_act; a.act_v = lv.src_act; a.shared = lpi.d.src == lv.d.src ? 1 : 0;
         a.hp = PpoHyperDev{hp->clip_ratio, hp->ent_coef, hp->vf_clip, hp->critic_coef}; a.inv_count = inv_world / mb;
-        int blocks = std::max(1, std::min(148, (mb + 15) / 16));
+        int blocks = std::max(1, std::min(148, (mb + 7) / 8));      // one sample per warp up to 1184 samples
         size_t shb = (size_t)(lpi.K * (adim + 1) + adim + 1) * sizeof(float);
         if (kpl <= 2) XLAUNCH((ppo_heads_kernel<2, 8>), blocks, 256, shb, S(stream), a);
+        else if (kpl <= 8 && adim <= 4) XLAUNCH((ppo_heads_kernel<8, 4>), blocks, 256, shb, S(stream), a);
         else if (kpl <= 8) XLAUNCH((ppo_heads_kernel<8, 8>), blocks, 256, shb, S(stream), a);
         else XLAUNCH((ppo_heads_kernel<16, 4>), blocks, 256, shb, S(stream), a);
         LAUNCH_CHECK();
@@ -1791,6 +1792,7 @@ static int rollout_infer_launch(xtb_net* net, const void* obs, const int32_t* st
       const float *wp = net->params + lpi.w_off, *bp = net->params + lpi.b_off, *wv = net->params + lv.w_off, *bv = net->params + lv.b_off;
       int blocks = std::max(1, std::min(148, (E + 7) / 8));
       if (kpl <= 2) XLAUNCH((ppo_infer_heads_kernel<2, 8>), blocks, 256, 0, S(stream), hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
+      else if (kpl <= 8 && adim <= 4) XLAUNCH((ppo_infer_heads_kernel<8, 4>), blocks, 256, 0, S(stream), hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
       else if (kpl <= 8) XLAUNCH((ppo_infer_heads_kernel<8, 8>), blocks, 256, 0, S(stream), hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
       else XLAUNCH((ppo_infer_heads_kernel<16, 8>), blocks, 256, 0, S(stream), hp, hv, wp, bp, wv, bv, E, lpi.K, adim, seed, offset_dev, t, a_t, lp_t, v_o, xtb_net_tensor(net, pi_t));
     } else {

@@ -1,5 +1,5 @@
 """Seeded synthetic rollouts of the shapes SURVEY.md 8(d) fixes (no environment, no dataset): used by bench.py and the
-measurement scripts.  Product-side utility -- the CPU oracle has its own generator for the parity tests."""
+measurement scripts.  Product-side utility (the parity tests generate their own inputs)."""
 import numpy as np
 
 
