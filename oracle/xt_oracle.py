@@ -215,18 +215,41 @@ _ACT = {
 }
 
 
+# Arithmetic type of the network / loss / optimiser restatement.  fp32 is the reference's own precision (the golden
+# fixtures and every bit-exact comparison use it); "f64" is the same code in float64: the error yardstick -- a parity
+# test asserts |gpu - f64| <= 2 |torch-CPU fp32 - f64|, i.e. the CUDA path is as close to exact arithmetic as the
+# reference's own fp32 execution is.
+_PREC = {"t": torch.float32, "np": np.float32}
+
+
+class precision(object):
+    """with precision("f64"): ...   runs forward / learners / Adam in float64 (test-only yardstick)."""
+
+    def __init__(self, name):
+        self.new = {"f32": (torch.float32, np.float32), "f64": (torch.float64, np.float64)}[name]
+
+    def __enter__(self):
+        self.old = (_PREC["t"], _PREC["np"])
+        _PREC["t"], _PREC["np"] = self.new
+        return self
+
+    def __exit__(self, *exc):
+        _PREC["t"], _PREC["np"] = self.old
+        return False
+
+
 def forward(arch, weights, obs, keep=False):
     """Network forward in torch-CPU fp32.  obs: ndarray/tensor [B,*state_dim].
 
     uint8 inputs are cast and divided by 255 (model_utils.py:187-189,
     dqn_cnn.py:48, state_transform :192-201 with mean 0).  Conv = NHWC,
     HWIO kernels (Keras Conv2D); flatten in HWC order (Keras Flatten on NHWC)."""
-    wt = {k: (v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))) for k, v in weights.items()}
+    wt = {k: (v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))).to(_PREC["t"]) for k, v in weights.items()}
     x = obs if torch.is_tensor(obs) else torch.from_numpy(np.ascontiguousarray(obs))
     if arch["input_dtype"] == "uint8":
-        x = x.to(torch.float32) / 255.0
+        x = x.to(_PREC["t"]) / 255.0
     else:
-        x = x.to(torch.float32)
+        x = x.to(_PREC["t"])
     t = {"obs": x}
     for name, kind, src, sp in arch["layers"]:
         a = t[src]
@@ -390,13 +413,15 @@ class TFAdam:
         self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
         self.m = [torch.zeros_like(p) for p in params]
         self.v = [torch.zeros_like(p) for p in params]
-        self.b1p = np.float32(1.0)
-        self.b2p = np.float32(1.0)
+        self.f = _PREC["np"]
+        self.b1p = self.f(1.0)
+        self.b2p = self.f(1.0)
 
     def step(self, grads):
-        self.b1p = np.float32(self.b1p * np.float32(self.b1))
-        self.b2p = np.float32(self.b2p * np.float32(self.b2))
-        lr_t = np.float32(self.lr) * np.sqrt(np.float32(1) - self.b2p) / (np.float32(1) - self.b1p)
+        f = self.f
+        self.b1p = f(self.b1p * f(self.b1))
+        self.b2p = f(self.b2p * f(self.b2))
+        lr_t = f(self.lr) * np.sqrt(f(1) - self.b2p) / (f(1) - self.b1p)
         with torch.no_grad():
             for p, g, m, v in zip(self.params, grads, self.m, self.v):
                 m.mul_(self.b1).add_(g, alpha=1 - self.b1)
@@ -405,7 +430,7 @@ class TFAdam:
 
 
 def _as_param_list(weights):
-    return [torch.from_numpy(np.array(v, np.float32, copy=True)).requires_grad_(True) for v in weights.values()]
+    return [torch.from_numpy(np.array(v, _PREC["np"], copy=True)).requires_grad_(True) for v in weights.values()]
 
 
 class PpoLearner:
@@ -427,7 +452,7 @@ class PpoLearner:
     def loss_and_grads(self, obs, action, old_logp, adv, old_v, target_v):
         w = dict(zip(self.names, self.params))
         logits, v = forward(self.arch, w, obs)
-        tt = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).view(-1, 1)
+        tt = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=_PREC["np"])).view(-1, 1)
         loss = ppo_loss(logits, v, torch.from_numpy(np.ascontiguousarray(action)), tt(old_logp), tt(adv),
                         tt(old_v), tt(target_v), self.cr, self.ec, self.vfc, self.cc)
         grads = torch.autograd.grad(loss, self.params)

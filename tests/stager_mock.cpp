@@ -32,8 +32,9 @@ cudaError_t cudaEventSynchronize(cudaEvent_t e) { while (cudaEventQuery(e) != cu
 int main() {
   std::mt19937_64 rng(1);
   auto& st = xtb::Stager::instance();
-  size_t ring = xtb::Stager::CHUNK * xtb::Stager::SLOTS;
-  std::vector<size_t> sizes = {1, 100, xtb::Stager::CHUNK, xtb::Stager::CHUNK + 1, 903168, 3612672, ring - 1, ring + 77, 4 * ring + 12345};
+  size_t ring = xtb::Stager::RING_BYTES;
+  const size_t chunk = getenv("XTB_STAGE_CHUNK_KB") ? (size_t)atol(getenv("XTB_STAGE_CHUNK_KB")) << 10 : (256u << 10);
+  std::vector<size_t> sizes = {1, 100, chunk, chunk + 1, 903168, 3612672, ring - 1, ring + 77, 4 * ring + 12345};
   for (int it = 0; it < 150; it++) {
     size_t n = it < (int)sizes.size() ? sizes[it] : (rng() % (it % 7 == 0 ? 3 * ring : 2000000)) + 1;
     std::vector<unsigned char> src(n), dst(n, 0), keep;

@@ -3,6 +3,7 @@
 Tolerances: bit-exact for action indices on shared noise; fp results within 1e-3 relative
 (BASELINE.json north_star), measured as max|gpu-ref| / max(max|ref|, floor)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -325,9 +326,83 @@ def test_network_forward_backward(xb, tc_mode, case, B, smooth):
         bad = {k: "%.2e" % e for k, e in errs.items() if not e < REL}
     else:
         errs = {k: l2_rel(got[k], params[k].grad.numpy()) for k in w}
+        # mask flips (see the float64 test below); their relative weight grows as the batch shrinks: 1.5e-2 at B=64
         bad = {k: "%.2e" % e for k, e in errs.items() if not e < 3e-2}
     assert not bad, bad
     # round trip of the weight dict
     back = net.get_weights()
     for k in w:
         np.testing.assert_array_equal(back[k], w[k])
+
+
+from parity_record import record as _record  # noqa: E402
+
+
+@pytest.mark.parametrize("smooth", [True, False], ids=["tanh", "relu"])
+@pytest.mark.parametrize("case,B", [("ppo_cnn", 320), ("impala_cnn", 130), ("dqn_cnn", 129)])
+def test_gradient_distance_to_float64_vs_torch_cpu(xb, tc_mode, case, B, smooth):
+    """Round-1 verdict item 4: the float64 restatement (oracle precision("f64"), pinned by tests/test_oracle_f64.py) is the
+    yardstick; e_gpu = |gpu - f64| and e_cpu = |torch-CPU fp32 - f64|, forward tensors in max-norm and parameter gradients
+    in relative L2, at config batch sizes.
+
+    tanh variant (smooth: every kernel, no kinks): the fp32 CUDA-core path must be as close to exact arithmetic as the
+    reference's own fp32 run, e_gpu <= 2 e_cpu + 2e-6; the tcgen05 path carries 16-bit operand mantissas (bf16 hi + lo, the
+    lo*lo term dropped: ~2^-17 per operand against 2^-24) and is held to TC_FWD_BOUND / TC_GRAD_BOUND = about 4 x the
+    errors observed on B200 (1.3e-5 forward, 1.5e-5 gradients), two orders inside the 1e-3 contract.
+    ReLU networks: one unit whose pre-activation lies within the forward rounding error of zero takes the other branch and
+    moves the conv gradients by ~5e-4 in L2 -- observed on B200 for the GPU fp32 path on dqn_cnn (5.9e-4 against the CPU's
+    1.2e-6) and, the other way round, for torch-CPU fp32 on impala_cnn (CPU 6.0e-4, GPU 2.9e-7); with the 1e-5 forward error
+    of bf16x3 a handful flip at B=320 (2.6e-3).  Hence the flip allowances RELU_FLIP_*.  All observed errors are recorded in
+    gpurun_out/parity_errors.json and quoted in profiles/r2_results.md."""
+    from xingtian_b200.engine import Net
+    arch, _ = _arch_cases()[case]
+    if smooth:
+        arch = _smooth(arch)
+    w = orc.init_weights(arch, seed=11)
+    for k in w:
+        if k.endswith("/bias"):
+            w[k] = (np.random.default_rng(1).standard_normal(w[k].shape) * 0.05).astype(np.float32)
+    net = Net(arch, max_batch=B)
+    net.set_weights(w)
+    rng = np.random.default_rng(2)
+    obs = rng.integers(0, 256, (B,) + arch["state_dim"], dtype=np.uint8)
+    heads = arch["outputs"]
+    gh = {h: rng.standard_normal((B, int(np.prod(orc.tensor_shapes(arch)[h])))).astype(np.float32) for h in heads}
+
+    def cpu(prec):
+        with orc.precision(prec):
+            params = {k: torch.from_numpy(v.astype(np.float64 if prec == "f64" else np.float32)).requires_grad_(True) for k, v in w.items()}
+            t = orc.forward(arch, params, obs, keep=True)
+            loss = sum((t[h].reshape(B, -1) * torch.from_numpy(gh[h]).to(t[h].dtype)).sum() for h in heads)
+            loss.backward()
+            return ({n: t[n].detach().reshape(B, -1).numpy() for n, _, _, _ in arch["layers"]},
+                    {k: params[k].grad.numpy() for k in w})
+    f64_t, f64_g = cpu("f64")
+    f32_t, f32_g = cpu("f32")
+    obs_d = dev(obs)
+    net.forward(obs_d, B)
+    for h in heads:
+        net.tensor_grad(h)[:B].copy_(dev(gh[h]))
+    gpu_t = {n: net.tensor(n)[:B].cpu().numpy() for n, _, _, _ in arch["layers"]}
+    net.backward(obs_d, B, heads)
+    gpu_g = net.get_weights(net.grads)
+    fwd = {n: (rel_err(gpu_t[n], f64_t[n]), rel_err(f32_t[n], f64_t[n])) for n in gpu_t}
+    grd = {k: (l2_rel(gpu_g[k], f64_g[k]), l2_rel(f32_g[k], f64_g[k])) for k in w}
+    _record("grad_vs_f64/%s/B%d/%s/%s" % (case, B, "tanh" if smooth else "relu", "tcgen05" if tc_mode else "fp32"),
+            {"forward_max_rel(gpu,cpu32)": {k: ["%.2e" % a, "%.2e" % b] for k, (a, b) in fwd.items()},
+             "grad_l2_rel(gpu,cpu32)": {k: ["%.2e" % a, "%.2e" % b] for k, (a, b) in grd.items()}})
+    flip = 0.0 if smooth else (RELU_FLIP_TC if tc_mode else RELU_FLIP_F32)
+    if tc_mode:
+        bad = {k: v for k, v in fwd.items() if not v[0] < TC_FWD_BOUND}
+        bad.update({k: v for k, v in grd.items() if not v[0] < TC_GRAD_BOUND + flip})
+    else:
+        bad = {k: v for k, v in fwd.items() if not v[0] <= 2 * v[1] + F32_FLOOR}
+        bad.update({k: v for k, v in grd.items() if not v[0] <= 2 * v[1] + F32_FLOOR + flip})
+    assert not bad, bad
+
+
+F32_FLOOR = 2e-6          # a few fp32 ulps of summation-order slack on top of 2 x the CPU's own error
+TC_FWD_BOUND = 5e-5       # bf16x3 forward, max-norm relative to float64 (observed <= 1.3e-5)
+TC_GRAD_BOUND = 6e-5      # bf16x3 parameter gradients without kinks, relative L2 (observed <= 1.5e-5)
+RELU_FLIP_F32 = 2e-3      # ReLU mask flips at fp32 forward error (observed 5.9e-4, one or two units)
+RELU_FLIP_TC = 1e-2       # ... at bf16x3 forward error (observed 2.6e-3 at B=320)

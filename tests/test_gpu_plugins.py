@@ -526,11 +526,8 @@ def test_ppo_c2_full_iteration_matches_oracle(tc):
     = 52 SGD steps through prepare_data / train, against the oracle learner on the same shuffle stream: the whole
     per-step loss trace, the mean loss and the final weights.
 
-    Observed on B200: trace within 6.1e-3 (tcgen05 bf16x3) / 5.8e-3 (fp32 CUDA-core kernels), final weights within 3.1e-2 /
-    2.6e-2 in L2, update cosine 0.933 / 0.952.  Both arithmetic paths sit at the same distance from the torch-CPU oracle: over
-    52 Adam steps on noise-dominated gradients (synthetic advantages) any two fp32 summation orders drift apart like this,
-    so the bounds below are trajectory-level (and run-to-run variable: atomics); the per-step contract (1e-3) is asserted by
-    the single-step tests."""
+    Observed distances (to the float64 learner, for the CUDA path and for the torch-CPU fp32 learner) are recorded in
+    gpurun_out/parity_errors.json and quoted in profiles/r2_results.md."""
     import xingtian_b200 as xb
     from xingtian_b200 import capi
     E, T = 32, 128
@@ -545,36 +542,78 @@ def test_ppo_c2_full_iteration_matches_oracle(tc):
 
 
 def _c2_iteration_vs_oracle(alg, E, T, tc):
+    """Three learners on the same shuffle stream: the CUDA path, the torch-CPU fp32 oracle (the reference's arithmetic) and
+    the float64 oracle (the yardstick).  The GPU trajectory may sit at most twice as far from float64 as the reference's
+    own fp32 arithmetic does (plus the per-step 1e-3 contract as a floor)."""
+    from parity_record import record as _record
     w0 = alg.get_weights()
-    ref = orc.PpoLearner(orc.ppo_cnn_arch(), w0, lr=0.00025, batch_size=320, critic_coef=1.0, ent_coef=0.003, clip_ratio=0.1,
-                         max_grad_norm=5.0, num_sgd_iter=4, vf_clip=5.0)
+    kw = dict(lr=0.00025, batch_size=320, critic_coef=1.0, ent_coef=0.003, clip_ratio=0.1, max_grad_norm=5.0, num_sgd_iter=4,
+              vf_clip=5.0)
+    ref = orc.PpoLearner(orc.ppo_cnn_arch(), w0, **kw)
+    with orc.precision("f64"):
+        ref64 = orc.PpoLearner(orc.ppo_cnn_arch(), w0, **kw)
     trajs = make_trajs(E, T, seed=11)
     for tr in trajs:
         alg.prepare_data({k: tr[k] for k in ("cur_state", "action", "logp", "adv", "old_value", "target_value")})
     np.random.seed(5)
     loss = alg.train()
-    np.random.seed(5)
     cat = lambda k: np.concatenate([t[k] for t in trajs])
-    ref_loss, ref_trace = ref.train([cat("cur_state")], [cat("action"), cat("logp"), cat("adv").astype(np.float32),
-                                                          cat("old_value"), cat("target_value").astype(np.float32)])
+    label = [cat("action"), cat("logp"), cat("adv").astype(np.float32), cat("old_value"), cat("target_value").astype(np.float32)]
+    np.random.seed(5)
+    ref_loss, ref_trace = ref.train([cat("cur_state")], label)
+    np.random.seed(5)
+    with orc.precision("f64"):
+        loss64, trace64 = ref64.train([cat("cur_state")], label)
     trace = alg.actor.last_losses
-    assert len(trace) == len(ref_trace) == 52
-    w1, r1 = alg.get_weights(), ref.weights()
-    upd = np.concatenate([(w1[k] - w0[k]).ravel() for k in w0])
-    rupd = np.concatenate([(r1[k] - w0[k]).ravel() for k in w0])
-    cos = float(np.dot(upd, rupd) / (np.linalg.norm(upd) * np.linalg.norm(rupd)))
-    print("C2 parity (tc=%d): trace rel err %.3e, loss %.6f vs %.6f, update cosine %.5f, update l2_rel %.3e" %
-          (tc, rel_err(trace, ref_trace), loss, ref_loss, cos, l2_rel(upd, rupd)))
-    # trajectory-level bounds (split-K / bias-gradient atomics make the rounding order differ from run to run, and 52
-    # Adam steps amplify it: the trace distance was 6e-3 in two runs and above 1e-2 in a third); a wrong gradient or
-    # optimiser constant shows up as tens of percent here
-    assert rel_err(trace, ref_trace) < 5e-2, (trace, ref_trace)
-    assert abs(loss - ref_loss) < 2e-2 * max(1.0, abs(ref_loss))
-    # 52 Adam steps turn ulp-level differences on near-zero gradients into +-lr random walks, so the *update* direction is
-    # only reported; the final weights themselves must agree norm-wise
-    flat = lambda w: np.concatenate([w[k].ravel() for k in w0])
-    print("C2 parity (tc=%d): final weights l2_rel %.3e" % (tc, l2_rel(flat(w1), flat(r1))))
-    assert l2_rel(flat(w1), flat(r1)) < 2e-1, (l2_rel(flat(w1), flat(r1)), cos)
+    assert len(trace) == len(ref_trace) == len(trace64) == 52
+    w1, r1, r64 = alg.get_weights(), ref.weights(), ref64.weights()
+    flat = lambda w: np.concatenate([np.asarray(w[k], np.float64).ravel() for k in w0])
+    upd, rupd, upd64 = flat(w1) - flat(w0), flat(r1) - flat(w0), flat(r64) - flat(w0)
+    cos = lambda a, b: float(np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b)))
+    obs = {"trace_rel(gpu,f64)": rel_err(trace, trace64), "trace_rel(cpu32,f64)": rel_err(ref_trace, trace64),
+           "trace_rel(gpu,cpu32)": rel_err(trace, ref_trace),
+           "first3_rel(gpu,f64)": rel_err(trace[:3], trace64[:3]), "first3_rel(cpu32,f64)": rel_err(ref_trace[:3], trace64[:3]),
+           "weights_l2(gpu,f64)": l2_rel(flat(w1), flat(r64)), "weights_l2(cpu32,f64)": l2_rel(flat(r1), flat(r64)),
+           "update_l2(gpu,f64)": l2_rel(upd, upd64), "update_l2(cpu32,f64)": l2_rel(rupd, upd64),
+           "update_cos(gpu,f64)": cos(upd, upd64), "update_cos(cpu32,f64)": cos(rupd, upd64),
+           "mean_loss": [loss, ref_loss, loss64]}
+    _record("c2_iteration/%s" % ("tcgen05" if tc else "fp32"), {k: (["%.6f" % x for x in v] if isinstance(v, list) else "%.3e" % v) for k, v in obs.items()})
+    # the first steps carry no amplification yet: the per-step contract
+    assert obs["first3_rel(gpu,f64)"] < REL
+    # 52 Adam steps on noise-dominated gradients amplify any rounding difference (ReLU mask flips, m/sqrt(v) on near-zero
+    # gradients): the reference's own fp32 run drifts from float64 too, and the CUDA path may drift at most twice as far
+    assert obs["trace_rel(gpu,f64)"] <= max(2 * obs["trace_rel(cpu32,f64)"], C2_TRACE_FLOOR), obs
+    assert abs(loss - loss64) <= max(2 * abs(ref_loss - loss64), C2_TRACE_FLOOR * max(1.0, abs(loss64))), obs
+    assert obs["weights_l2(gpu,f64)"] <= max(2 * obs["weights_l2(cpu32,f64)"], C2_WEIGHT_FLOOR), obs
+
+
+# floors of the trajectory-level bounds: the verdict's targets for a reduction-order-deterministic step
+C2_TRACE_FLOOR = 1e-2
+C2_WEIGHT_FLOOR = 5e-2
+
+
+def test_ppo_training_is_bitwise_reproducible():
+    """No atomics on the PPO step (ordered split-K finish, per-CTA weight-gradient slabs, per-block head slabs reduced in
+    block order): two runs from the same weights and shuffle stream give identical loss traces and identical weights."""
+    import xingtian_b200 as xb
+    E, T = 16, 64
+    trajs = make_trajs(E, T, seed=13)
+    runs = []
+    w_init = None
+    for _ in range(2):
+        alg = xb.alg_builder("PPO", ppo_cnn_info(batch=320, iters=2), alg_cfg(instance_num=E))
+        if w_init is None:
+            w_init = alg.get_weights()
+        alg.set_weights(w_init)
+        for tr in trajs:
+            alg.prepare_data({k: tr[k] for k in ("cur_state", "action", "logp", "adv", "old_value", "target_value")})
+        np.random.seed(21)
+        alg.train()
+        runs.append((np.asarray(alg.actor.last_losses, np.float32), alg.get_weights()))
+    assert len(runs[0][0]) == 2 * 4                     # 1024 samples / 320 -> 4 minibatches (ragged last one) x 2 epochs
+    assert np.array_equal(runs[0][0], runs[1][0]), (runs[0][0], runs[1][0])
+    for k in runs[0][1]:
+        assert np.array_equal(runs[0][1][k], runs[1][1][k]), k
 
 
 def test_batched_predictor_serves_real_ppo_cnn():

@@ -145,8 +145,9 @@ def test_stager_thread_pool_with_mock_dma(repo_root, tmp_path):
     subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I/usr/local/cuda/include",
                     "-I" + os.path.join(repo_root, "xingtian_b200", "csrc"),
                     os.path.join(repo_root, "tests", "stager_mock.cpp"), "-o", str(exe)], check=True, capture_output=True)
-    for threads in ("0", "1", "6"):
-        res = subprocess.run([str(exe)], env=dict(os.environ, XTB_STAGE_THREADS=threads), capture_output=True, text=True, timeout=300)
+    for threads, chunk_kb in (("0", "256"), ("1", "256"), ("6", "256"), ("6", "64"), ("3", "128")):
+        res = subprocess.run([str(exe)], env=dict(os.environ, XTB_STAGE_THREADS=threads, XTB_STAGE_CHUNK_KB=chunk_kb),
+                             capture_output=True, text=True, timeout=300)
         assert res.returncode == 0 and "all ok" in res.stdout, res.stdout[-500:]
 
 

@@ -915,6 +915,7 @@ struct RedSeg {
   int kind;                                          // 0: conv weight partials [R][128][N]; 1: plain vector (bias)
   int N, C, KW, mts, s2d_k4;                         // conv mapping
   long long dst_off; float alpha;
+  float* dst_ptr;                                    // destination base instead of the gradient bucket (kind 1), or NULL
 };
 // real HWIO row of row k' = ((ty*k4 + tx)*16 + dy*4 + dx)*4 + c of the (k4 x k4, stride 1, 64 channel) conv over a
 // space-to-depth plane: ((4ty+dy)*4k4 + 4tx+dx)*4 + c of the (4k4 x 4k4, stride 4, 4 channel) conv
@@ -974,7 +975,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const __grid_constant_
       if (s.s2d_k4) row = s2d_real_row(row, s.s2d_k4);
       dst = s.dst_off + (long long)row * s.N + n;
     } else dst = s.dst_off + ie;
-    grads[dst] = s.alpha * v[e];
+    (s.dst_ptr ? s.dst_ptr : grads)[dst] = s.alpha * v[e];
   }
 }
 

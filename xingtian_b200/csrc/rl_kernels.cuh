@@ -444,10 +444,13 @@ struct PpoHeadsArgs {
   __nv_bfloat16* gp_hi; long long gp_lo; __nv_bfloat16* gv_hi; long long gv_lo;   // their batch-planar bf16 planes (bp_gemm.cuh), may be NULL
   int pitch;                               // rows per feature chunk of those planes
   const float* w_pi; const float* b_pi; const float* w_v; const float* b_v;
-  float* dw_pi; float* db_pi; float* dw_v; float* db_v;
-  float* dbh_pi; float* dbh_v;             // bias gradients of the layers that produced h_pi / h_v (column sums of g)
+  // Parameter-gradient partial sums, one slab of `slab` floats per block, reduced afterwards in block order by
+  // bp::grad_reduce_kernel (no atomics: the step is bitwise reproducible).  Slab layout (K hidden units, A actions):
+  // [dW_pi K*A | dW_v K | dbh_pi K | dbh_v K | db_pi A | db_v 1 | loss 1]; dbh_* = bias gradients of the layers that
+  // produced h_pi / h_v (column sums of g).
+  float* part; int slab;
   const int32_t* idx; const int32_t* action; const float* old_logp; const float* adv; const float* old_v; const float* target_v;
-  float* logits_out; float* v_out; float* loss_out;
+  float* logits_out; float* v_out;
   int B, K, A, act_pi, act_v, shared;
   PpoHyperDev hp; float inv_count;
 };
@@ -455,12 +458,10 @@ struct PpoHeadsArgs {
 template <int HEAD_KPL, int HEAD_AMAX>
 __global__ void __launch_bounds__(256) ppo_heads_kernel(PpoHeadsArgs a) {
   pdl_wait(); pdl_trigger();
-  extern __shared__ float sh_dw[];          // [K*(A+1) + (A+1)] block-level weight/bias gradient accumulators
+  extern __shared__ float sh_dw[];          // [nwarp][nacc] per-warp partial sums in slab layout
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int K = a.K, A = a.A, kpl = K / 32;
-  const int nacc = K * (A + 1) + (A + 1);
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sh_dw[i] = 0.f;
-  __syncthreads();
+  const int nacc = K * A + 3 * K + A + 2;
   float wpi[HEAD_KPL][HEAD_AMAX], wv[HEAD_KPL];
   float dwp[HEAD_KPL][HEAD_AMAX], dwv[HEAD_KPL];
 #pragma unroll
@@ -583,49 +584,32 @@ __global__ void __launch_bounds__(256) ppo_heads_kernel(PpoHeadsArgs a) {
       }
     }
   }
-  // ---- block reduction of the parameter gradients, then one atomic per parameter per block
+  // ---- every warp parks its sums in its own row; the rows are added in warp order and written to this block's slab
+  float* row = sh_dw + (size_t)warp * nacc;
 #pragma unroll
   for (int j = 0; j < HEAD_KPL; j++) {
     if (j < kpl) {
       int k = lane + 32 * j;
 #pragma unroll
-      for (int i = 0; i < HEAD_AMAX; i++) if (i < A) atomicAdd(&sh_dw[k * (A + 1) + i], dwp[j][i]);
-      atomicAdd(&sh_dw[k * (A + 1) + A], dwv[j]);
+      for (int i = 0; i < HEAD_AMAX; i++) if (i < A) row[k * A + i] = dwp[j][i];
+      row[K * A + k] = dwv[j];
+      row[K * A + K + k] = bh_pi[j];
+      row[K * A + 2 * K + k] = a.shared ? 0.f : bh_v[j];
     }
   }
   if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < HEAD_AMAX; i++) if (i < A) atomicAdd(&sh_dw[K * (A + 1) + i], dbp[i]);
-    atomicAdd(&sh_dw[K * (A + 1) + A], dbv);
+    for (int i = 0; i < HEAD_AMAX; i++) if (i < A) row[K * A + 3 * K + i] = dbp[i];
+    row[K * A + 3 * K + A] = dbv;
+    row[K * A + 3 * K + A + 1] = lsum;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < K * (A + 1); i += blockDim.x) {
-    int k = i / (A + 1), n = i - k * (A + 1);
-    float g = sh_dw[i];
-    if (n < A) atomicAdd(a.dw_pi + k * A + n, g); else atomicAdd(a.dw_v + k, g);
+  float* out = a.part + (size_t)blockIdx.x * a.slab;
+  for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
+    float t = sh_dw[e];
+    for (int w = 1; w < nwarp; w++) t += sh_dw[(size_t)w * nacc + e];
+    out[e] = t;
   }
-  if (threadIdx.x <= A) {
-    float g = sh_dw[K * (A + 1) + threadIdx.x];
-    if ((int)threadIdx.x < A) atomicAdd(a.db_pi + threadIdx.x, g); else atomicAdd(a.db_v, g);
-  }
-  // bias gradients of the hidden layer(s): column sums of g, reduced over the block through shared memory
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) sh_dw[i] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < HEAD_KPL; j++) {
-    if (j < kpl) {
-      int k = lane + 32 * j;
-      atomicAdd(&sh_dw[k], bh_pi[j]);
-      if (!a.shared) atomicAdd(&sh_dw[K + k], bh_v[j]);
-    }
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    if (a.dbh_pi) atomicAdd(a.dbh_pi + k, sh_dw[k]);
-    if (!a.shared && a.dbh_v) atomicAdd(a.dbh_v + k, sh_dw[K + k]);
-  }
-  block_atomic_add(lsum, a.loss_out);
 }
 
 // Inference heads: logits / value of both dense heads + Gumbel-max sampling in one kernel (one warp per sample).

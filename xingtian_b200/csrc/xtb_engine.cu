@@ -236,7 +236,7 @@ struct xtb_net {
   size_t obs_bp_off = 0; int obs_feats = 0;            // decoded-frame plane (space-to-depth canvas)
   int H4 = 0, W4 = 0;
   size_t blob_off = 0; long long blob_elems = 0;       // weight blobs: hi plane, lo plane follows
-  size_t splitk_off = 0, zeros_off = 0, segs_off = 0;
+  size_t splitk_off = 0, zeros_off = 0, segs_off = 0, heads_part_off = 0;
   std::vector<bp::BlobSeg> blob_segs;
   bool any_tc = false;
   float* params = nullptr; float* grads = nullptr; char* ws = nullptr;
@@ -451,6 +451,8 @@ extern "C" int xtb_net_create(const xtb_net_desc* desc, int max_batch, xtb_net**
     w += align_up(need + 256, 256);
   }
   net->zeros_off = w; w += 4096;
+  // per-block parameter-gradient slabs of the fused PPO heads kernel (K <= 512 hidden units, A <= 8 actions)
+  net->heads_part_off = w; w += align_up((size_t)kSMs * (512 * 8 + 3 * 512 + 16) * sizeof(float), 256);
   net->segs_off = w; w += align_up(sizeof(bp::BlobSeg) * XTB_MAX_LAYERS, 256);
   net->ws_bytes = w;
   net->f32_ok.assign(nt, 0); net->bp_ok.assign(nt, 0); net->gf32_ok.assign(nt, 0); net->gbp_ok.assign(nt, 0);
@@ -584,6 +586,10 @@ static cudaError_t ensure_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(bp::bp_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(bp::bp_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(bp::bp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(xtb::ppo_heads_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(xtb::ppo_heads_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(xtb::ppo_heads_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(xtb::ppo_heads_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
   done = true;
   return cudaSuccess;
 }
@@ -1154,7 +1160,7 @@ static int net_backward_impl(xtb_net* net, const void* obs, const int32_t* gathe
   std::vector<char> has_grad(nl + 1, 0), written(nl + 1, 0);
   long long early_off = 0, early_cnt = 0;
   for (int t = 1; t <= nl; t++) net->gf32_ok[t] = net->gbp_ok[t] = 0;
-  net->pending.clear();
+  if (zero_grads) net->pending.clear();      // a fused loss kernel (zero_grads == false) has queued its own reductions
   for (int h = 0; h < n_heads; h++) {
     int t = head_tensors[h];
     if (t < 1 || t > nl) return fail(XTB_ERR_ARG, "bad head tensor %d", t);
@@ -1521,6 +1527,7 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
       if (rc) return rc;
       if (fuse) {
         CUDA_TRY(cudaMemsetAsync(net->grads, 0, net->n_params * sizeof(float), S(stream)));
+        net->pending.clear();
         PpoHeadsArgs a;
         a.h_pi = (const float*)(net->ws + net->out_off[lpi.d.src]); a.h_v = (const float*)(net->ws + net->out_off[lv.d.src]);
         a.g_pi = (float*)(net->ws + net->gout_off[lpi.d.src]); a.g_v = (float*)(net->ws + net->gout_off[lv.d.src]);
@@ -1531,25 +1538,41 @@ static int ppo_train_launch(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout* 
         a.gv_hi = bp_v ? gout_bp(net, lv.d.src).hi : nullptr; a.gv_lo = net->plane_elems[lv.d.src];
         a.pitch = net->pitch;
         a.w_pi = net->params + lpi.w_off; a.b_pi = net->params + lpi.b_off; a.w_v = net->params + lv.w_off; a.b_v = net->params + lv.b_off;
-        a.dw_pi = net->grads + lpi.w_off; a.db_pi = net->grads + lpi.b_off; a.dw_v = net->grads + lv.w_off; a.db_v = net->grads + lv.b_off;
         // the hidden layers' bias gradients (column sums of g) when they are dense and only feed the heads
         auto only_feeds_heads = [&](int tsr) { for (int j = 0; j < (int)net->L.size(); j++) if (net->L[j].d.src == tsr && !(skip & (1u << j))) return false; return true; };
         bool bh_pi_ok = net->L[lpi.d.src - 1].d.kind == XTB_DENSE && only_feeds_heads(lpi.d.src);
         bool bh_v_ok = net->L[lv.d.src - 1].d.kind == XTB_DENSE && only_feeds_heads(lv.d.src);
-        a.dbh_pi = bh_pi_ok ? net->grads + net->L[lpi.d.src - 1].b_off : nullptr;
-        a.dbh_v = bh_v_ok ? net->grads + net->L[lv.d.src - 1].b_off : nullptr;
         unsigned bias_done = (bh_pi_ok ? (1u << lpi.d.src) : 0u) | ((lpi.d.src != lv.d.src && bh_v_ok) ? (1u << lv.d.src) : 0u);
         a.idx = idx; a.action = ro->action; a.old_logp = ro->old_logp; a.adv = ro->adv; a.old_v = ro->old_v; a.target_v = ro->target_v;
-        a.logits_out = xtb_net_tensor(net, pi_t); a.v_out = xtb_net_tensor(net, v_t); a.loss_out = loss_per_step + step;
+        a.logits_out = xtb_net_tensor(net, pi_t); a.v_out = xtb_net_tensor(net, v_t);
         a.B = mb; a.K = lpi.K; a.A = adim; a.act_pi = lpi.src_act; a.act_v = lv.src_act; a.shared = lpi.d.src == lv.d.src ? 1 : 0;
         a.hp = PpoHyperDev{hp->clip_ratio, hp->ent_coef, hp->vf_clip, hp->critic_coef}; a.inv_count = inv_world / mb;
         int blocks = std::max(1, std::min(148, (mb + 7) / 8));      // one sample per warp up to 1184 samples
-        size_t shb = (size_t)(lpi.K * (adim + 1) + adim + 1) * sizeof(float);
+        const int HK = lpi.K, nacc = HK * adim + 3 * HK + adim + 2;
+        a.part = (float*)(net->ws + net->heads_part_off); a.slab = (nacc + 3) & ~3;
+        size_t shb = (size_t)8 * nacc * sizeof(float);
+        { cudaError_t ea = ensure_kernel_attrs(); if (ea != cudaSuccess) return fail(XTB_ERR_CUDA, "kernel attributes: %s", cudaGetErrorString(ea)); }
         if (kpl <= 2) XLAUNCH((ppo_heads_kernel<2, 8>), blocks, 256, shb, S(stream), a);
         else if (kpl <= 8 && adim <= 4) XLAUNCH((ppo_heads_kernel<8, 4>), blocks, 256, shb, S(stream), a);
         else if (kpl <= 8) XLAUNCH((ppo_heads_kernel<8, 8>), blocks, 256, shb, S(stream), a);
         else XLAUNCH((ppo_heads_kernel<16, 4>), blocks, 256, shb, S(stream), a);
         LAUNCH_CHECK();
+        {   // ordered reduction of the per-block slabs (queued; runs with the other partial sums at the end of backward)
+          auto seg = [&](int off, int count, long long dst_off, float* dst_ptr) {
+            bp::RedSeg r;
+            memset(&r, 0, sizeof r);
+            r.part = a.part + off; r.n_slabs = blocks; r.slab = a.slab; r.count = count; r.kind = 1;
+            r.dst_off = dst_off; r.alpha = 1.f; r.dst_ptr = dst_ptr;
+            net->pending.push_back(r);
+          };
+          seg(0, HK * adim, lpi.w_off, nullptr);
+          seg(HK * adim, HK, lv.w_off, nullptr);
+          if (bh_pi_ok) seg(HK * adim + HK, HK, net->L[lpi.d.src - 1].b_off, nullptr);
+          if (!a.shared && bh_v_ok) seg(HK * adim + 2 * HK, HK, net->L[lv.d.src - 1].b_off, nullptr);
+          seg(HK * adim + 3 * HK, adim, lpi.b_off, nullptr);
+          seg(HK * adim + 3 * HK + adim, 1, lv.b_off, nullptr);
+          seg(HK * adim + 3 * HK + adim + 1, 1, 0, loss_per_step + step);
+        }
         int srcs[2] = {lpi.d.src, lv.d.src};
         unsigned hbp = (bp_pi ? (1u << lpi.d.src) : 0u) | (bp_v ? (1u << lv.d.src) : 0u);   // the fused kernel wrote planes there
         rc = net_backward_impl(net, ro->obs, idx, mb, srcs, a.shared ? 1 : 2, stream, skip, false, bias_done, hbp, g_comm);
