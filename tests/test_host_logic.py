@@ -180,3 +180,26 @@ def test_space_to_depth_identity_of_the_first_conv_layer():
     cols = np.stack([plane[:, ty:ty + OH, tx:tx + OW, :] for ty in range(k4) for tx in range(k4)], axis=3)
     out = cols.reshape(B, OH, OW, k4 * k4 * 64) @ w2
     assert np.allclose(out, ref, rtol=1e-4, atol=1e-2)
+
+
+def test_algorithm_base_subclasses_the_reference_when_importable(tmp_path, repo_root):
+    """algorithm/base.py: under xt_main (reference package on the path) Algorithm inherits xt.algorithm.algorithm.Algorithm
+    and only replaces construction; stand-alone it falls back to its own surface.  The reference itself cannot be imported
+    by this interpreter (zeus/common/utils.py:17 imports `imp`, gone in Python 3.12), so a stand-in package plays its part."""
+    import subprocess
+    import sys
+    pkg = tmp_path / "xt" / "algorithm"
+    pkg.mkdir(parents=True)
+    (tmp_path / "xt" / "__init__.py").write_text("")
+    (pkg / "__init__.py").write_text("")
+    (pkg / "algorithm.py").write_text(
+        "class Algorithm(object):\n    marker = 'reference'\n    def __init__(self, *a, **k):\n        raise RuntimeError('reference ctor must not run')\n"
+        "    def if_save(self, n):\n        return 'ref-if-save'\n")
+    code = ("from xingtian_b200.algorithm.base import Algorithm, _StandaloneSurface\n"
+            "print(Algorithm.inherits_reference, getattr(Algorithm, 'marker', None), issubclass(Algorithm, _StandaloneSurface))\n")
+    env = dict(os.environ, PYTHONPATH=str(tmp_path) + os.pathsep + repo_root)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert out.stdout.split() == ["True", "reference", "False"], (out.stdout, out.stderr[-500:])
+    env = dict(os.environ, PYTHONPATH=repo_root)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=str(pkg))
+    assert out.stdout.split() == ["False", "None", "True"], (out.stdout, out.stderr[-500:])
