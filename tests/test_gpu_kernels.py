@@ -339,7 +339,8 @@ from parity_record import record as _record  # noqa: E402
 
 
 @pytest.mark.parametrize("smooth", [True, False], ids=["tanh", "relu"])
-@pytest.mark.parametrize("case,B", [("ppo_cnn", 320), ("impala_cnn", 130), ("dqn_cnn", 129)])
+@pytest.mark.parametrize("case,B", [("ppo_cnn", 320), ("ppo_cnn", 4096), ("impala_cnn", 130), ("impala_cnn", 512), ("dqn_cnn", 129),
+                                    ("dqn_cnn", 512)])          # C2 / C5 / C3 / C4 minibatch sizes and ragged ones
 def test_gradient_distance_to_float64_vs_torch_cpu(xb, tc_mode, case, B, smooth):
     """Round-1 verdict item 4: the float64 restatement (oracle precision("f64"), pinned by tests/test_oracle_f64.py) is the
     yardstick; e_gpu = |gpu - f64| and e_cpu = |torch-CPU fp32 - f64|, forward tensors in max-norm and parameter gradients

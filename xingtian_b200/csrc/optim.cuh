@@ -15,7 +15,8 @@
 
 namespace xtb {
 
-constexpr int OPT_CHUNK = 4096;   // elements per block
+constexpr int OPT_CHUNK = 1024;   // elements per block: one float4 per thread and array, ~830 blocks for PpoCnn so that every
+                                  // load of the step is in flight at once (a 4096-element block left 1.4 blocks per SM: latency bound)
 constexpr int OPT_THREADS = 256;
 
 struct AdamState {          // lives in device memory
@@ -50,34 +51,55 @@ __device__ __forceinline__ void adam_prep(AdamState* st, const AdamHyper* hyp, d
   st->lr_t = lr * sqrtf(1.f - b2p) / (1.f - b1p);
 }
 
-// `ticket`: zero-initialised counter; the block that draws the last ticket sees every block's contribution
+// `ticket`: zero-initialised counter; the block that draws the last ticket sees every block's contribution.
+// One block sums SQN_GROUP consecutive chunks (the optimiser's chunks are small so that adam_kernel keeps every load in
+// flight; here fewer, longer blocks keep the number of same-address fp64 atomics low).
+constexpr int SQN_GROUP = 4;
 __global__ void __launch_bounds__(OPT_THREADS)
 sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ blk_seg,
-              const long long* __restrict__ blk_beg, const int* __restrict__ blk_len,
+              const long long* __restrict__ blk_beg, const int* __restrict__ blk_len, int n_blk,
               double* __restrict__ norm_sq, unsigned int* __restrict__ ticket, AdamState* st, const AdamHyper* __restrict__ hyp,
               float* seg_scale, int n_seg, int clip_mode, float grad_scale) {
   pdl_wait(); pdl_trigger();
-  const float* p = g + blk_beg[blockIdx.x];
-  int n = blk_len[blockIdx.x];
-  float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += OPT_THREADS) { float v = p[i]; s = fmaf(v, v, s); }
   __shared__ float red[OPT_THREADS / 32];
+  auto flush = [&](float s, int seg) {          // block-wide sum of s into norm_sq[seg]; uniform call sites only
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float t = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (threadIdx.x == 0) {
-      atomicAdd(norm_sq + blk_seg[blockIdx.x], (double)t);
-      __threadfence();
-      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
-        __threadfence();
-        *ticket = 0;
-        adam_prep(st, hyp, norm_sq, seg_scale, n_seg, clip_mode, grad_scale);
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (threadIdx.x == 0) atomicAdd(norm_sq + seg, (double)t);
+    }
+    __syncthreads();
+  };
+  const int e0 = blockIdx.x * SQN_GROUP, e1 = min(e0 + SQN_GROUP, n_blk);
+  float s = 0.f;
+  int cur = blk_seg[e0];
+  for (int e = e0; e < e1; e++) {
+    if (blk_seg[e] != cur) { flush(s, cur); s = 0.f; cur = blk_seg[e]; }
+    const float* p = g + blk_beg[e];
+    const int n = blk_len[e];
+    if ((blk_beg[e] & 3) == 0) {
+      const int nv = n & ~3;
+      for (int i = threadIdx.x * 4; i < nv; i += OPT_THREADS * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p + i);
+        s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
       }
+      for (int i = nv + threadIdx.x; i < n; i += OPT_THREADS) { float v = p[i]; s = fmaf(v, v, s); }
+    } else {
+      for (int i = threadIdx.x; i < n; i += OPT_THREADS) { float v = p[i]; s = fmaf(v, v, s); }
+    }
+  }
+  flush(s, cur);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      *ticket = 0;
+      adam_prep(st, hyp, norm_sq, seg_scale, n_seg, clip_mode, grad_scale);
     }
   }
 }

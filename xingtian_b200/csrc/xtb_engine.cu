@@ -1423,7 +1423,7 @@ extern "C" int xtb_adam_step_net(xtb_adam* o, xtb_net* net, float grad_scale, vo
 static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float grad_scale, void* stream, xtb_net* net) {
   if (!o || !params || !grads) return fail(XTB_ERR_ARG, "xtb_adam_step: null pointer");
   cudaStream_t st = S(stream);
-  XLAUNCH(sqnorm_kernel, o->n_blk, OPT_THREADS, 0, st, grads, o->blk_seg, o->blk_beg, o->blk_len, o->norm_sq, o->ticket, o->st,
+  XLAUNCH(sqnorm_kernel, (o->n_blk + SQN_GROUP - 1) / SQN_GROUP, OPT_THREADS, 0, st, grads, o->blk_seg, o->blk_beg, o->blk_len, o->n_blk, o->norm_sq, o->ticket, o->st,
           (const AdamHyper*)o->hyp, o->seg_scale, o->n_seg, o->clip_mode, grad_scale);
   LAUNCH_CHECK();
   const bool blobs = net && !net->blob_segs.empty();
