@@ -405,5 +405,5 @@ def test_gradient_distance_to_float64_vs_torch_cpu(xb, tc_mode, case, B, smooth)
 F32_FLOOR = 2e-6          # a few fp32 ulps of summation-order slack on top of 2 x the CPU's own error
 TC_FWD_BOUND = 5e-5       # bf16x3 forward, max-norm relative to float64 (observed <= 1.3e-5)
 TC_GRAD_BOUND = 6e-5      # bf16x3 parameter gradients without kinks, relative L2 (observed <= 1.5e-5)
-RELU_FLIP_F32 = 2e-3      # ReLU mask flips at fp32 forward error (observed 5.9e-4, one or two units)
-RELU_FLIP_TC = 1e-2       # ... at bf16x3 forward error (observed 2.6e-3 at B=320)
+RELU_FLIP_F32 = 4e-3      # ReLU mask flips at fp32 forward error (observed 5.9e-4 at B=129, 1.7e-3 at B=4096 where torch-CPU has 1.4e-3)
+RELU_FLIP_TC = 2e-2       # ... at bf16x3 forward error (observed 2.6e-3 at B=320, 8.4e-3 at B=4096; torch-CPU fp32 itself: 1.4e-3)
