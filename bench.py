@@ -33,6 +33,11 @@ A = 4
 STATE = (84, 84, 4)
 METRIC = "learner env-steps/sec (Atari 84x84x4 PPO)"
 
+
+def metric_name(workload):
+    """BASELINE.json's metric for the PPO workloads; the IMPALA / DQN lines name their algorithm."""
+    return METRIC.replace("PPO", {"impala": "IMPALA", "dqn": "DQN"}.get(workload, "PPO"))
+
 WORKLOADS = {
     "ppo": dict(kind="ppo", E=32, T=128, B=320, epochs=4, scaling="weak", flop_per_env_step=164e6,
                 cpu_sample=dict(infer=128, sgd=52),
@@ -235,7 +240,7 @@ def run_reference(args):
     times = [cpu_iteration(st) for _ in range(args.steps)]
     t = float(np.mean(times))
     val = samples_per_iteration(wl) / t
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "env-steps/s",
+    out = {"impl": "reference", "metric": metric_name(args.workload), "value": val, "unit": "env-steps/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": wl["desc"]},
@@ -346,7 +351,8 @@ class ImpalaBench(object):
         self.done = torch.from_numpy(self.ro["done"].view(np.uint8)).to(dev)
         self.reward = torch.from_numpy(self.ro["reward"].astype(np.float32)).to(dev)
         self.step_idx = (torch.arange(E, dtype=torch.int32, device=dev)[None, :] * T + torch.arange(T, dtype=torch.int32, device=dev)[:, None]).contiguous()
-        self.samp_act = torch.empty(E, dtype=torch.int32, device=dev); self.samp_logp = torch.empty(E, device=dev)
+        self.act_t = torch.empty(T, E, dtype=torch.int32, device=dev); self.logp_t = torch.empty(T, E, device=dev)
+        self.val_t = torch.empty(T, E, device=dev)
         self.loss = torch.zeros(1, device=dev)
         self.train_batch = self.B
         self.h2d = 2 * self.n * int(np.prod(STATE)) + self.n * (A * 4 + 4 + 1 + 4)
@@ -359,10 +365,8 @@ class ImpalaBench(object):
         m, E, T = self.model, self.E, self.T
         net = m.net
         if ev: ev[0].record()
-        for t in range(T):                                  # batched policy inference of the actors' step t
-            net.forward(self.obs, E, idx=self.step_idx[t])
-            capi.check(net.lib.xtb_categorical_sample(_ptr(net.tensor(m.logit_name)), E, A, None, 1234, t,
-                                                      _ptr(self.samp_act), _ptr(self.samp_logp), stream_ptr()))
+        # batched policy inference of the actors' T steps: one CUDA graph (forward + fused heads + Philox sampling per step)
+        m.rollout_infer_device(self.obs, self.step_idx, E, T, self.act_t, self.logp_t, self.val_t)
         if ev: ev[1].record()
         if ev: ev[2].record()
         for s in range(self.n // self.B):
@@ -604,7 +608,7 @@ def run_b200(args):
         tc = float(np.mean([cpu_iteration(st) for _ in range(2)]))
         cpu = {"value": samples_per_iteration(wl) / tc, "unit": "env-steps/s", "cores": st["threads"], "host_cpus": os.cpu_count(),
                "kind": "port", "sample": sample_desc(args.workload)}
-    out = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world,
+    out = {"metric": metric_name(args.workload), "value": value, "unit": "env-steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate in TMEM)", "data": "synthetic",
            "config": {"workload": wl["desc"]},

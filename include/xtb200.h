@@ -249,6 +249,13 @@ int xtb_ppo_predict_host(xtb_net* net, const void* obs_host, size_t obs_bytes, v
                          int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
                          float* out_dev, float* out_host, int use_graph, void* stream);
 
+/* The same call for actors whose predict() also returns the logits (ImpalaCnnOpt.predict,
+ * xt/model/impala/impala_cnn_opt.py:267-277: [logits, baseline, action]): additionally copies the [n_env, A] logits of
+ * tensor `pi_tensor` into `logits_host` (pinned; NULL = skip) before the synchronise. */
+int xtb_actor_predict_host(xtb_net* net, const void* obs_host, size_t obs_bytes, void* obs_dev, int n_env,
+                           int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
+                           float* out_dev, float* out_host, float* logits_host, int use_graph, void* stream);
+
 /* Data-parallel hook: called between backward and the optimiser with the flat
  * gradient bucket; must SUM it over ranks on `stream` (e.g. ncclAllReduce).  Called once with
  * grads == NULL before the loop: must return the world size.  While a hook is installed the

@@ -219,6 +219,19 @@ def test_impala_opt_train_matches_oracle():
     rl, rb = orc.forward(arch, w1, ro["obs"][:5])
     assert logits.shape == (5, 4) and base.shape == (5,) and act.shape == (5,) and act.dtype == np.int32
     assert rel_err(logits, rl.numpy()) < REL and rel_err(base, rb.numpy()[:, 0]) < REL
+    assert ((act >= 0) & (act < 4)).all()
+    # graph-captured rollout inference (T steps, one graph) = the per-step host predict on the same frames
+    m = alg.actor
+    E, T = 3, 4
+    obs_d = torch.from_numpy(ro["obs"][:E * T]).cuda()
+    step_idx = torch.arange(E * T, dtype=torch.int32, device="cuda").reshape(T, E).contiguous()      # time-major rows
+    a_t = torch.empty(T, E, dtype=torch.int32, device="cuda"); lp_t = torch.empty(T, E, device="cuda"); v_t = torch.empty(T, E, device="cuda")
+    m.rollout_infer_device(obs_d, step_idx, E, T, a_t, lp_t, v_t)
+    rl2, rb2 = orc.forward(arch, w1, ro["obs"][:E * T])
+    assert rel_err(v_t.cpu().numpy().reshape(-1), rb2.numpy()[:, 0]) < REL
+    lsm = torch.log_softmax(rl2, 1).numpy()
+    picked = lsm[np.arange(E * T), a_t.cpu().numpy().reshape(-1)]
+    assert np.abs(lp_t.cpu().numpy().reshape(-1) - picked).max() < 2e-3
     assert alg.dist_model_policy.get_dist_info(-1) == {"broker_id": -1, "explorer_id": -1}
 
 

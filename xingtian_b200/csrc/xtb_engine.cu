@@ -1490,6 +1490,7 @@ struct GraphKey {
   bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
 };
 struct GraphVal { cudaGraphExec_t exec; long long kernels; };
+static constexpr size_t kMaxCachedGraphs = 256;   // per cache; beyond it the cache is emptied (keys are buffer addresses)
 static std::map<GraphKey, GraphVal> g_graphs;
 
 static int g_fuse_heads = [] { const char* e = getenv("XTB_FUSE_HEADS"); return e ? atoi(e) : 1; }();
@@ -1642,6 +1643,10 @@ extern "C" int xtb_ppo_train(xtb_net* net, xtb_adam* opt, const xtb_ppo_rollout*
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    if (g_graphs.size() >= kMaxCachedGraphs) {
+      for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second.exec);
+      g_graphs.clear();
+    }
     it = g_graphs.emplace(key, GraphVal{exec, captured}).first;
   }
   CUDA_TRY(cudaGraphLaunch(it->second.exec, sc.st));
@@ -1687,6 +1692,10 @@ static int run_step_graph(const StepKey& key, int use_graph, void* stream, F&& l
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(XTB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    if (g_step_graphs.size() >= kMaxCachedGraphs) {     // callers that pass fresh buffers every step must not leak executables
+      for (auto& kv : g_step_graphs) cudaGraphExecDestroy(kv.second.exec);
+      g_step_graphs.clear();
+    }
     it = g_step_graphs.emplace(key, GraphVal{exec, captured}).first;
   }
   CUDA_TRY(cudaGraphLaunch(it->second.exec, sc.st));
@@ -1890,10 +1899,10 @@ extern "C" int xtb_copy_h2d_staged(void* dst, const void* src, size_t bytes, voi
 }
 // PPO.predict with host buffers in one call (xt/model/ppo/ppo.py:104-109): staged H2D of the observations, the
 // (graphed) forward + sampling, one packed D2H of [action | logp | value] and a stream synchronise.
-extern "C" int xtb_ppo_predict_host(xtb_net* net, const void* obs_host, size_t obs_bytes, void* obs_dev, int n_env,
-                                    int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
-                                    float* out_dev, float* out_host, int use_graph, void* stream) {
-  if (!obs_host || !obs_dev || !out_dev || !out_host) return fail(XTB_ERR_ARG, "xtb_ppo_predict_host: null pointer");
+extern "C" int xtb_actor_predict_host(xtb_net* net, const void* obs_host, size_t obs_bytes, void* obs_dev, int n_env,
+                                      int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
+                                      float* out_dev, float* out_host, float* logits_host, int use_graph, void* stream) {
+  if (!net || !obs_host || !obs_dev || !out_dev || !out_host) return fail(XTB_ERR_ARG, "xtb_actor_predict_host: null pointer");
   StreamScope sc;
   int src = sc.begin(stream, use_graph != 0);
   if (src) return src;
@@ -1903,8 +1912,17 @@ extern "C" int xtb_ppo_predict_host(xtb_net* net, const void* obs_host, size_t o
                                  reinterpret_cast<int32_t*>(out_dev), out_dev + n_env, out_dev + 2 * (size_t)n_env, use_graph, st);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out_host, out_dev, sizeof(float) * 3 * (size_t)n_env, cudaMemcpyDeviceToHost, sc.st));
+  if (logits_host)
+    CUDA_TRY(cudaMemcpyAsync(logits_host, xtb_net_tensor(net, pi_tensor), sizeof(float) * (size_t)n_env * net->tsize[pi_tensor],
+                             cudaMemcpyDeviceToHost, sc.st));
   CUDA_TRY(cudaStreamSynchronize(sc.st));
   return sc.end();
+}
+extern "C" int xtb_ppo_predict_host(xtb_net* net, const void* obs_host, size_t obs_bytes, void* obs_dev, int n_env,
+                                    int pi_tensor, int v_tensor, uint64_t seed, unsigned long long* offset_dev,
+                                    float* out_dev, float* out_host, int use_graph, void* stream) {
+  return xtb_actor_predict_host(net, obs_host, obs_bytes, obs_dev, n_env, pi_tensor, v_tensor, seed, offset_dev, out_dev, out_host,
+                                nullptr, use_graph, stream);
 }
 extern "C" int xtb_copy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
   CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, S(stream)));

@@ -18,6 +18,17 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def stage_h2d(dst, arr, np_dtype):
+    """Copy one host (pageable) array into the contiguous device tensor `dst` through the library's staged copy
+    (`xtb_copy_h2d_staged`: worker threads fill a pinned ring while earlier chunks are in flight); asynchronous on the
+    current stream, the source may be reused as soon as the call returns."""
+    import numpy as np
+    a = np.ascontiguousarray(arr, dtype=np_dtype).reshape(tuple(dst.shape))
+    if not dst.is_contiguous():
+        raise ValueError("staging target must be contiguous")
+    capi.check(capi.lib().xtb_copy_h2d_staged(_ptr(dst), a.ctypes.data, a.nbytes, stream_ptr()))
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError("xingtian_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")

@@ -107,12 +107,51 @@ class ImpalaCnnOpt(XTModel):
         loss = self.train_device(b["obs"], b["bp"], b["action"], b["done"], b["reward"], n, b["loss"])
         return float(loss.cpu()[0])
 
+    def _predict_io(self, n):
+        """Persistent staging of the host-facing predict(): device frames, packed device / pinned result blocks."""
+        io = self._bufs.get(("io", n))
+        if io is None:
+            dev = self.device
+            out_dev = torch.empty(3, n, dtype=torch.float32, device=dev)
+            io = dict(obs=torch.empty((n,) + tuple(self.state_dim), dtype=torch.uint8, device=dev), out_dev=out_dev,
+                      pin_out=torch.empty(3, n, dtype=torch.float32).pin_memory(),
+                      pin_logits=torch.empty(n, self.action_dim, dtype=torch.float32).pin_memory())
+            io["out_np"], io["logits_np"] = io["pin_out"].numpy(), io["pin_logits"].numpy()
+            self._bufs[("io", n)] = io
+        return io
+
+    def rollout_infer_device(self, obs_dev, step_idx, n_env, n_step, action, logp, value):
+        """n_step batched policy evaluations on device-resident frames as ONE CUDA graph (the learner-side replacement of
+        the explorers' per-step predict calls): time-major action / logp / baseline [n_step, n_env]; the logits of the last
+        step stay in net.tensor(logit_name)."""
+        import ctypes as C
+        if getattr(self, "_offset_dev", None) is None:
+            self._offset_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.net.ensure_batch(n_env)
+        check(self.net.lib.xtb_ppo_rollout_infer(self.net.handle, _ptr(obs_dev), _ptr(step_idx), int(n_env), int(n_step),
+                                                 self.net.tid[self.logit_name], self.net.tid[self.base_name],
+                                                 C.c_uint64(self._sample_seed), _ptr(self._offset_dev), _ptr(action), _ptr(logp),
+                                                 _ptr(value), 1 if self.use_graph else 0, stream_ptr()))
+
     def predict(self, state, uniforms=None):
         """impala_cnn_opt.py:267-277: [logits [B,A], baseline [B], action [B]]."""
         state = np.ascontiguousarray(state, np.uint8)
         n = state.shape[0]
-        b = self._buffers(n)
         net = self.net
+        if uniforms is None and n <= net.max_batch:
+            # staged H2D -> graphed forward + fused heads + Philox sampling -> packed D2H (+ logits) -> sync: one native call
+            import ctypes as C
+            io = self._predict_io(n)
+            if getattr(self, "_offset_dev", None) is None:
+                self._offset_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+            net.ensure_batch(n)
+            check(net.lib.xtb_actor_predict_host(net.handle, state.ctypes.data, state.nbytes, _ptr(io["obs"]), n,
+                                                 net.tid[self.logit_name], net.tid[self.base_name], C.c_uint64(self._sample_seed),
+                                                 _ptr(self._offset_dev), _ptr(io["out_dev"]), _ptr(io["pin_out"]),
+                                                 _ptr(io["pin_logits"]), 1 if self.use_graph else 0, stream_ptr()))
+            out = io["out_np"]
+            return [io["logits_np"].copy(), out[2].copy(), out[0].view(np.int32).copy()]
+        b = self._buffers(n)
         net.ensure_batch(n)
         b["obs"].copy_(torch.from_numpy(state), non_blocking=True)
         net.forward(b["obs"], n)
