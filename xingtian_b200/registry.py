@@ -81,9 +81,11 @@ def install(target_registers=None):
     reference's ``@Registers`` replacement-with-warning semantics make them the active ones)."""
     if target_registers is None:
         from zeus.common.util.register import Registers as target_registers  # noqa: only in a reference env
-    for kind in ("model", "algorithm", "agent"):
+    for kind in ("model", "algorithm", "agent", "comm"):
         src = getattr(Registers, kind)
-        dst = getattr(target_registers, kind)
+        dst = getattr(target_registers, kind, None)
+        if dst is None:
+            continue
         for key in list(src.keys()):
             dst(src[key])
     return target_registers
