@@ -198,6 +198,11 @@ int xtb_adam_step(xtb_adam* opt, float* params, const float* grads, float grad_s
 int xtb_adam_step_net(xtb_adam* opt, xtb_net* net, float grad_scale, void* stream);
 const float* xtb_adam_grad_norm(const xtb_adam* opt);
 int xtb_adam_set_lr(xtb_adam* opt, float lr);
+/* Switch the optimiser handle to tf.train.RMSPropOptimizer(lr, decay, epsilon, centered=True) (momentum 0), the
+ * `opt_type: rmsprop` branch of xt/model/impala/impala_cnn_opt.py:205-206: the `m` buffer of xtb_adam_create becomes the
+ * mean-square slot and `mean_grad` (count floats) the mean-gradient slot; this call sets them to ones / zeros as TF
+ * initialises them; `v` is unused.  Clipping, chunking and the weight-blob refresh are those of the Adam step. */
+int xtb_opt_use_rmsprop(xtb_adam* opt, float* mean_grad, float decay, float epsilon);
 
 /* ---- fused learner loops -------------------------------------------------------- */
 /* PPO.train (xt/model/ppo/ppo.py:111-132): for every minibatch slice of `perm`

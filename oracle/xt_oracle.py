@@ -429,6 +429,32 @@ class TFAdam:
                 p.sub_(float(lr_t) * m / (v.sqrt() + self.eps))
 
 
+class TFRMSProp:
+    """tf.train.RMSPropOptimizer(lr, decay, epsilon, centered=True), momentum 0 (impala_cnn_opt.py:205-206), as documented
+    for TF-1.15 (training_ops ApplyCenteredRMSProp): mg = rho mg + (1-rho) g; ms = rho ms + (1-rho) g^2;
+    theta -= lr g / sqrt(ms - mg^2 + eps); the `rms` slot is initialised to ONES, `mg` to zeros."""
+
+    def __init__(self, params, lr, decay=0.99, eps=0.1):
+        self.params, self.lr, self.rho, self.eps = params, lr, decay, eps
+        self.ms = [torch.ones_like(p) for p in params]
+        self.mg = [torch.zeros_like(p) for p in params]
+
+    def step(self, grads):
+        with torch.no_grad():
+            for p, g, ms, mg in zip(self.params, grads, self.ms, self.mg):
+                mg.mul_(self.rho).add_(g, alpha=1 - self.rho)
+                ms.mul_(self.rho).addcmul_(g, g, value=1 - self.rho)
+                p.sub_(self.lr * g / (ms - mg * mg + self.eps).sqrt())
+
+
+def linear_cosine_decay(lr, global_step, decay_steps, num_periods=0.5, alpha=0.0, beta=0.001):
+    """tf.train.linear_cosine_decay as documented (used by impala_cnn_opt.py:234-249 with beta = schedule[1][1] / decay)."""
+    s = min(float(global_step), float(decay_steps))
+    linear = (decay_steps - s) / decay_steps
+    cosine = 0.5 * (1.0 + math.cos(math.pi * 2.0 * num_periods * s / decay_steps))
+    return lr * ((alpha + linear) * cosine + beta)
+
+
 def _as_param_list(weights):
     return [torch.from_numpy(np.array(v, _PREC["np"], copy=True)).requires_grad_(True) for v in weights.values()]
 
@@ -545,10 +571,12 @@ def impala_loss(tp_logits_flat, baseline_flat, bp_logits, actions, dones, reward
 class ImpalaLearner:
     """Restates ImpalaCnnOpt's train graph (impala_cnn_opt.py:188-217, :251-265)."""
 
-    def __init__(self, arch, weights, lr=0.0005, grad_norm_clip=40.0, sample_batch_step=128, gamma=0.99):
+    def __init__(self, arch, weights, lr=0.0005, grad_norm_clip=40.0, sample_batch_step=128, gamma=0.99, opt_type="adam",
+                 lr_schedule=None):
         self.arch, self.names = arch, list(weights.keys())
         self.params = _as_param_list(weights)
-        self.opt = TFAdam(self.params, lr)
+        self.opt = TFAdam(self.params, lr) if opt_type == "adam" else TFRMSProp(self.params, lr)
+        self.lr_schedule, self.global_step = (lr_schedule if opt_type == "adam" else None), 0
         self.clip, self.step_len, self.gamma = grad_norm_clip, sample_batch_step, gamma
         self.last_grad_norm = None
 
@@ -565,6 +593,9 @@ class ImpalaLearner:
         loss, grads = self.loss_and_grads(state, *label)
         grads, gn = clip_by_global_norm(grads, self.clip)
         self.last_grad_norm = gn
+        if self.lr_schedule:
+            self.opt.lr = linear_cosine_decay(self.lr_schedule[0][1], self.global_step, 20000.0, beta=self.lr_schedule[1][1] / 20000.0)
+        self.global_step += 1
         self.opt.step(grads)
         return float(loss.detach())
 

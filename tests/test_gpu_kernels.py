@@ -237,6 +237,34 @@ def test_adam_clip_ten_steps(xb, mode):
     xb["lib"].xtb_adam_destroy(h)
 
 
+def test_rmsprop_centered_ten_steps_and_lr_updates(xb):
+    """a14: tf.train.RMSPropOptimizer(lr, decay=.99, epsilon=.1, centered=True) + clip_by_global_norm(40) on the flat bucket
+    (impala_cnn_opt.py:205-215), and xtb_adam_set_lr between steps (the linear_cosine_decay schedule of :234-249)."""
+    from xingtian_b200.engine import _ptr, stream_ptr
+    capi = xb["capi"]
+    n = 100003
+    rng = np.random.default_rng(7)
+    p0 = rng.standard_normal(n).astype(np.float32) * 0.05
+    p = dev(p0.copy()); ms = torch.ones(n, device="cuda"); v = torch.zeros(n, device="cuda"); mg = torch.zeros(n, device="cuda")
+    h = C.c_void_p()
+    seg = (C.c_longlong * 2)(0, n)
+    capi.check(xb["lib"].xtb_adam_create(n, 5e-4, 0.9, 0.999, 1e-8, capi.CLIP_GLOBAL_NORM, 40.0, seg, 1, _ptr(ms), _ptr(v), C.byref(h)))
+    capi.check(xb["lib"].xtb_opt_use_rmsprop(h, _ptr(mg), 0.99, 0.1))
+    ref_p = [torch.from_numpy(p0.copy())]
+    opt = orc.TFRMSProp(ref_p, 5e-4, decay=0.99, eps=0.1)
+    for step in range(10):
+        lr = orc.linear_cosine_decay(5e-4, step * 1500, 20000.0, beta=1e-6 / 20000.0)
+        opt.lr = lr
+        capi.check(xb["lib"].xtb_adam_set_lr(h, lr))
+        g = (rng.standard_normal(n) * (0.5 if step % 2 else 0.05)).astype(np.float32)      # |g| ~ 158 / 15.8: clip 40 bites on odd steps
+        gl, _ = orc.clip_by_global_norm([torch.from_numpy(g.copy())], 40.0)
+        opt.step(gl)
+        capi.check(xb["lib"].xtb_adam_step(h, _ptr(p), _ptr(dev(g)), 1.0, stream_ptr()))
+    assert rel_err(p.cpu().numpy() - p0, ref_p[0].numpy() - p0) < REL
+    assert rel_err(ms.cpu().numpy(), opt.ms[0].numpy()) < REL and rel_err(mg.cpu().numpy(), opt.mg[0].numpy()) < REL
+    xb["lib"].xtb_adam_destroy(h)
+
+
 # ------------------------------------------------------------------------------------------- networks
 def _arch_cases():
     return {

@@ -92,3 +92,20 @@ def test_float64_adam_matches_closed_form():
         opt32.step([torch.from_numpy(g.astype(np.float32))])
     upd64 = np_f64.adam_steps(p0, gs, 2.5e-4) - p0
     assert np.abs((params32[0].numpy() - p0.astype(np.float32)) - upd64).max() < 2e-6 * np.abs(upd64).max() + 2e-7
+
+
+def test_rmsprop_and_lr_schedule_restatements():
+    """TFRMSProp (centred, rms slot initialised to ones) against a scalar hand computation; linear_cosine_decay at its
+    documented end points (tf.train.linear_cosine_decay: (alpha + linear) * cosine + beta)."""
+    p = [torch.tensor([1.0, -2.0], dtype=torch.float64)]
+    opt = orc.TFRMSProp(p, 0.01, decay=0.9, eps=0.1)
+    g = torch.tensor([0.5, -0.25], dtype=torch.float64)
+    opt.step([g])
+    mg = 0.1 * g.numpy(); ms = 0.9 * 1.0 + 0.1 * g.numpy() ** 2
+    want = np.array([1.0, -2.0]) - 0.01 * g.numpy() / np.sqrt(ms - mg ** 2 + 0.1)
+    np.testing.assert_allclose(p[0].numpy(), want, rtol=0, atol=1e-15)
+    assert abs(orc.linear_cosine_decay(0.01, 0, 20000.0, beta=1e-4) - 0.01 * (1.0 + 1e-4)) < 1e-15
+    assert abs(orc.linear_cosine_decay(0.01, 20000, 20000.0, beta=1e-4) - 0.01 * 1e-4) < 1e-15
+    assert abs(orc.linear_cosine_decay(0.01, 10 ** 9, 20000.0, beta=1e-4) - 0.01 * 1e-4) < 1e-15       # clamped at decay_steps
+    mid = orc.linear_cosine_decay(0.01, 10000, 20000.0, beta=0.0)
+    assert abs(mid - 0.01 * 0.5 * 0.5 * (1 + np.cos(np.pi * 0.5))) < 1e-15

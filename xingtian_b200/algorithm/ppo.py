@@ -34,8 +34,9 @@ class PPO(Algorithm):
 
     def _init_train_list(self):
         self._count = 0           # samples staged so far
-        self._raw_segments = []   # (offset, length) of trajectories that still need device GAE
-        self._raw = None
+        self._raw_segments = []   # (offset, length, value offset) of trajectories that still need device GAE
+        if not hasattr(self, "_raw"):
+            self._raw = None      # device buffers of raw trajectories (kept across iterations)
 
     # -- data path ---------------------------------------------------------------------------
     def _stage(self, dst, arr, np_dtype):
@@ -72,38 +73,49 @@ class PPO(Algorithm):
             self._stage(ro.old_v[sl], train_data["old_value"], np.float32)
             self._stage(ro.target_v[sl], train_data["target_value"], np.float32)
         else:
-            dev = ro.obs.device
             value = np.ascontiguousarray(train_data["value"], np.float32).reshape(-1)
-            val = torch.empty(value.size, dtype=torch.float32, device=dev)
-            rew = torch.empty(n, dtype=torch.float32, device=dev)
-            don = torch.empty(n, dtype=torch.uint8, device=dev)
-            self._stage(val, value, np.float32)        # staged (asynchronous) copies: no host sync per trajectory
-            self._stage(rew, np.asarray(train_data["reward"]).reshape(-1), np.float32)
-            self._stage(don, np.asarray(train_data["done"]).reshape(-1).astype(np.bool_, copy=False).view(np.uint8), np.uint8)
-            if val.numel() != n + 1:
-                raise ValueError("raw trajectory needs value[T+1] (bootstrap appended), got %d for T=%d" % (val.numel(), n))
-            self._raw_segments.append((self._count, n, val, rew, don))
+            if value.size != n + 1:
+                raise ValueError("raw trajectory needs value[T+1] (bootstrap appended), got %d for T=%d" % (value.size, n))
+            raw = self._raw_store(self._count + n, len(self._raw_segments) + 1)
+            voff = self._count + len(self._raw_segments)          # every earlier raw trajectory holds one bootstrap value more
+            self._stage(raw["val"][voff:voff + n + 1], value, np.float32)     # staged (asynchronous): no host sync per trajectory
+            self._stage(raw["rew"][sl], np.asarray(train_data["reward"]).reshape(-1), np.float32)
+            self._stage(raw["don"][sl], np.asarray(train_data["done"]).reshape(-1).astype(np.bool_, copy=False).view(np.uint8), np.uint8)
+            self._raw_segments.append((self._count, n, voff))
         self._count += n
         ro.n = self._count
 
+    def _raw_store(self, n, n_traj):
+        """Grow-only device buffers of the raw trajectories (value[T+1] per trajectory back to back, reward, done)."""
+        raw = self._raw
+        if raw is not None and raw["rew"].numel() >= n and raw["val"].numel() >= n + n_traj:
+            return raw
+        dev = self.actor.rollout.obs.device
+        cap = max(n, 2 * (raw["rew"].numel() if raw else 0))
+        cap_t = max(n_traj, 2 * ((raw["val"].numel() - raw["rew"].numel()) if raw else 0), 64)
+        new = dict(val=torch.empty(cap + cap_t, dtype=torch.float32, device=dev), rew=torch.empty(cap, dtype=torch.float32, device=dev),
+                   don=torch.empty(cap, dtype=torch.uint8, device=dev))
+        if raw is not None:
+            for k in new:
+                new[k][:raw[k].numel()].copy_(raw[k])
+        self._raw = new
+        return new
+
     def _device_gae(self):
+        """GAE of the raw trajectories on the device: one launch over [E, T] when they are equally long and adjacent (the
+        value buffer is then exactly [E, T+1]), else one launch per trajectory."""
         ro = self.actor.rollout
         lib = self.actor.net.lib
         segs = self._raw_segments
         if not segs:
             return
-        same = len({s[1] for s in segs}) == 1 and all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(len(segs) - 1))
-        if same and len(segs) > 1:   # one batched launch over [E, T]
-            t = segs[0][1]
-            off = segs[0][0]
-            val = torch.cat([s[2] for s in segs]); rew = torch.cat([s[3] for s in segs]); don = torch.cat([s[4] for s in segs])
-            check(lib.xtb_gae(_ptr(val), _ptr(rew), _ptr(don), len(segs), t, GAMMA, LAM, int(self.sign_clip_reward),
-                              _ptr(ro.adv[off:]), _ptr(ro.old_v[off:]), _ptr(ro.target_v[off:]), stream_ptr()))
-        else:
-            for off, t, val, rew, don in segs:
-                check(lib.xtb_gae(_ptr(val), _ptr(rew), _ptr(don), 1, t, GAMMA, LAM, int(self.sign_clip_reward),
-                                  _ptr(ro.adv[off:]), _ptr(ro.old_v[off:]), _ptr(ro.target_v[off:]), stream_ptr()))
-        torch.cuda.current_stream().synchronize()   # keep the staged inputs alive until consumed
+        raw = self._raw
+        same = len({s[1] for s in segs}) == 1 and all(segs[i][0] + segs[i][1] == segs[i + 1][0] and segs[i][2] + segs[i][1] + 1 == segs[i + 1][2]
+                                                      for i in range(len(segs) - 1))
+        groups = [(segs[0][0], segs[0][1], segs[0][2], len(segs))] if same else [(o, t, v, 1) for o, t, v in segs]
+        for off, t, voff, count in groups:
+            check(lib.xtb_gae(_ptr(raw["val"][voff:]), _ptr(raw["rew"][off:]), _ptr(raw["don"][off:]), count, t, GAMMA, LAM,
+                              int(self.sign_clip_reward), _ptr(ro.adv[off:]), _ptr(ro.old_v[off:]), _ptr(ro.target_v[off:]), stream_ptr()))
         self._raw_segments = []
 
     def train(self, **kwargs):

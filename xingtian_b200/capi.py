@@ -79,6 +79,7 @@ _SIGS = {
     "xtb_adam_step_net": (C.c_int, [_P, _P, C.c_float, _P]),
     "xtb_adam_grad_norm": (_P, [_P]),
     "xtb_adam_set_lr": (C.c_int, [_P, C.c_float]),
+    "xtb_opt_use_rmsprop": (C.c_int, [_P, _P, C.c_float, C.c_float]),
     "xtb_ppo_train": (C.c_int, [_P, _P, C.POINTER(PpoRollout), C.c_int, C.c_int, C.c_int, _P,
                                 C.POINTER(PpoHyper), C.c_int, C.c_int, _P, C.c_int, _P]),
     "xtb_ppo_rollout_infer": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, _P, C.c_int, _P]),

@@ -1349,6 +1349,7 @@ struct xtb_adam {
   float lr, beta1, beta2, eps, clip;
   int clip_mode = 0, n_seg = 0, n_blk = 0;
   float *m = nullptr, *v = nullptr;
+  float* mg = nullptr; float rms_rho = 0.f, rms_eps = 0.f;   // centred RMSProp instead of Adam when mg != NULL (m = ms)
   int* blk_seg = nullptr; long long* blk_beg = nullptr; int* blk_len = nullptr;
   double* norm_sq = nullptr; float* seg_scale = nullptr; AdamState* st = nullptr; AdamHyper* hyp = nullptr; unsigned int* ticket = nullptr;
 };
@@ -1427,6 +1428,13 @@ static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float 
           (const AdamHyper*)o->hyp, o->seg_scale, o->n_seg, o->clip_mode, grad_scale);
   LAUNCH_CHECK();
   const bool blobs = net && !net->blob_segs.empty();
+  if (o->mg) {
+    XLAUNCH(rmsprop_kernel, o->n_blk, OPT_THREADS, 0, st, params, grads, o->m, o->mg, o->blk_seg, o->blk_beg, o->blk_len,
+            o->seg_scale, (const AdamHyper*)o->hyp, o->rms_rho, o->rms_eps, blobs ? (const bp::BlobSeg*)(net->ws + net->segs_off) : nullptr,
+            blobs ? (int)net->blob_segs.size() : 0, blobs ? (__nv_bfloat16*)(net->ws + net->blob_off) : nullptr, blobs ? net->blob_elems : 0LL);
+    LAUNCH_CHECK();
+    return XTB_OK;
+  }
   XLAUNCH(adam_kernel, o->n_blk, OPT_THREADS, 0, st, params, grads, o->m, o->v, o->blk_seg, o->blk_beg, o->blk_len,
           o->seg_scale, o->st, (const AdamHyper*)o->hyp, blobs ? (const bp::BlobSeg*)(net->ws + net->segs_off) : nullptr,
           blobs ? (int)net->blob_segs.size() : 0, blobs ? (__nv_bfloat16*)(net->ws + net->blob_off) : nullptr, blobs ? net->blob_elems : 0LL);
@@ -1435,6 +1443,19 @@ static int adam_step_impl(xtb_adam* o, float* params, const float* grads, float 
 }
 
 extern "C" const float* xtb_adam_grad_norm(const xtb_adam* o) { return o ? &o->st->grad_norm : nullptr; }
+extern "C" int xtb_opt_use_rmsprop(xtb_adam* o, float* mean_grad, float decay, float epsilon) {
+  if (!o || !mean_grad) return fail(XTB_ERR_ARG, "xtb_opt_use_rmsprop: null pointer");
+  if (!(decay > 0.f && decay < 1.f) || !(epsilon > 0.f)) return fail(XTB_ERR_ARG, "xtb_opt_use_rmsprop: decay in (0,1), epsilon > 0");
+  drop_graphs_of(o);                       // captured steps baked the Adam kernel in
+  {   // slot initial values of tf.train.RMSPropOptimizer: rms = ones, mg = zeros (one-time, synchronous)
+    std::vector<float> ones((size_t)o->count, 1.f);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(o->m, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(mean_grad, 0, ones.size() * sizeof(float)));
+  }
+  o->mg = mean_grad; o->rms_rho = decay; o->rms_eps = epsilon;
+  return XTB_OK;
+}
 extern "C" int xtb_adam_set_lr(xtb_adam* o, float lr) {
   if (!o) return fail(XTB_ERR_ARG, "null optimiser");
   o->lr = lr;

@@ -222,6 +222,14 @@ class Adam(object):
         except Exception:
             pass
 
+    def use_rmsprop(self, decay=0.99, epsilon=0.1):
+        """tf.train.RMSPropOptimizer(lr, decay, epsilon, centered=True): mean-square slot starts at ones, mean-gradient at zeros."""
+        self.mean_grad = torch.zeros_like(self.net.params)
+        check(self.lib.xtb_opt_use_rmsprop(self.handle, _ptr(self.mean_grad), float(decay), float(epsilon)))
+
+    def set_lr(self, lr):
+        check(self.lib.xtb_adam_set_lr(self.handle, float(lr)))
+
     def step(self, grad_scale=1.0):
         check(self.lib.xtb_adam_step_net(self.handle, self.net.handle, float(grad_scale), stream_ptr()))
 

@@ -34,12 +34,10 @@ class ImpalaCnnOpt(XTModel):
         self.sample_batch_steps = model_config.get("sample_batch_step", 50)
         self._init_seed = model_config.get("init_seed")
         self.use_graph = bool(model_config.get("use_cuda_graph", True))
-        if self.opt_type != "adam":
-            # rmsprop(decay .99, eps .1, centered) exists in the reference (impala_cnn_opt.py:205-206) but
-            # no shipped YAML selects it
-            raise KeyError("invalid opt_type: {}".format(self.opt_type))
-        if self.lr_schedule:
-            raise NotImplementedError("lr_schedule (linear_cosine_decay) is not on the benchmarked path")
+        if self.opt_type not in ("adam", "rmsprop"):
+            raise KeyError("invalid opt_type: {}".format(self.opt_type))          # impala_cnn_opt.py:207-208
+        if self.lr_schedule and len(self.lr_schedule) != 2:
+            raise ValueError("lr_schedule invalid: {}".format(self.lr_schedule))  # impala_cnn_opt.py:237-240 (logging.fatal)
         if self.input_dtype not in ("uint8",) or abs(self.sta_mean) >= 1e-4:
             # state_transform (model_utils.py:192-201): uint8 with mean~0 => x/std
             raise NotImplementedError("ImpalaCnnOpt: only uint8 observations with state_mean 0 are supported")
@@ -60,6 +58,9 @@ class ImpalaCnnOpt(XTModel):
         self.net.view(name).copy_(torch.from_numpy(o))
         self.net.params_changed()
         self.opt = Adam(self.net, self.lr, eps=1e-8, clip_mode=capi.CLIP_GLOBAL_NORM, clip=self.grad_norm_clip)
+        if self.opt_type == "rmsprop":
+            self.opt.use_rmsprop(decay=0.99, epsilon=0.1)          # impala_cnn_opt.py:205-206 (the schedule is Adam-only there)
+        self._global_step = 0
         self._bufs = {}
         self._sample_seed = int(np.random.randint(0, 2 ** 31 - 1))
         self._sample_offset = 0
@@ -88,11 +89,25 @@ class ImpalaCnnOpt(XTModel):
             raise ValueError("batch of %d samples is not a whole number of %d-step trajectories" % (n, s))
         net.ensure_batch(n)
         loss_buf.zero_()
+        if self.lr_schedule and self.opt_type == "adam":
+            self.opt.set_lr(self.scheduled_lr(self._global_step))
+        self._global_step += 1
         # forward, in-graph V-trace + losses, backward, clip + Adam: one native call, replayed as a CUDA graph
         check(net.lib.xtb_impala_train(net.handle, self.opt.handle, _ptr(obs), None, _ptr(bp_logits), _ptr(actions), _ptr(dones),
                                        _ptr(rewards), int(n), s, float(GAMMA), net.tid[self.logit_name], net.tid[self.base_name],
                                        _ptr(loss_buf), 1 if self.use_graph else 0, stream_ptr()))
         return loss_buf
+
+    def scheduled_lr(self, global_step, decay_step=20000.0):
+        """impala_cnn_opt.py:234-249: tf.train.linear_cosine_decay(lr_schedule[0][1], global_step, 20000,
+        beta=lr_schedule[1][1] / 20000) with the TF defaults num_periods=0.5, alpha=0:
+        lr * ((alpha + (D - s) / D) * 0.5 * (1 + cos(pi * 2 * num_periods * s / D)) + beta), s = min(global_step, D)."""
+        import math
+        base, beta = float(self.lr_schedule[0][1]), float(self.lr_schedule[1][1]) / float(decay_step)
+        s = min(float(global_step), float(decay_step))
+        linear = (decay_step - s) / decay_step
+        cosine = 0.5 * (1.0 + math.cos(math.pi * 2.0 * 0.5 * s / decay_step))
+        return base * (linear * cosine + beta)
 
     def train(self, state, label):
         """impala_cnn_opt.py:251-265: train(state, [bp_logic_outs, actions, dones, rewards]) -> loss."""
