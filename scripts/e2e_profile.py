@@ -14,20 +14,30 @@ ro = dict(obs=rng.integers(0, 256, (E * T, 84, 84, 4), dtype=np.uint8), action=r
           logp=np.full((E * T, 1), -1.386, np.float32), value=rng.standard_normal((E, T + 1, 1)).astype(np.float32),
           reward=rng.integers(-1, 2, (E * T, 1)).astype(np.float32), done=rng.random((E * T, 1)) < 0.01)
 host_obs = [np.ascontiguousarray(ro["obs"][np.arange(E) * T + t]) for t in range(T)]
-traj = [dict(cur_state=ro["obs"][e * T:(e + 1) * T], action=ro["action"][e * T:(e + 1) * T], logp=ro["logp"][e * T:(e + 1) * T],
+alg.actor.keep_predict_obs(E, T)      # frames reach the device once, inside predict()
+traj = [dict(ring_rows=(e, 0, T), action=ro["action"][e * T:(e + 1) * T], logp=ro["logp"][e * T:(e + 1) * T],
              value=ro["value"][e], reward=ro["reward"][e * T:(e + 1) * T], done=ro["done"][e * T:(e + 1) * T]) for e in range(E)]
-for rep in range(3):
+for rep in range(4):
+    alg.actor._obs_ring["t"] = 0
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for t in range(T):
         alg.actor.predict(host_obs[t])
     t1 = time.perf_counter()
     for e in range(E):
         alg.prepare_data(traj[e])
+    t2a = time.perf_counter()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    alg.train()
+    alg._device_gae()
+    t3a = time.perf_counter()
+    perm = alg.actor.make_perm(alg._count)
+    t3b = time.perf_counter()
+    loss = alg.actor.train_device(alg._count, perm)
     t3 = time.perf_counter()
-    print("predict x128 %.1f ms | prepare_data x32 %.1f ms | train %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
+    alg._init_train_list()
+    print("predict x128 %.2f ms | prepare_data x32 %.2f ms host + %.2f ms drain | device GAE call %.2f | make_perm %.2f | train_device (launch + sync + loss) %.2f ms"
+          % ((t1 - t0) * 1e3, (t2a - t1) * 1e3, (t2 - t2a) * 1e3, (t3a - t2) * 1e3, (t3b - t3a) * 1e3, (t3 - t3b) * 1e3))
 
 # ---- split of one predict() call: staged H2D alone, device inference alone ------------------------------
 from xingtian_b200.engine import _ptr, stream_ptr

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -44,6 +45,7 @@ class Stager {
     cudaError_t err = init();
     if (err != cudaSuccess) return err;
     const size_t n = (bytes + chunk_ - 1) / chunk_;
+    release_if_idle();
     const char* s = static_cast<const char*>(src);
     char* d = static_cast<char*>(dst);
     if (n == 1 || workers_.empty()) {                        // small copy: stage on the calling thread
@@ -57,6 +59,8 @@ class Stager {
       seq_ += n;
       return cudaSuccess;
     }
+    const bool tr = trace_on();
+    const auto t_in = tr ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point();
     // publish the job, then open it by resetting `next_`
     if (done_.size() < n) done_ = std::vector<std::atomic<int>>(n);
     for (size_t c = 0; c < n; c++) done_[c].store(0, std::memory_order_relaxed);
@@ -78,6 +82,9 @@ class Stager {
 
     cudaError_t first = cudaSuccess;
     const size_t nw = workers_.size();
+    const auto t_pub = tr ? std::chrono::steady_clock::now() : t_in;
+    auto t_first = t_pub;
+    bool seen_first = false;
     for (size_t c = 0; c < n;) {
       // wait for chunk c; the caller stages chunks itself only while more are unclaimed than the workers can take
       // (or the workers are still asleep): a chunk in hand would delay the copies that are ready to be issued
@@ -90,12 +97,15 @@ class Stager {
           if (query_slot(slot) == cudaSuccess) allowed_.store(++allowed, std::memory_order_release);
         }
       }
+      if (tr && !seen_first) { t_first = std::chrono::steady_clock::now(); seen_first = true; }
       // one DMA for the run of finished chunks that is contiguous in the ring: c .. e
       size_t e = c;
       while (e + 1 < n && (int)((seq_ + e + 1) % slots_) != 0 && done_[e + 1].load(std::memory_order_acquire)) e++;
       const int slot0 = (int)((seq_ + c) % slots_);
       const size_t off = c * chunk_, end = std::min(bytes, (e + 1) * chunk_);
+      const auto t_a = tr ? std::chrono::steady_clock::now() : t_in;
       if (first == cudaSuccess) first = issue(slot0, (int)(e - c + 1), d + off, end - off, stream);
+      if (tr) { trace_.api += us(t_a, std::chrono::steady_clock::now()); trace_.dmas++; }
       c = e + 1;
       if (allowed < n && allowed <= c) {                     // nothing else can be staged: block on the oldest DMA
         int s2 = (int)((seq_ + allowed) % slots_);
@@ -105,13 +115,32 @@ class Stager {
       }
     }
     seq_ += n;
+    if (tr) {
+      const auto t_out = std::chrono::steady_clock::now();
+      trace_.publish += us(t_in, t_pub); trace_.first_done += us(t_pub, t_first); trace_.issue_loop += us(t_first, t_out);
+      if (++trace_.calls == 128) {
+        fprintf(stderr, "[stager] %zu chunks/call: publish %.1f us, first chunk staged after %.1f us, issue loop %.1f us (of which "
+                "copy/record API %.1f us), %.2f DMAs per call\n", n, trace_.publish / 128, trace_.first_done / 128,
+                trace_.issue_loop / 128, trace_.api / 128, trace_.dmas / 128.0);
+        trace_ = Trace();
+      }
+    }
     return first;
   }
 
   int threads() const { return (int)workers_.size(); }
 
+  // XTB_STAGE_TRACE=1: mean per-call phase times on stderr every 128 multi-chunk calls (diagnosis only)
+  struct Trace { double publish = 0, first_done = 0, issue_loop = 0, api = 0; long dmas = 0, calls = 0; };
+
  private:
   Stager() {}
+
+  static bool trace_on() { static const bool on = getenv("XTB_STAGE_TRACE") != nullptr; return on; }
+  static double us(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  }
+  Trace trace_;
 
   static void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
@@ -152,6 +181,17 @@ class Stager {
     return cudaSuccess;
   }
 
+  // A few queries instead of one wait per slot: when the most recent copy of every stream used since the ring was last
+  // idle has completed, every earlier DMA has completed too and the whole ring is free (the common case: the caller
+  // synchronised its stream after the previous call).
+  void release_if_idle() {
+    if (n_ls_ == 0 || ls_overflow_) return;
+    for (int k = 0; k < n_ls_; k++)
+      if (cudaEventQuery(ev_[ls_ev_[k]]) != cudaSuccess) return;        // cudaErrorNotReady is not sticky
+    for (int i = 0; i < slots_; i++) used_[i] = false;
+    n_ls_ = 0;
+  }
+
   // A run of slots issued as one DMA shares the event of its last slot (owner_[slot]); that event may be re-recorded
   // by a later run ending in the same slot, which only makes a wait on it more conservative.
   cudaError_t wait_slot(int slot) {
@@ -169,6 +209,10 @@ class Stager {
     if (e != cudaSuccess) return e;
     const int last = slot + count - 1;
     for (int i = slot; i <= last; i++) { used_[i] = true; owner_[i] = last; }
+    int k = 0;
+    while (k < n_ls_ && ls_stream_[k] != stream) k++;
+    if (k == n_ls_) { if (n_ls_ < MAX_LS) { ls_stream_[n_ls_++] = stream; } else { ls_overflow_ = true; k = 0; } }
+    ls_ev_[k] = last;                                                    // most recent DMA of this stream
     return cudaEventRecord(ev_[last], stream);
   }
 
@@ -230,6 +274,11 @@ class Stager {
   char* ring_ = nullptr;
   bool inited_ = false;
   int n_events_ = 0;
+  static constexpr int MAX_LS = 8;
+  cudaStream_t ls_stream_[MAX_LS];   // streams with copies issued since the ring was last known idle ...
+  int ls_ev_[MAX_LS];                // ... and the event of the most recent copy on each
+  int n_ls_ = 0;
+  bool ls_overflow_ = false;
   size_t chunk_ = 256u << 10;   // bytes per pinned slot
   int slots_ = 48;              // RING_BYTES / chunk_
   cudaEvent_t ev_[MAX_SLOTS];
