@@ -41,6 +41,10 @@ class XTModel(object):
         self.model_format = model_info.get("model_format")
         self.max_to_keep = model_info.get("max_to_keep", 100)
         self.device = torch.device(model_info.get("device", "cuda:%d" % torch.cuda.current_device()))
+        if self.device.type != "cuda" or (self.device.index is not None and self.device.index != torch.cuda.current_device()):
+            # native calls run on the current device's stream and the staging ring lives on the device of its first use
+            raise ValueError("model device {} is not the current CUDA device {}: call torch.cuda.set_device first".format(
+                self.device, torch.cuda.current_device()))
         self.net = None
         self.model = self.create_model(model_info)
         if "init_weights" in model_info:
