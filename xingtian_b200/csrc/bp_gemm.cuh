@@ -1150,42 +1150,45 @@ __global__ void bp_wprep_kernel(const float* __restrict__ params, const BlobSeg*
 // uint8 frames [n][H][W][4] (+ minibatch gather) -> batch-planar space-to-depth plane (exact in bf16, hi only):
 // the image is embedded at (padT, padL) in a zero canvas of [4*H4][4*W4] pixels, pixel block (Y, X) = 64 features
 // (dy, dx, c); a 16-byte output piece = 8 source bytes (2 pixels x 4 channels).
-// One block = one block-row Y of 32 samples.  Phase 1 reads the 4 image rows of every sample with 16-byte loads
-// along the row (contiguous 1344-byte runs per sample) into shared memory; phase 2 hands every piece to one warp
-// whose lanes are the 32 samples, so each store instruction writes 512 contiguous bytes of the plane.
+// One block = one image row of 32 samples.  Phase 1 reads that row of every sample with 16-byte loads (contiguous
+// 336-byte runs per sample) into shared memory; phase 2 hands every piece to one warp whose lanes are the 32 samples,
+// so each store instruction writes 512 contiguous bytes of the plane.
 constexpr int DEC_SAMPLES = 32;
 constexpr int DEC_THREADS = 256;
 __global__ void __launch_bounds__(DEC_THREADS)
 bp_decode_s2d_kernel(const uint8_t* __restrict__ obs, const int32_t* __restrict__ idx, int B, int H, int W, int H4, int W4,
                      int padT, int padL, BpT dst) {
+  // One block = one image row (canvas row Y, sub-row dy) of DEC_SAMPLES samples: 4*H4 x ceil(B/32) blocks, so that the
+  // inference batch (B = 32: one sample group) still spreads over 84 blocks.
   extern __shared__ __align__(16) uint8_t dec_sm[];
   pdl_wait(); pdl_trigger();
-  const int Y = blockIdx.x, b0 = blockIdx.y * DEC_SAMPLES;
+  const int Y = blockIdx.x >> 2, dy = blockIdx.x & 3, b0 = blockIdx.y * DEC_SAMPLES;
   const int row_bytes = W * 4, units = row_bytes >> 4;          // 16-byte units per image row
-  const int sstride = 4 * row_bytes + 8;                        // per-sample stride: +8 B keeps 8-byte lane reads conflict-free
+  const int sstride = row_bytes + 8;                            // per-sample stride: +8 B keeps 8-byte lane reads conflict-free
   const int ns = min(DEC_SAMPLES, B - b0);
   const long long img = (long long)H * row_bytes;
-  for (int i = threadIdx.x; i < ns * 4 * units; i += DEC_THREADS) {
-    const int sidx = i / (4 * units), rem = i - sidx * 4 * units, r = rem / units, ux = rem - r * units;
-    const int y = 4 * Y + r - padT;
+  const int y = 4 * Y + dy - padT;
+  const bool in_img = y >= 0 && y < H;
+  for (int i = threadIdx.x; i < ns * units; i += DEC_THREADS) {
+    const int sidx = i / units, ux = i - sidx * units;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < H) {
+    if (in_img) {
       const long long srow = idx ? idx[b0 + sidx] : b0 + sidx;
       v = *reinterpret_cast<const uint4*>(obs + srow * img + (long long)y * row_bytes + ux * 16);
     }
-    uint2* d = reinterpret_cast<uint2*>(dec_sm + sidx * sstride + r * row_bytes + ux * 16);
+    uint2* d = reinterpret_cast<uint2*>(dec_sm + sidx * sstride + ux * 16);
     d[0] = make_uint2(v.x, v.y);
     d[1] = make_uint2(v.z, v.w);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half_units = W >> 1;                                // 8-byte units (pixel pairs) per image row
-  for (int q = warp; q < W4 * 8; q += DEC_THREADS / 32) {
-    const int X = q >> 3, dy = (q >> 1) & 3, dxh = q & 1;
+  for (int q = warp; q < W4 * 2; q += DEC_THREADS / 32) {
+    const int X = q >> 1, dxh = q & 1;
     const int u8 = 2 * X + dxh - (padL >> 1);                   // pixel pair inside the source row
     uint4 o = make_uint4(0, 0, 0, 0);
     if (lane < ns && u8 >= 0 && u8 < half_units) {
-      const uint2 v = *reinterpret_cast<const uint2*>(dec_sm + lane * sstride + dy * row_bytes + u8 * 8);
+      const uint2 v = *reinterpret_cast<const uint2*>(dec_sm + lane * sstride + u8 * 8);
       o.x = pack_bf16((float)(v.x & 0xff), (float)((v.x >> 8) & 0xff));
       o.y = pack_bf16((float)((v.x >> 16) & 0xff), (float)(v.x >> 24));
       o.z = pack_bf16((float)(v.y & 0xff), (float)((v.y >> 8) & 0xff));

@@ -931,8 +931,8 @@ static int op_decode(xtb_net* net, const void* obs, const int32_t* idx, int B, c
   const LayerPlan* first = nullptr;
   for (const auto& lp : net->L) if (lp.s2d && use_tc(lp)) { first = &lp; break; }
   if (!first) return XTB_OK;
-  dim3 grid(net->H4, (B + bp::DEC_SAMPLES - 1) / bp::DEC_SAMPLES);
-  const int smem = bp::DEC_SAMPLES * (4 * net->desc.in_w * 4 + 8);
+  dim3 grid(4 * net->H4, (B + bp::DEC_SAMPLES - 1) / bp::DEC_SAMPLES);
+  const int smem = bp::DEC_SAMPLES * (net->desc.in_w * 4 + 8);
   XLAUNCH(bp::bp_decode_s2d_kernel, grid, bp::DEC_THREADS, smem, st, (const uint8_t*)obs, idx, B, net->desc.in_h, net->desc.in_w, net->H4,
           net->W4, first->g.padT, first->g.padL, obs_bp(net));
   LAUNCH_CHECK();
