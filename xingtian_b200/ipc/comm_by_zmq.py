@@ -1,56 +1,61 @@
-"""zmq transport with the surface of zeus/common/ipc/comm_by_zmq.py:30-110; ``pyarrow.serialize`` (gone from current
-pyarrow) is replaced by pickle protocol 5 with out-of-band numpy buffers sent as extra zmq frames (zero-copy send)."""
+"""zmq transport behind ``Registers.comm`` (role of zeus/common/ipc/comm_by_zmq.py:30-110).
+
+Same construction contract -- ``comm_info`` = {type: PUB/SUB/PUSH/PULL/REP/REQ, addr, port}; an address containing ``*``
+binds a random port in [20000, 40000), anything else connects -- and the same four methods.  The wire format differs:
+``pyarrow.serialize`` no longer exists, so a message is one pickle-5 header frame followed by the numpy buffers as raw
+zmq frames (sent without copying)."""
 import pickle
 
 import zmq
 
 from ..registry import Registers
 
-ZMQ_MIN_PORT = 20000
-ZMQ_MAX_PORT = 40000
+PORT_RANGE = (20000, 40000)
+_SOCKET_KIND = dict(PUB=zmq.PUB, SUB=zmq.SUB, PUSH=zmq.PUSH, PULL=zmq.PULL, REP=zmq.REP, REQ=zmq.REQ)
 
 
 @Registers.comm
 class CommByZmq(object):
     def __init__(self, comm_info):
-        addr = comm_info.get("addr", "*")
-        port = comm_info.get("port")
-        zmq_type = comm_info.get("type", "PUB")
-        comm_type = {"PUB": zmq.PUB, "SUB": zmq.SUB, "PUSH": zmq.PUSH, "PULL": zmq.PULL, "REP": zmq.REP, "REQ": zmq.REQ}.get(zmq_type)
+        self.kind = comm_info.get("type", "PUB")
+        if self.kind not in _SOCKET_KIND:
+            raise KeyError("unknown zmq socket type: {}".format(self.kind))
         self._ctx = zmq.Context()
-        socket = self._ctx.socket(comm_type)
-        self._type = zmq_type
-        self.bound_port = None
-        if "*" in addr:
-            self.bound_port = socket.bind_to_random_port("tcp://*", min_port=ZMQ_MIN_PORT, max_port=ZMQ_MAX_PORT, max_tries=100)
-        else:
-            socket.connect("tcp://" + str(addr) + ":" + str(port))
-        if zmq_type == "SUB":
-            socket.setsockopt(zmq.SUBSCRIBE, b"")
-        self.socket = socket
+        self.socket = self._ctx.socket(_SOCKET_KIND[self.kind])
+        self.port = self._attach(str(comm_info.get("addr", "*")), comm_info.get("port"))
+        if self.kind == "SUB":
+            self.socket.setsockopt(zmq.SUBSCRIBE, b"")
 
+    def _attach(self, addr, port):
+        """Server side (wildcard address): bind a free port and report it; client side: connect to addr:port."""
+        if "*" in addr:
+            return self.socket.bind_to_random_port("tcp://*", min_port=PORT_RANGE[0], max_port=PORT_RANGE[1], max_tries=100)
+        self.socket.connect("tcp://{}:{}".format(addr, port))
+        return None
+
+    # -- python objects ----------------------------------------------------------------------------------------------
     def send(self, ctr_info, data, name=None, block=True):
-        bufs = []
-        head = pickle.dumps((ctr_info, data), protocol=5, buffer_callback=bufs.append)
-        self.socket.send_multipart([head] + [b.raw() for b in bufs], copy=False)
+        frames = []
+        header = pickle.dumps((ctr_info, data), protocol=5, buffer_callback=frames.append)
+        self.socket.send_multipart([header] + [f.raw() for f in frames], copy=False)
 
     def recv(self, name=None, block=True):
-        msg = self.socket.recv_multipart(copy=False)
-        ctr_info, data = pickle.loads(msg[0].buffer, buffers=[m.buffer for m in msg[1:]])
-        return ctr_info, data
+        parts = self.socket.recv_multipart(copy=False)
+        return pickle.loads(parts[0].buffer, buffers=[p.buffer for p in parts[1:]])       # (ctr_info, data)
 
+    # -- raw buffers -------------------------------------------------------------------------------------------------
     def send_bytes(self, ctr_info, data):
         self.socket.send_multipart([ctr_info, data], copy=False)
 
     def recv_bytes(self, block=True):
-        recv_data = self.socket.recv_multipart()
-        return recv_data[0], recv_data[1]
+        head, body = self.socket.recv_multipart()[:2]
+        return head, body
 
     def __str__(self):
-        return str({"port": self.bound_port, "type": self._type})
+        return str({"port": self.port, "type": self.kind})
 
     def close(self):
-        if self.socket:
-            self.socket.close(linger=0)
-            self.socket = None
-        self._ctx.term()
+        sock, self.socket = self.socket, None
+        if sock is not None:
+            sock.close(linger=0)
+            self._ctx.term()
