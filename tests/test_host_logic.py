@@ -203,3 +203,17 @@ def test_algorithm_base_subclasses_the_reference_when_importable(tmp_path, repo_
     env = dict(os.environ, PYTHONPATH=repo_root)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=str(pkg))
     assert out.stdout.split() == ["False", "None", "True"], (out.stdout, out.stderr[-500:])
+
+
+def test_impala_lr_schedule_matches_linear_cosine_decay():
+    """ImpalaCnnOpt.scheduled_lr (host arithmetic of impala_cnn_opt.py:234-249) against the oracle's restatement of
+    tf.train.linear_cosine_decay, including the clamp beyond decay_steps."""
+    from xingtian_b200.model.impala import ImpalaCnnOpt
+
+    class Stub(object):
+        lr_schedule = [[0, 0.001], [20000, 0.000002]]
+
+    for step in (0, 1, 5000, 14000, 20000, 50000):
+        want = orc.linear_cosine_decay(0.001, step, 20000.0, beta=0.000002 / 20000.0)
+        assert abs(ImpalaCnnOpt.scheduled_lr(Stub(), step) - want) < 1e-15, step
+    assert ImpalaCnnOpt.scheduled_lr(Stub(), 0) > ImpalaCnnOpt.scheduled_lr(Stub(), 10000) > ImpalaCnnOpt.scheduled_lr(Stub(), 20000)
