@@ -19,8 +19,13 @@ executed too, over a numpy stand-in for the dozen TensorFlow ops it calls
 (``tf_losses.npz``): the STRUCTURE of those functions is pinned, the TF kernels
 behind the individual ops are not.  What still bottoms out in tensorflow alone
 (conv/dense layers, autodiff, ``AdamOptimizer``, ``clip_by_global_norm``,
-``tf.random.categorical``) is restated from TF-1.15's documented semantics:
-for those rows parity is UNPINNED and the restatement is the pin.
+``tf.random.categorical``, ``RMSPropOptimizer``, ``linear_cosine_decay``) is restated
+from TF-1.15's documented semantics: for those rows parity against TensorFlow itself
+is UNPINNED.  They are cross-checked independently instead (tests/test_oracle_f64.py):
+conv/dense/flatten/SAME padding against a numpy-only float64 direct convolution
+(oracle/np_f64.py, 1e-13), autograd against float64 finite differences, Adam /
+RMSProp / the schedule against closed forms.  ``precision("f64")`` runs this module in
+float64: the yardstick of the GPU parity tests.
 
 Each function cites the reference file:line it follows (paths relative to
 /root/reference).
