@@ -650,7 +650,8 @@ static cudaError_t tc_forward(xtb_net* net, int i, int B, bool want_f32, bool wa
   int nz = 1;
   a.kc_split = a.kchunks;
   if (tiles < kSMs && a.kchunks >= 32) {
-    int want = std::min((kSMs + tiles - 1) / tiles, a.kchunks / 8);
+    // as many K slices as fit in ONE wave of CTAs (rounding up instead left a few CTAs with two slices: twice the latency)
+    int want = std::min(kSMs / tiles, a.kchunks / 8);
     if (want > 1) {
       a.kc_split = ((a.kchunks + want - 1) / want + 7) / 8 * 8;     // whole 64-element stages per split
       nz = (a.kchunks + a.kc_split - 1) / a.kc_split;
