@@ -17,8 +17,10 @@
 //     taps: stride, padding (out-of-image taps are simply skipped) and the transposed convolution of the data
 //     gradient are all "which feature chunks does this stage read" -- no zero-filled operand tiles, no parity classes.
 //
-// Kernels (all persistent, warp specialised: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 =
-// epilogue, double-buffered TMEM accumulators, mbarrier full/empty rings):
+// Kernels (all persistent, one CTA per SM, warp specialised with replicated roles: 4 bulk-copy producer warps, each
+// owning the ring slots s == warp (mod 4); 4 MMA-issue warps, each owning one in-flight output tile with its own TMEM
+// accumulator and its own set of full barriers; 8 epilogue warps, two per TMEM lane quarter; every issue is done by one
+// elected lane with warp-uniform operands; stage / unit tables and the conv weight blobs live in shared memory):
 //   bp_rows_kernel<0>  forward     D[b, n]  = act(alpha * sum_k A[b, k] W[k, n] + bias)        conv / dense
 //   bp_rows_kernel<1>  forward, split-K partial sums (dense layers with a long K)
 //   bp_rows_kernel<2>  data grad   D[b, k]  = (sum_n G[b, n] W[k, n]) * act'(X[b, k])           conv / dense
