@@ -92,3 +92,60 @@ def test_batched_predictor_over_the_shared_memory_store():
     for i in range(5):
         assert got[i] == float(frames[i].sum())
     req.close(); rep.close()
+
+
+def _explorer(req, rep, explorer_id, frames, out_q):
+    from xingtian_b200.service.predictor import RemotePredict
+    stub = RemotePredict(req, rep, explorer_id=explorer_id, broker_id=0)
+    out_q.put((explorer_id, [float(stub.predict(f)) for f in frames]))
+
+
+def test_remote_predict_from_explorer_processes_over_shared_memory():
+    """f2 + f3 together on CPU: two explorer PROCESSES hold no model, send frames through the shared-memory store with
+    RemotePredict and block on their own reply channel; the predictor (stub model) answers batched; replies are routed by
+    explorer id the way the broker does it (xt/framework/broker.py:401-419)."""
+    from xingtian_b200.ipc import UniComm
+    from xingtian_b200.service.predictor import BatchedPredictor
+
+    class StubAlg(object):
+        class actor(object):
+            state_dim = (84, 84, 4)
+
+    sizes = []
+
+    def predict_fn(batch):
+        sizes.append(batch.shape[0])
+        return batch.reshape(batch.shape[0], -1).astype(np.float64).sum(1)
+
+    class Router(object):                      # reply side of the broker: one channel per explorer
+        def __init__(self, chans):
+            self.chans = chans
+
+        def send(self, msg):
+            self.chans[msg["ctr_info"]["explorer_id"]].send(msg)
+
+    req = UniComm("ShareByPlasma")
+    reps = {i: UniComm("ShareByPlasma") for i in (0, 1)}
+    pred = BatchedPredictor(0, StubAlg(), req, Router(reps), predict_fn=predict_fn, max_batch=16, max_wait_s=0.02, report_period=10 ** 9)
+    rng = np.random.default_rng(4)
+    frames = {i: [rng.integers(0, 256, (84, 84, 4), dtype=np.uint8) for _ in range(3)] for i in (0, 1)}
+    ctx = mp.get_context("fork")
+    out_q = ctx.Queue()
+    procs = [ctx.Process(target=_explorer, args=(req, reps[i], i, frames[i], out_q)) for i in (0, 1)]
+    for p in procs:
+        p.start()
+    answered = 0
+    import time
+    deadline = time.time() + 30
+    while answered < 6 and time.time() < deadline:
+        answered += pred.process_once(timeout=0.5)
+    got = dict(out_q.get(timeout=10) for _ in range(2))
+    for p in procs:
+        p.join(10)
+        assert p.exitcode == 0
+    assert answered == 6 and sum(sizes) == 6 and max(sizes) <= 2
+    for i in (0, 1):
+        assert got[i] == [float(f.astype(np.float64).sum()) for f in frames[i]]
+    req.close()
+    for c in reps.values():
+        c.close()

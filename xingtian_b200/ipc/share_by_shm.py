@@ -28,10 +28,22 @@ def _dumps(obj):
     return head, raws, sizes, total
 
 
+def _untrack(seg):
+    """multiprocessing's resource tracker unlinks every segment a process created (or, in 3.12, merely attached) when that
+    process exits -- here the creator is an explorer that may exit while its message is still waiting in the store, and
+    the segment's lifetime is managed explicitly (receiver unlinks / delete()).  Take the segment off the tracker's list."""
+    try:
+        from multiprocessing import resource_tracker
+        resource_tracker.unregister(seg._name, "shared_memory")
+    except Exception:          # tracker layout differs (3.13+: created with track=False instead)
+        pass
+
+
 def _put(obj):
     """Serialise `obj` into a fresh segment; returns its name (the object id)."""
     head, raws, sizes, total = _dumps(obj)
     seg = shared_memory.SharedMemory(create=True, size=max(total, 1))
+    _untrack(seg)
     mv = seg.buf
     _HDR.pack_into(mv, 0, len(head), len(sizes))
     off = _HDR.size
@@ -46,7 +58,9 @@ def _put(obj):
 
 
 def _get(name, unlink=True):
-    seg = shared_memory.SharedMemory(name=name)
+    seg = shared_memory.SharedMemory(name=name)         # 3.12 registers an attached segment too ...
+    if not unlink:
+        _untrack(seg)                                   # ... unlink() below takes it off again, otherwise do it here
     try:
         mv = seg.buf
         hlen, nb = _HDR.unpack_from(mv, 0)

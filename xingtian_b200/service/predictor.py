@@ -177,7 +177,11 @@ class RemotePredict(object):
         msg = make_msg(state, cmd="predict", sub_cmd="predict", explorer_id=self.explorer_id, broker_id=self.broker_id)
         (self.send_q.send if hasattr(self.send_q, "send") else self.send_q.put)(msg)
         reply = self.recv_q.recv() if hasattr(self.recv_q, "recv") else self.recv_q.get()
-        return reply["data"] if isinstance(reply, dict) and "ctr_info" in reply else reply
+        if isinstance(reply, dict) and "ctr_info" in reply:
+            return reply["data"]
+        if isinstance(reply, tuple) and len(reply) == 2 and isinstance(reply[0], dict):     # UniComm.recv(): (ctr_info, data)
+            return reply[1]
+        return reply
 
     def sync_weights(self, weights):
         msg = make_msg(weights, cmd="predict", sub_cmd="sync_weights", explorer_id=self.explorer_id, broker_id=self.broker_id)
